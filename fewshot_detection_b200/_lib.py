@@ -1,0 +1,87 @@
+"""ctypes binding of libfsdet.so (declared in include/fsdet.h).
+
+There is NO fallback: if the shared library is missing or a symbol cannot be
+resolved the import fails loudly.  `call(name, *args)` raises RuntimeError with
+`fsdet_last_error()` on a non-zero return code.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libfsdet.so')
+
+_P, _I, _F, _D, _Z, _Q = (ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_size_t,
+                          ctypes.c_longlong)
+_T = {'p': _P, 'i': _I, 'f': _F, 'd': _D, 'z': _Z, 'q': _Q}
+
+# name -> (argument codes, restype code)   [must match include/fsdet.h]
+SIGNATURES = {
+    'fsdet_version': ('', 'i'),
+    'fsdet_last_error': ('', 's'),
+    'fsdet_compiled_arch': ('', 'i'),
+    'fsdet_nchw_to_nhwc': ('pipipiiiip', 'i'),
+    'fsdet_nhwc_to_nchw': ('pippiiip', 'i'),
+    'fsdet_conv_fwd': ('pipppip iiiiiii p'.replace(' ', ''), 'i'),
+    'fsdet_conv_stat_rows': ('i', 'i'),
+    'fsdet_conv_wgrad': ('pipippz iiiiii p'.replace(' ', ''), 'i'),
+    'fsdet_conv_wgrad_workspace_floats': ('iiiiii', 'z'),
+    'fsdet_weight_flip_transpose': ('ppiiip', 'i'),
+    'fsdet_pad_channels': ('pipizp', 'i'),
+    'fsdet_bn_finalize': ('pidppppffppppiip', 'i'),
+    'fsdet_bn_act_fwd': ('pippfpipiiiiip', 'i'),
+    'fsdet_bn_act_bwd_reduce': ('pipipippppfpiiiiip', 'i'),
+    'fsdet_bn_bwd_rows': ('iii', 'i'),
+    'fsdet_bn_bwd_finalize': ('pidpppppiip', 'i'),
+    'fsdet_bn_act_bwd_apply': ('pipipipppppfpiiiiiip', 'i'),
+    'fsdet_maxpool_fwd': ('pipiiiiiip', 'i'),
+    'fsdet_maxpool_bwd': ('pipipiiiiiip', 'i'),
+    'fsdet_reorg_fwd': ('pipiiiiip', 'i'),
+    'fsdet_reorg_bwd': ('pipiiiiip', 'i'),
+    'fsdet_globalmax_fwd': ('pippiiip', 'i'),
+    'fsdet_globalmax_bwd': ('pppiiiip', 'i'),
+    'fsdet_copy_channels': ('pipiziip', 'i'),
+    'fsdet_head_weff': ('pppppiiiip', 'i'),
+    'fsdet_head_param_grads': ('pppppiiip', 'i'),
+    'fsdet_head_bias_grad': ('pippziip', 'i'),
+    'fsdet_head_bias_grad_workspace_floats': ('zii', 'z'),
+    'fsdet_region_decode': ('ppiiiiippp', 'i'),
+    'fsdet_build_targets': ('pppiiiiifffqppppppppppp', 'i'),
+    'fsdet_region_loss_grad': ('ppppp iiiiiiii ppppppppp ff ii p p'.replace(' ', ''), 'i'),
+    'fsdet_sgd_step': ('ppppppiiffffip', 'i'),
+    'fsdet_fill': ('pfzp', 'i'),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'libfsdet.so not found at %s. Build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            '(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU or PyTorch fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (args, res) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+        fn.argtypes = [_T[c] for c in args]
+        fn.restype = ctypes.c_char_p if res == 's' else _T[res]
+    return lib
+
+
+lib = _load()
+
+
+def last_error():
+    e = lib.fsdet_last_error()
+    return e.decode() if e else ''
+
+
+def call(name, *args):
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError('%s failed (rc=%d): %s' % (name, rc, last_error()))
+    return rc
+
+
+def ptr(t, offset_elems=0):
+    """Device pointer of a torch tensor (or None) plus an element offset."""
+    if t is None:
+        return None
+    return t.data_ptr() + offset_elems * t.element_size()

@@ -1,0 +1,402 @@
+// Train/eval BatchNorm2d + LeakyReLU(0.1) + MaxPool2d(2,2) fused passes over
+// NHWC fp32 activations (HBM-bound; float4 along channels, coalesced).
+//
+// Replaces nn.BatchNorm2d / nn.LeakyReLU / nn.MaxPool2d of the reference's conv
+// blocks (darknet_meta.py:240-268) and their autograd backward.
+//
+//   forward : conv kernel writes pre-BN z once (+ per-CTA sum / sum-of-squares)
+//             bn_finalize  -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale
+//             bn_act_fwd   -> y = leaky(z*scale+shift) [and/or its 2x2/2 max-pool]
+//   backward: bn_act_bwd_reduce -> sum(du), sum(du*xhat) partials (du = dy through pool+leaky)
+//             bn_bwd_finalize   -> dgamma, dbeta, c1 = dbeta/N, c2 = dgamma/N
+//             bn_act_bwd_apply  -> dz = scale*(du - c1 - xhat*c2)
+#include "common.cuh"
+
+namespace fsdet {
+
+// ------------------------------------------------------------ finalize (fwd)
+// grid: ceil(2C/32) blocks of 32x32 threads; column j<C: sum, j>=C: sum of squares
+__global__ void __launch_bounds__(1024) colsum_double_kernel(const float* __restrict__ part, int nparts, int ncols,
+                                                             double* __restrict__ out) {
+    __shared__ double red[32][33];
+    int col = blockIdx.x * 32 + threadIdx.x;
+    double s = 0.0;
+    if (col < ncols) {
+        int r = threadIdx.y;
+        for (; r + 96 < nparts; r += 128) {
+            float a = part[(long long)r * ncols + col];
+            float b = part[(long long)(r + 32) * ncols + col];
+            float c = part[(long long)(r + 64) * ncols + col];
+            float d = part[(long long)(r + 96) * ncols + col];
+            s += (double)a + (double)b + (double)c + (double)d;
+        }
+        for (; r < nparts; r += 32) s += (double)part[(long long)r * ncols + col];
+    }
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < ncols) {
+        double t = 0.0;
+        for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
+        out[col] = t;
+    }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum, float eps, float* __restrict__ mean,
+                                   float* __restrict__ invstd, float* __restrict__ scale, float* __restrict__ shift,
+                                   int C, int training) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float m, is;
+    if (training) {
+        double mu = sums[c] / count;
+        double var = sums[C + c] / count - mu * mu;
+        if (var < 0.0) var = 0.0;
+        m = (float)mu;
+        is = (float)(1.0 / sqrt(var + (double)eps));
+        if (running_mean) {
+            double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+        }
+    } else {
+        m = running_mean[c];
+        is = 1.f / sqrtf(running_var[c] + eps);
+    }
+    float g = gamma ? gamma[c] : 1.f;
+    float b = beta ? beta[c] : 0.f;
+    float sc = g * is;
+    if (mean) mean[c] = m;
+    if (invstd) invstd[c] = is;
+    scale[c] = sc;
+    shift[c] = b - m * sc;
+}
+
+// ------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(256) bn_act_flat_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, float slope,
+                                                          float* __restrict__ y, int ldy, long long npix, int C4) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long n = npix * C4;
+    if (i >= n) return;
+    long long p = i / C4;
+    int c = (int)(i - p * C4) * 4;
+    float4 v = ldg4(z + p * ldz + c);
+    float4 sc = ldg4(scale + c), sh = ldg4(shift + c);
+    v.x = leaky(fmaf(v.x, sc.x, sh.x), slope);
+    v.y = leaky(fmaf(v.y, sc.y, sh.y), slope);
+    v.z = leaky(fmaf(v.z, sc.z, sh.z), slope);
+    v.w = leaky(fmaf(v.w, sc.w, sh.w), slope);
+    *reinterpret_cast<float4*>(y + p * ldy + c) = v;
+}
+
+__device__ __forceinline__ float4 act4(float4 v, float4 sc, float4 sh, float slope) {
+    v.x = leaky(fmaf(v.x, sc.x, sh.x), slope);
+    v.y = leaky(fmaf(v.y, sc.y, sh.y), slope);
+    v.z = leaky(fmaf(v.z, sc.z, sh.z), slope);
+    v.w = leaky(fmaf(v.w, sc.w, sh.w), slope);
+    return v;
+}
+
+// one thread = one 2x2 window x 4 channels; windows cover ceil(H/2) x ceil(W/2)
+__global__ void __launch_bounds__(256) bn_act_pool_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, float slope,
+                                                          float* __restrict__ yf, int ldf, float* __restrict__ yp, int ldp,
+                                                          int B, int H, int W, int C4) {
+    const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long n = (long long)B * H2 * W2 * C4;
+    if (i >= n) return;
+    int c = (int)(i % C4) * 4;
+    long long wi = i / C4;
+    int w2 = (int)(wi % W2);
+    long long t = wi / W2;
+    int h2 = (int)(t % H2);
+    int b = (int)(t / H2);
+    float4 sc = ldg4(scale + c), sh = ldg4(shift + c);
+    float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            int h = h2 * 2 + dy, w = w2 * 2 + dx;
+            if (h < H && w < W) {
+                long long p = ((long long)b * H + h) * W + w;
+                float4 v = act4(ldg4(z + p * ldz + c), sc, sh, slope);
+                if (yf) *reinterpret_cast<float4*>(yf + p * ldf + c) = v;
+                mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+            }
+        }
+    if (yp && h2 < Hp && w2 < Wp) {
+        long long pp = ((long long)b * Hp + h2) * Wp + w2;
+        *reinterpret_cast<float4*>(yp + pp * ldp + c) = mx;
+    }
+}
+
+// ----------------------------------------------------------------- backward
+struct BwdArgs {
+    const float* z;
+    const float* dyf;
+    const float* dyp;
+    const float* scale;
+    const float* shift;
+    const float* mean;
+    const float* invstd;
+    const float* coef;
+    float* dz;
+    float* partial;
+    int ldz, ld_dyf, ld_dyp, lddz;
+    int B, H, W, C;
+    float slope;
+    int has_bn;
+};
+
+template <bool APPLY>
+__global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BwdArgs a) {
+    const int H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1, Hp = a.H >> 1, Wp = a.W >> 1;
+    const int C4 = a.C >> 2;
+    const int TC = blockDim.x;          // channel-vector lanes
+    const int cv = blockIdx.y * TC + threadIdx.x;
+    const bool cok = cv < C4;
+    const int c = cv * 4;
+    const long long nwin = (long long)a.B * H2 * W2;
+
+    float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0), mu = sh, is = sc, c1 = sh, c2 = sh;
+    if (cok) {
+        sc = ldg4(a.scale + c);
+        sh = ldg4(a.shift + c);
+        if (a.has_bn) { mu = ldg4(a.mean + c); is = ldg4(a.invstd + c); }
+        if (APPLY && a.has_bn) { c1 = ldg4(a.coef + c); c2 = ldg4(a.coef + a.C + c); }
+    }
+    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+
+    for (long long wi = (long long)blockIdx.x * blockDim.y + threadIdx.y; cok && wi < nwin;
+         wi += (long long)gridDim.x * blockDim.y) {
+        int w2 = (int)(wi % W2);
+        long long t = wi / W2;
+        int h2 = (int)(t % H2);
+        int b = (int)(t / H2);
+        float zv[4][4], yv[4][4];
+        long long pix[4];
+        bool ok[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int h = h2 * 2 + (q >> 1), w = w2 * 2 + (q & 1);
+            ok[q] = h < a.H && w < a.W;
+            pix[q] = ((long long)b * a.H + h) * a.W + w;
+            float4 v = ok[q] ? ldg4(a.z + pix[q] * a.ldz + c) : make_float4(0, 0, 0, 0);
+            zv[q][0] = v.x; zv[q][1] = v.y; zv[q][2] = v.z; zv[q][3] = v.w;
+        }
+        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+        const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+        float du[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { yv[q][k] = fmaf(zv[q][k], scv[k], shv[k]); du[q][k] = 0.f; }
+        if (a.dyf) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (ok[q]) {
+                    float4 g = ldg4(a.dyf + pix[q] * a.ld_dyf + c);
+                    du[q][0] = g.x; du[q][1] = g.y; du[q][2] = g.z; du[q][3] = g.w;
+                }
+        }
+        if (a.dyp && h2 < Hp && w2 < Wp) {
+            long long pp = ((long long)b * Hp + h2) * Wp + w2;
+            float4 g = ldg4(a.dyp + pp * a.ld_dyp + c);
+            const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // first maximum of the activated values in scan order (torch max_pool2d: strict >)
+                int best = 0;
+                float bv = leaky(yv[0][k], a.slope);
+#pragma unroll
+                for (int q = 1; q < 4; ++q) {
+                    float v = leaky(yv[q][k], a.slope);
+                    if (v > bv) { bv = v; best = q; }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q == best) du[q][k] += gv[k];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (!ok[q]) continue;
+            float o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float d = du[q][k] * (yv[q][k] > 0.f ? 1.f : a.slope);
+                float xh = (zv[q][k] - muv[k]) * isv[k];
+                if (APPLY) {
+                    o[k] = a.has_bn ? scv[k] * (d - (k == 0 ? c1.x : k == 1 ? c1.y : k == 2 ? c1.z : c1.w) -
+                                                xh * (k == 0 ? c2.x : k == 1 ? c2.y : k == 2 ? c2.z : c2.w))
+                                    : d;
+                } else {
+                    s1[k] += d;
+                    s2[k] += d * xh;
+                }
+            }
+            if (APPLY) *reinterpret_cast<float4*>(a.dz + pix[q] * a.lddz + c) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+
+    if (!APPLY) {
+        // reduce over threadIdx.y -> one partial row per blockIdx.x
+        extern __shared__ float red[];  // [blockDim.y][TC*8]
+        float* mine = red + ((size_t)threadIdx.y * TC + threadIdx.x) * 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { mine[k] = s1[k]; mine[4 + k] = s2[k]; }
+        __syncthreads();
+        if (threadIdx.y == 0 && cok) {
+            float t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
+            for (int r = 0; r < blockDim.y; ++r) {
+                const float* o = red + ((size_t)r * TC + threadIdx.x) * 8;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { t1[k] += o[k]; t2[k] += o[4 + k]; }
+            }
+            float* dst = a.partial + (long long)blockIdx.x * 2 * a.C;
+            *reinterpret_cast<float4*>(dst + c) = make_float4(t1[0], t1[1], t1[2], t1[3]);
+            *reinterpret_cast<float4*>(dst + a.C + c) = make_float4(t2[0], t2[1], t2[2], t2[3]);
+        }
+    }
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                       const float* __restrict__ invstd, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ coef, int C, int has_bn) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double sdu = sums[c], sdux = sums[C + c];
+    if (dbeta) dbeta[c] = (float)sdu;
+    if (has_bn) {
+        if (dgamma) dgamma[c] = (float)sdux;
+        coef[c] = (float)(sdu / count);
+        coef[C + c] = (float)(sdux / count);
+    }
+}
+
+static int bwd_rows(int B, int H, int W) {
+    long long nwin = (long long)B * ((H + 1) / 2) * ((W + 1) / 2);
+    long long r = (nwin + 63) / 64;
+    if (r > 8 * kNumSMs) r = 8 * kNumSMs;
+    if (r < 1) r = 1;
+    return (int)r;
+}
+
+}  // namespace fsdet
+
+using namespace fsdet;
+
+// The double-precision column sums (2*C doubles) are written behind the
+// partial rows: callers size the partial buffer with one extra "row pair"
+// (rows = fsdet_*_rows() + 2 gives 2*(2C) floats = 2C doubles).
+static inline double* sums_area(const float* partial, int nrows, int C) {
+    return reinterpret_cast<double*>(const_cast<float*>(partial) + (size_t)nrows * 2 * C);
+}
+
+extern "C" int fsdet_bn_bwd_rows(int B, int H, int W) { return bwd_rows(B, H, W); }
+
+extern "C" int fsdet_bn_finalize(const float* stat_partial, int nparts, double count, const float* gamma,
+                                 const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                                 float* mean, float* invstd, float* scale, float* shift, int C, int training,
+                                 void* stream) {
+    FSDET_CHECK_ARG(scale && shift && C > 0, "bn_finalize: bad args");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* sums = nullptr;
+    if (training) {
+        FSDET_CHECK_ARG(stat_partial && nparts > 0, "bn_finalize: training needs the conv partials");
+        FSDET_CHECK_ARG((((size_t)nparts * 2 * C) & 1) == 0, "bn_finalize: odd partial size");
+        sums = sums_area(stat_partial, nparts, C);
+        dim3 block(32, 32), grid(ceil_div(2 * C, 32));
+        colsum_double_kernel<<<grid, block, 0, s>>>(stat_partial, nparts, 2 * C, sums);
+        int st = launch_status("bn_finalize/colsum");
+        if (st) return st;
+    } else {
+        FSDET_CHECK_ARG(running_mean && running_var, "bn_finalize: eval needs running stats");
+    }
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(sums, count, gamma, beta, running_mean, running_var, momentum,
+                                                        eps, mean, invstd, scale, shift, C, training);
+    return launch_status("bn_finalize");
+}
+
+extern "C" int fsdet_bn_act_fwd(const float* z, int ldz, const float* scale, const float* shift, float slope,
+                                float* y_full, int ld_full, float* y_pool, int ld_pool, int B, int H, int W, int C,
+                                void* stream) {
+    FSDET_CHECK_ARG(z && scale && shift && (y_full || y_pool), "bn_act_fwd: null pointer");
+    FSDET_CHECK_ARG(C % 4 == 0 && ldz % 4 == 0 && (!y_full || ld_full % 4 == 0) && (!y_pool || ld_pool % 4 == 0),
+                    "bn_act_fwd: C=%d and leading dims must be multiples of 4", C);
+    cudaStream_t s = (cudaStream_t)stream;
+    int C4 = C / 4;
+    if (!y_pool) {
+        long long n = (long long)B * H * W * C4;
+        if (n == 0) return 0;
+        bn_act_flat_kernel<<<ceil_div(n, 256), 256, 0, s>>>(z, ldz, scale, shift, slope, y_full, ld_full,
+                                                            (long long)B * H * W, C4);
+    } else {
+        long long n = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * C4;
+        if (n == 0) return 0;
+        bn_act_pool_kernel<<<ceil_div(n, 256), 256, 0, s>>>(z, ldz, scale, shift, slope, y_full, ld_full, y_pool,
+                                                            ld_pool, B, H, W, C4);
+    }
+    return launch_status("bn_act_fwd");
+}
+
+static int launch_bwd(bool apply, const BwdArgs& a, cudaStream_t s) {
+    int C4 = a.C / 4;
+    int TC = C4 >= 32 ? 32 : (C4 >= 16 ? 16 : (C4 >= 8 ? 8 : (C4 >= 4 ? 4 : (C4 >= 2 ? 2 : 1))));
+    int TY = 256 / TC;
+    dim3 block(TC, TY), grid(bwd_rows(a.B, a.H, a.W), ceil_div(C4, TC));
+    if (apply) {
+        bn_act_bwd_kernel<true><<<grid, block, 0, s>>>(a);
+    } else {
+        size_t smem = (size_t)TY * TC * 8 * sizeof(float);  // 8 KB
+        bn_act_bwd_kernel<false><<<grid, block, smem, s>>>(a);
+    }
+    return launch_status(apply ? "bn_act_bwd_apply" : "bn_act_bwd_reduce");
+}
+
+extern "C" int fsdet_bn_act_bwd_reduce(const float* z, int ldz, const float* dy_full, int ld_dyf, const float* dy_pool,
+                                       int ld_dyp, const float* scale, const float* shift, const float* mean,
+                                       const float* invstd, float slope, float* partial, int B, int H, int W, int C,
+                                       int has_bn, void* stream) {
+    FSDET_CHECK_ARG(z && scale && shift && partial && (dy_full || dy_pool), "bn_act_bwd_reduce: null pointer");
+    FSDET_CHECK_ARG(!has_bn || (mean && invstd), "bn_act_bwd_reduce: BN needs mean/invstd");
+    FSDET_CHECK_ARG(C % 4 == 0 && ldz % 4 == 0 && ld_dyf % 4 == 0 && ld_dyp % 4 == 0, "bn_act_bwd_reduce: alignment");
+    BwdArgs a;
+    a.z = z; a.dyf = dy_full; a.dyp = dy_pool; a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd;
+    a.coef = nullptr; a.dz = nullptr; a.partial = partial; a.ldz = ldz; a.ld_dyf = ld_dyf; a.ld_dyp = ld_dyp; a.lddz = 0;
+    a.B = B; a.H = H; a.W = W; a.C = C; a.slope = slope; a.has_bn = has_bn;
+    return launch_bwd(false, a, (cudaStream_t)stream);
+}
+
+extern "C" int fsdet_bn_bwd_finalize(const float* partial, int nparts, double count, const float* gamma,
+                                     const float* invstd, float* dgamma, float* dbeta, float* coef, int C, int has_bn,
+                                     void* stream) {
+    FSDET_CHECK_ARG(partial && nparts > 0 && C > 0 && (!has_bn || coef), "bn_bwd_finalize: bad args");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* sums = sums_area(partial, nparts, C);
+    dim3 block(32, 32), grid(ceil_div(2 * C, 32));
+    colsum_double_kernel<<<grid, block, 0, s>>>(partial, nparts, 2 * C, sums);
+    int st = launch_status("bn_bwd_finalize/colsum");
+    if (st) return st;
+    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(sums, count, gamma, invstd, dgamma, dbeta, coef, C, has_bn);
+    return launch_status("bn_bwd_finalize");
+}
+
+extern "C" int fsdet_bn_act_bwd_apply(const float* z, int ldz, const float* dy_full, int ld_dyf, const float* dy_pool,
+                                      int ld_dyp, const float* scale, const float* shift, const float* mean,
+                                      const float* invstd, const float* coef, float slope, float* dz, int lddz, int B,
+                                      int H, int W, int C, int has_bn, void* stream) {
+    FSDET_CHECK_ARG(z && scale && shift && dz && (dy_full || dy_pool), "bn_act_bwd_apply: null pointer");
+    FSDET_CHECK_ARG(!has_bn || (mean && invstd && coef), "bn_act_bwd_apply: BN needs mean/invstd/coef");
+    FSDET_CHECK_ARG(C % 4 == 0 && ldz % 4 == 0 && ld_dyf % 4 == 0 && ld_dyp % 4 == 0 && lddz % 4 == 0,
+                    "bn_act_bwd_apply: alignment");
+    BwdArgs a;
+    a.z = z; a.dyf = dy_full; a.dyp = dy_pool; a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd;
+    a.coef = coef; a.dz = dz; a.partial = nullptr; a.ldz = ldz; a.ld_dyf = ld_dyf; a.ld_dyp = ld_dyp; a.lddz = lddz;
+    a.B = B; a.H = H; a.W = W; a.C = C; a.slope = slope; a.has_bn = has_bn;
+    return launch_bwd(true, a, (cudaStream_t)stream);
+}

@@ -1,0 +1,707 @@
+"""Host-side executor of the cfg-driven networks on libfsdet.so.
+
+The reference interprets its block list with one torch module per block
+(darknet_meta.py:130-195, darknet.py:80-129) and lets autograd + cuDNN do the
+rest.  Here the same block list is walked, but every block launches hand-written
+sm_100a kernels through the C ABI (include/fsdet.h) on NHWC fp32 buffers, and a
+small tape replays the blocks in reverse for the backward pass.
+
+Memory comes from torch's caching allocator (`torch.empty`): torch is used for
+device memory, streams and autograd plumbing only -- no torch compute op runs on
+the hot path.
+"""
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+LEAKY_SLOPE = 0.1
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _empty(*shape, dtype=torch.float32, device=None):
+    return torch.empty(*shape, dtype=dtype, device=device)
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class Act(object):
+    """A view [B*H*W pixels] x [C channels at column `off`] of a 2-D NHWC buffer."""
+    __slots__ = ('buf', 'off', 'C', 'B', 'H', 'W', 'g', 'needs_grad', 'parent')
+
+    def __init__(self, buf, off, C, B, H, W, needs_grad=True, parent=None):
+        self.buf, self.off, self.C, self.B, self.H, self.W = buf, off, C, B, H, W
+        self.g = None            # gradient Act (same geometry) once some consumer wrote it
+        self.needs_grad = needs_grad
+        self.parent = parent     # concat buffer this view is a slice of
+
+    @property
+    def ld(self):
+        return self.buf.shape[1]
+
+    @property
+    def npix(self):
+        return self.B * self.H * self.W
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + 4 * self.off
+
+    @staticmethod
+    def new(B, H, W, C, device, needs_grad=True):
+        return Act(_empty(B * H * W, C, device=device), 0, C, B, H, W, needs_grad)
+
+    def slice(self, off, C):
+        return Act(self.buf, self.off + off, C, self.B, self.H, self.W, self.needs_grad, parent=(self, off))
+
+    def grad_for_write(self):
+        """Returns (grad Act, accumulate flag) for a consumer about to write its
+        contribution to d(loss)/d(this activation)."""
+        if self.g is not None:
+            return self.g, 1
+        if self.parent is not None:
+            par, off = self.parent
+            if par.g is None:
+                raise NotImplementedError('gradient of a concat slice written before the concat buffer')
+            self.g = par.g.slice(off, self.C)
+            return self.g, 1
+        self.g = Act.new(self.B, self.H, self.W, self.C, self.buf.device, needs_grad=False)
+        return self.g, 0
+
+    def grad_for_read(self):
+        if self.g is None and self.parent is not None:
+            par, off = self.parent
+            if par.g is not None:
+                self.g = par.g.slice(off, self.C)
+        return self.g
+
+
+# ----------------------------------------------------------------- plan
+class Spec(object):
+    def __init__(self, kind, idx, **kw):
+        self.kind = kind
+        self.idx = idx
+        self.__dict__.update(kw)
+
+
+def is_dynamic(block):
+    return 'dynamic' in block and int(block['dynamic']) == 1
+
+
+def compile_blocks(blocks):
+    """Block list -> list of Spec (one per module index, the reference's `ind`).
+
+    Fusions decided here:
+      * conv(+BN+leaky) followed by maxpool 2/2: the pool is computed in the
+        conv block's activation pass; the full-resolution activation is only
+        materialised if a route refers to the conv.
+      * dynamic conv followed by a linear 1x1 conv: one GEMM with per-class
+        effective weights (the [B*n_cls,1024,G,G] tensor is never built).
+      * two-layer routes: producers write straight into slices of one buffer.
+    """
+    specs = []
+    in_ch = 3
+    out_ch = []
+    ind = -1
+    body = []
+    for block in blocks:
+        t = block['type']
+        if t in ('net', 'learnet'):
+            in_ch = int(block['channels'])
+            continue
+        body.append(block)
+    prev = in_ch
+    for block in body:
+        ind += 1
+        t = block['type']
+        if t == 'convolutional':
+            filters = int(block['filters'])
+            k = int(block['size'])
+            if int(block['stride']) != 1:
+                raise NotImplementedError('convolutional stride %s' % block['stride'])
+            if k not in (1, 3) or not int(block['pad']) and k != 1:
+                raise NotImplementedError('convolutional size=%d pad=%s' % (k, block['pad']))
+            act = block['activation']
+            if act not in ('leaky', 'linear'):
+                raise NotImplementedError('activation %s' % act)
+            specs.append(Spec('conv', ind, cin=prev, cout=filters, k=k, bn=int(block['batch_normalize']),
+                              slope=LEAKY_SLOPE if act == 'leaky' else 1.0, dynamic=is_dynamic(block),
+                              fuse_pool=False, head=False))
+            prev = filters
+        elif t == 'maxpool':
+            size, stride = int(block['size']), int(block['stride'])
+            if size != 2 or stride not in (1, 2):
+                raise NotImplementedError('maxpool size=%d stride=%d' % (size, stride))
+            specs.append(Spec('maxpool', ind, stride=stride, fused=False))
+        elif t == 'reorg':
+            s = int(block['stride'])
+            if s != 2:
+                raise NotImplementedError('reorg stride %d' % s)
+            specs.append(Spec('reorg', ind))
+            prev = 4 * prev
+        elif t == 'route':
+            layers = [int(i) for i in block['layers'].split(',')]
+            layers = [i if i > 0 else i + ind for i in layers]
+            if len(layers) == 1:
+                prev = out_ch[layers[0]]
+            elif len(layers) == 2:
+                if 'concat' in block and int(block['concat']) == 0:
+                    raise NotImplementedError('route concat=0')
+                prev = out_ch[layers[0]] + out_ch[layers[1]]
+            else:
+                raise NotImplementedError('route with %d layers' % len(layers))
+            specs.append(Spec('route', ind, layers=layers))
+        elif t == 'globalmax':
+            specs.append(Spec('globalmax', ind))
+        elif t in ('region', 'cost'):
+            specs.append(Spec('skip', ind))
+        else:
+            raise NotImplementedError('block type %s' % t)
+        out_ch.append(prev)
+    # ---- fusion passes
+    routed = set()
+    for s in specs:
+        if s.kind == 'route':
+            routed.update(s.layers)
+    for i, s in enumerate(specs):
+        nxt = specs[i + 1] if i + 1 < len(specs) else None
+        if s.kind == 'conv' and not s.dynamic and nxt is not None and nxt.kind == 'maxpool' and nxt.stride == 2:
+            s.fuse_pool = True
+            s.keep_full = s.idx in routed
+            nxt.fused = True
+        if s.kind == 'conv' and s.dynamic:
+            ok = (nxt is not None and nxt.kind == 'conv' and not nxt.dynamic and nxt.k == 1 and not nxt.bn and
+                  nxt.slope == 1.0 and s.k == 1 and not s.bn and s.slope == 1.0)
+            if not ok:
+                raise NotImplementedError('dynamic conv must be 1x1/linear and followed by a linear 1x1 conv')
+            s.kind = 'dyn'
+            nxt.head = True
+    # ---- zero-copy concat planning: producer idx -> (route idx, channel offset)
+    placement = {}
+    for s in specs:
+        if s.kind == 'route' and len(s.layers) == 2:
+            off = 0
+            ok = all(l not in placement and specs[l].kind in ('conv', 'reorg', 'maxpool') for l in s.layers) \
+                and s.layers[0] != s.layers[1]
+            for l in s.layers:
+                if ok:
+                    placement[l] = (s.idx, off)
+                off += out_ch[l]
+            s.zero_copy = ok
+            s.total = off
+    return specs, out_ch, placement, in_ch
+
+
+# ------------------------------------------------------------- executor
+class Tape(object):
+    def __init__(self):
+        self.records = []
+
+
+class NetRunner(object):
+    """Executes one cfg network (detector or support net) for a Darknet module."""
+
+    def __init__(self, blocks, models):
+        self.blocks = blocks
+        self.models = models  # nn.ModuleList aligned with spec.idx
+        self.specs, self.out_ch, self.placement, self.in_ch = compile_blocks(blocks)
+        self.in_cpad = _round_up(self.in_ch, 4)
+
+    # -- helpers ---------------------------------------------------------
+    @staticmethod
+    def _conv_modules(seq):
+        conv = bn = None
+        for m in seq.children():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                bn = m
+            elif hasattr(m, 'weight') or getattr(m, 'is_dynamic_conv', False):
+                if conv is None:
+                    conv = m
+        return conv, bn
+
+    @staticmethod
+    def _ohwi(w):
+        """Physical OHWI view of a conv weight Parameter (converted in place once)."""
+        if w.dim() == 4 and not w.is_contiguous(memory_format=torch.channels_last):
+            w.data = w.data.contiguous(memory_format=torch.channels_last)
+        return w
+
+    @staticmethod
+    def _param_grad(p):
+        """Returns (tensor to write the gradient into, finish callback)."""
+        if p.grad is None:
+            p.grad = torch.empty_like(p)  # preserve_format: same (OHWI) strides as p
+            return p.grad, None
+        if p.grad.stride() != p.stride():
+            p.grad = p.grad.contiguous(memory_format=torch.channels_last if p.dim() == 4 else torch.contiguous_format)
+        tmp = torch.empty_like(p)
+        return tmp, (lambda: p.grad.add_(tmp))
+
+    # -- forward -----------------------------------------------------------
+    def forward(self, inputs, extra=None, training=True, record=True):
+        """inputs: list of NCHW tensors concatenated along channels (image[, mask]).
+        extra: reweighting vectors [n_cls, K(,1,1)] for a dynamic head.
+        Returns (output tensor, tape)."""
+        x0 = inputs[0]
+        dev = x0.device
+        B, _, H, W = x0.shape
+        st = _stream()
+        tape = Tape() if record else None
+        c0 = x0.shape[1]
+        c1 = inputs[1].shape[1] if len(inputs) > 1 else 0
+        if c0 + c1 != self.in_ch:
+            raise ValueError('network expects %d input channels, got %d' % (self.in_ch, c0 + c1))
+        for t in inputs:
+            if t.dtype != torch.float32 or not t.is_cuda:
+                raise TypeError('inputs must be float32 CUDA tensors (no CPU fallback)')
+        xin = Act.new(B, H, W, self.in_cpad, dev, needs_grad=False)
+        call('fsdet_nchw_to_nhwc', ptr(inputs[0].contiguous()), c0,
+             ptr(inputs[1].contiguous()) if c1 else None, c1, xin.ptr, xin.ld, self.in_cpad, B, H * W, st)
+        outputs = {}
+        cat_bufs = {}
+        cur = xin
+        result = None
+        specs = self.specs
+        i = 0
+
+        def out_act(idx, B_, H_, W_, C_):
+            """Allocate (or place into a concat buffer) the output of module idx."""
+            if idx in self.placement:
+                ridx, off = self.placement[idx]
+                rs = specs[ridx]
+                if ridx not in cat_bufs:
+                    cat_bufs[ridx] = Act.new(B_, H_, W_, rs.total, dev)
+                return cat_bufs[ridx].slice(off, C_)
+            return Act.new(B_, H_, W_, C_, dev)
+
+        while i < len(specs):
+            s = specs[i]
+            if s.kind == 'conv' and not s.head:
+                cur, rec = self._conv_fwd(s, cur, training, out_act, st)
+                if s.fuse_pool:
+                    full, pooled = cur
+                    outputs[s.idx] = full
+                    outputs[s.idx + 1] = pooled
+                    cur = pooled
+                    i += 1  # the fused maxpool spec
+                else:
+                    outputs[s.idx] = cur
+                if tape is not None:
+                    tape.records.append(rec)
+            elif s.kind == 'dyn':
+                head = specs[i + 1]
+                result, rec = self._head_fwd(s, head, cur, extra, st)
+                if tape is not None:
+                    tape.records.append(rec)
+                outputs[s.idx] = None
+                outputs[head.idx] = None
+                cur = None
+                i += 1
+            elif s.kind == 'maxpool':
+                Ho, Wo = (cur.H // 2, cur.W // 2) if s.stride == 2 else (cur.H, cur.W)
+                y = out_act(s.idx, cur.B, Ho, Wo, cur.C)
+                call('fsdet_maxpool_fwd', cur.ptr, cur.ld, y.ptr, y.ld, cur.B, cur.H, cur.W, cur.C, s.stride, st)
+                if tape is not None:
+                    tape.records.append(('maxpool', s, cur, y))
+                cur = y
+                outputs[s.idx] = cur
+            elif s.kind == 'reorg':
+                y = out_act(s.idx, cur.B, cur.H // 2, cur.W // 2, cur.C * 4)
+                call('fsdet_reorg_fwd', cur.ptr, cur.ld, y.ptr, y.ld, cur.B, cur.H, cur.W, cur.C, st)
+                if tape is not None:
+                    tape.records.append(('reorg', s, cur, y))
+                cur = y
+                outputs[s.idx] = cur
+            elif s.kind == 'route':
+                if len(s.layers) == 1:
+                    cur = outputs[s.layers[0]]
+                    if cur is None:
+                        raise NotImplementedError('route to a fused-away layer %d' % s.layers[0])
+                else:
+                    a0, a1 = outputs[s.layers[0]], outputs[s.layers[1]]
+                    if a0 is None or a1 is None:
+                        raise NotImplementedError('route to a fused-away layer')
+                    if s.zero_copy:
+                        cur = cat_bufs[s.idx]
+                    else:
+                        if (a0.B, a0.H, a0.W) != (a1.B, a1.H, a1.W):
+                            raise NotImplementedError('route of different geometries (maybe_repeat)')
+                        cur = Act.new(a0.B, a0.H, a0.W, a0.C + a1.C, dev)
+                        call('fsdet_copy_channels', a0.ptr, a0.ld, cur.ptr, cur.ld, a0.npix, a0.C, 0, st)
+                        call('fsdet_copy_channels', a1.ptr, a1.ld, cur.ptr + 4 * a0.C, cur.ld, a1.npix, a1.C, 0, st)
+                        if tape is not None:
+                            tape.records.append(('cat', s, a0, a1, cur))
+                outputs[s.idx] = cur
+            elif s.kind == 'globalmax':
+                if cur.H != cur.W:
+                    raise NotImplementedError('GlobalMaxPool2d uses kernel = W; non-square maps unsupported')
+                y = _empty(cur.B, cur.C, device=dev)
+                arg = _empty(cur.B, cur.C, dtype=torch.int32, device=dev)
+                call('fsdet_globalmax_fwd', cur.ptr, cur.ld, ptr(y), ptr(arg), cur.B, cur.H * cur.W, cur.C, st)
+                if tape is not None:
+                    tape.records.append(('globalmax', s, cur, arg))
+                result = y.view(cur.B, cur.C, 1, 1)
+                cur = None
+                outputs[s.idx] = None
+            elif s.kind == 'skip':
+                pass
+            else:
+                raise NotImplementedError(s.kind)
+            i += 1
+        if result is None:
+            # network ends in an ordinary activation: hand it back as NCHW
+            if cur is None:
+                raise RuntimeError('network produced no output')
+            c_true = self.out_ch[[sp.idx for sp in specs if sp.kind != 'skip'][-1]]
+            result = _empty(cur.B, c_true, cur.H, cur.W, device=dev)
+            call('fsdet_nhwc_to_nchw', cur.ptr, cur.ld, None, ptr(result), cur.B, c_true, cur.H * cur.W, st)
+            if tape is not None:
+                tape.records.append(('output', cur, c_true))
+        return result, tape
+
+    def _conv_fwd(self, s, x, training, out_act, st):
+        seq = self.models[s.idx]
+        conv, bn = self._conv_modules(seq)
+        dev = x.buf.device
+        B, H, W = x.B, x.H, x.W
+        npix = x.npix
+        w = self._ohwi(conv.weight)
+        kk = s.k * s.k
+        cin_p = x.C  # activation channel count (input padded to a multiple of 4)
+        if cin_p != s.cin:
+            wuse = _empty(s.cout, kk, cin_p, device=dev)
+            call('fsdet_pad_channels', ptr(w), s.cin, ptr(wuse), cin_p, s.cout * kk, st)
+        else:
+            wuse = w
+        cout_p = _round_up(s.cout, 4)
+        if bn is not None:
+            assert cout_p == s.cout, 'BatchNorm conv with Cout % 4 != 0 is unsupported'
+            z = Act.new(B, H, W, s.cout, dev)
+            use_batch_stats = training or not bn.track_running_stats
+            rows = _lib.lib.fsdet_conv_stat_rows(npix)
+            stat = _empty(rows + 2, 2 * s.cout, device=dev) if use_batch_stats else None
+            call('fsdet_conv_fwd', x.ptr, x.ld, ptr(wuse), None, z.ptr, z.ld, ptr(stat), B, H, W, cin_p, s.cout, s.k, 0, st)
+            vec = _empty(4, s.cout, device=dev)  # mean, invstd, scale, shift
+            upd = training and bn.track_running_stats
+            call('fsdet_bn_finalize', ptr(stat), rows, float(npix), ptr(bn.weight), ptr(bn.bias),
+                 ptr(bn.running_mean) if (upd or not use_batch_stats) else None,
+                 ptr(bn.running_var) if (upd or not use_batch_stats) else None,
+                 BN_MOMENTUM if bn.momentum is None else float(bn.momentum), float(bn.eps),
+                 ptr(vec[0]), ptr(vec[1]), ptr(vec[2]), ptr(vec[3]), s.cout, 1 if use_batch_stats else 0, st)
+            if upd and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+            full = pooled = None
+            if s.fuse_pool:
+                pooled = out_act(s.idx + 1, B, H // 2, W // 2, s.cout)
+                if s.keep_full:
+                    full = out_act(s.idx, B, H, W, s.cout)
+            else:
+                full = out_act(s.idx, B, H, W, s.cout)
+            call('fsdet_bn_act_fwd', z.ptr, z.ld, ptr(vec[2]), ptr(vec[3]), s.slope,
+                 full.ptr if full else None, full.ld if full else 0, pooled.ptr if pooled else None,
+                 pooled.ld if pooled else 0, B, H, W, s.cout, st)
+            rec = ('convbn', s, x, wuse, z, vec, full, pooled, conv, bn)
+            return ((full, pooled) if s.fuse_pool else full), rec
+        # conv + bias (+ leaky), no BN
+        if cout_p != s.cout:
+            wp = torch.zeros(cout_p, kk, cin_p, device=dev)
+            wp[:s.cout].copy_(wuse.detach().reshape(s.cout, kk, cin_p) if wuse is not w else
+                              w.detach().permute(0, 2, 3, 1).reshape(s.cout, kk, cin_p))
+            bp = torch.zeros(cout_p, device=dev)
+            if conv.bias is not None:
+                bp[:s.cout].copy_(conv.bias.detach())
+        else:
+            wp = wuse
+            bp = conv.bias
+        z = Act.new(B, H, W, cout_p, dev)
+        call('fsdet_conv_fwd', x.ptr, x.ld, ptr(wp), ptr(bp), z.ptr, z.ld, None, B, H, W, cin_p, cout_p, s.k, 0, st)
+        ones = zeros = None
+        if s.slope != 1.0:
+            ones = torch.ones(cout_p, device=dev)
+            zeros = torch.zeros(cout_p, device=dev)
+        full = pooled = None
+        if s.fuse_pool or s.slope != 1.0:
+            if ones is None:
+                ones = torch.ones(cout_p, device=dev)
+                zeros = torch.zeros(cout_p, device=dev)
+            if s.fuse_pool:
+                pooled = out_act(s.idx + 1, B, H // 2, W // 2, cout_p)
+                if s.keep_full:
+                    full = out_act(s.idx, B, H, W, cout_p)
+            else:
+                full = out_act(s.idx, B, H, W, cout_p)
+            call('fsdet_bn_act_fwd', z.ptr, z.ld, ptr(ones), ptr(zeros), s.slope, full.ptr if full else None,
+                 full.ld if full else 0, pooled.ptr if pooled else None, pooled.ld if pooled else 0, B, H, W, cout_p, st)
+        else:
+            full = z  # linear: the conv output is the block output
+        rec = ('convbias', s, x, wp, z, (ones, zeros), full, pooled, conv, cout_p)
+        return ((full, pooled) if s.fuse_pool else full), rec
+
+    def _head_fwd(self, s, head, x, rw, st):
+        """dynamic_conv.DynamicConv2d.forward (dynamic_conv.py:125-164) + the
+        following nn.Conv2d(K, O, 1): out[b*n_cls+c] = (W (.) rw[c]) x[b] + bias."""
+        if rw is None:
+            raise ValueError('this network has a dynamic convolution: dynamic weights are required')
+        dev = x.buf.device
+        conv, _ = self._conv_modules(self.models[head.idx])
+        K = x.C
+        n_cls = rw.shape[0]
+        if rw.numel() != n_cls * K:
+            raise ValueError('dynamic weights must be [n_cls, %d, 1, 1], got %s' % (K, tuple(rw.shape)))
+        rw2 = rw.detach().reshape(n_cls, K).contiguous()
+        O = head.cout
+        N = n_cls * O
+        Npad = _round_up(N, 32)
+        W = conv.weight  # [O, K, 1, 1]: OIHW == OHWI storage for 1x1
+        weff = _empty(Npad, K, device=dev)
+        beff = _empty(Npad, device=dev)
+        call('fsdet_head_weff', ptr(W), ptr(conv.bias), ptr(rw2), ptr(weff), ptr(beff), n_cls, O, K, Npad, st)
+        z = Act.new(x.B, x.H, x.W, Npad, dev)
+        call('fsdet_conv_fwd', x.ptr, x.ld, ptr(weff), ptr(beff), z.ptr, z.ld, None, x.B, x.H, x.W, K, Npad, 1, 0, st)
+        out = _empty(x.B * n_cls, O, x.H, x.W, device=dev)
+        call('fsdet_nhwc_to_nchw', z.ptr, z.ld, None, ptr(out), x.B, N, x.H * x.W, st)
+        rec = ('head', s, head, x, rw2, weff, conv, n_cls, O, Npad)
+        return out, rec
+
+    # -- backward ----------------------------------------------------------
+    def backward(self, tape, gout):
+        """Replays the tape in reverse. gout: gradient of the NCHW result.
+        Parameter gradients are written into `.grad` directly. Returns the
+        gradient w.r.t. the dynamic weights (or None)."""
+        st = _stream()
+        gout = gout.contiguous()
+        drw = None
+        for rec in reversed(tape.records):
+            kind = rec[0]
+            if kind == 'head':
+                drw = self._head_bwd(rec, gout, st)
+            elif kind == 'output':
+                _, act, c_true = rec
+                g, acc = act.grad_for_write()
+                if acc:
+                    raise NotImplementedError('network output consumed elsewhere')
+                call('fsdet_nchw_to_nhwc', ptr(gout), c_true, None, 0, g.ptr, g.ld, g.C, act.B, act.H * act.W, st)
+            elif kind == 'globalmax':
+                _, s, x, arg = rec
+                g, acc = x.grad_for_write()
+                tgt = g if not acc else Act.new(x.B, x.H, x.W, x.C, x.buf.device, False)
+                gy = gout.reshape(x.B, x.C)
+                call('fsdet_globalmax_bwd', ptr(gy), ptr(arg), tgt.ptr, tgt.ld, x.B, x.H * x.W, x.C, st)
+                if acc:
+                    call('fsdet_copy_channels', tgt.ptr, tgt.ld, g.ptr, g.ld, x.npix, x.C, 1, st)
+            elif kind == 'convbn':
+                self._convbn_bwd(rec, st)
+            elif kind == 'convbias':
+                self._convbias_bwd(rec, st)
+            elif kind == 'maxpool':
+                _, s, x, y = rec
+                gy = y.grad_for_read()
+                if gy is None or not x.needs_grad:
+                    continue
+                g, acc = x.grad_for_write()
+                tgt = g if not acc else Act.new(x.B, x.H, x.W, x.C, x.buf.device, False)
+                call('fsdet_maxpool_bwd', x.ptr, x.ld, gy.ptr, gy.ld, tgt.ptr, tgt.ld, x.B, x.H, x.W, x.C, s.stride, st)
+                if acc:
+                    call('fsdet_copy_channels', tgt.ptr, tgt.ld, g.ptr, g.ld, x.npix, x.C, 1, st)
+            elif kind == 'reorg':
+                _, s, x, y = rec
+                gy = y.grad_for_read()
+                if gy is None or not x.needs_grad:
+                    continue
+                g, acc = x.grad_for_write()
+                tgt = g if not acc else Act.new(x.B, x.H, x.W, x.C, x.buf.device, False)
+                call('fsdet_reorg_bwd', gy.ptr, gy.ld, tgt.ptr, tgt.ld, x.B, x.H, x.W, x.C, st)
+                if acc:
+                    call('fsdet_copy_channels', tgt.ptr, tgt.ld, g.ptr, g.ld, x.npix, x.C, 1, st)
+            elif kind == 'cat':
+                _, s, a0, a1, cat = rec
+                gc = cat.grad_for_read()
+                if gc is None:
+                    continue
+                off = 0
+                for a in (a0, a1):
+                    if a.needs_grad:
+                        g, acc = a.grad_for_write()
+                        call('fsdet_copy_channels', gc.ptr + 4 * off, gc.ld, g.ptr, g.ld, a.npix, a.C, acc, st)
+                    off += a.C
+            else:
+                raise NotImplementedError(kind)
+        return drw
+
+    def _dgrad(self, x, dz, w_ohwi, cin_p, cout, k, st):
+        """dX = conv(dZ, flip-transposed W) accumulated into x's gradient."""
+        if not x.needs_grad:
+            return
+        dev = x.buf.device
+        kk = k * k
+        wt = _empty(cin_p, kk, cout, device=dev)
+        call('fsdet_weight_flip_transpose', ptr(w_ohwi), ptr(wt), cout, kk, cin_p, st)
+        g, acc = x.grad_for_write()
+        call('fsdet_conv_fwd', dz.ptr, dz.ld, ptr(wt), None, g.ptr, g.ld, None, x.B, x.H, x.W, cout, cin_p, k, acc, st)
+
+    def _wgrad(self, x, dz, out_tensor, cin_p, cout, k, st):
+        dev = x.buf.device
+        nws = _lib.lib.fsdet_conv_wgrad_workspace_floats(x.B, x.H, x.W, cin_p, cout, k)
+        ws = _empty(max(nws, 4), device=dev)
+        call('fsdet_conv_wgrad', x.ptr, x.ld, dz.ptr, dz.ld, ptr(out_tensor), ptr(ws), nws, x.B, x.H, x.W, cin_p, cout, k, st)
+
+    def _convbn_bwd(self, rec, st):
+        _, s, x, wuse, z, vec, full, pooled, conv, bn = rec
+        dev = x.buf.device
+        B, H, W = x.B, x.H, x.W
+        gf = full.grad_for_read() if full is not None else None
+        gp = pooled.grad_for_read() if pooled is not None else None
+        gw, fin_w = self._param_grad(conv.weight)
+        gg, fin_g = self._param_grad(bn.weight)
+        gb, fin_b = self._param_grad(bn.bias)
+        if gf is None and gp is None:
+            for t in (gw, gg, gb):
+                t.zero_()
+            for f in (fin_w, fin_g, fin_b):
+                if f:
+                    f()
+            return
+        rows = _lib.lib.fsdet_bn_bwd_rows(B, H, W)
+        part = _empty(rows + 2, 2 * s.cout, device=dev)
+        coef = _empty(2, s.cout, device=dev)
+        a_gf = (gf.ptr, gf.ld) if gf is not None else (None, 0)
+        a_gp = (gp.ptr, gp.ld) if gp is not None else (None, 0)
+        call('fsdet_bn_act_bwd_reduce', z.ptr, z.ld, a_gf[0], a_gf[1], a_gp[0], a_gp[1], ptr(vec[2]), ptr(vec[3]),
+             ptr(vec[0]), ptr(vec[1]), s.slope, ptr(part), B, H, W, s.cout, 1, st)
+        call('fsdet_bn_bwd_finalize', ptr(part), rows, float(x.npix), ptr(bn.weight), ptr(vec[1]), ptr(gg), ptr(gb),
+             ptr(coef), s.cout, 1, st)
+        dz = Act.new(B, H, W, s.cout, dev, False)
+        call('fsdet_bn_act_bwd_apply', z.ptr, z.ld, a_gf[0], a_gf[1], a_gp[0], a_gp[1], ptr(vec[2]), ptr(vec[3]),
+             ptr(vec[0]), ptr(vec[1]), ptr(coef), s.slope, dz.ptr, dz.ld, B, H, W, s.cout, 1, st)
+        cin_p = x.C
+        if cin_p != s.cin:
+            gwp = _empty(s.cout, s.k * s.k, cin_p, device=dev)
+            self._wgrad(x, dz, gwp, cin_p, s.cout, s.k, st)
+            call('fsdet_pad_channels', ptr(gwp), cin_p, ptr(gw), s.cin, s.cout * s.k * s.k, st)
+        else:
+            self._wgrad(x, dz, gw, cin_p, s.cout, s.k, st)
+        self._dgrad(x, dz, wuse, cin_p, s.cout, s.k, st)
+        for f in (fin_w, fin_g, fin_b):
+            if f:
+                f()
+
+    def _convbias_bwd(self, rec, st):
+        _, s, x, wp, z, onez, full, pooled, conv, cout_p = rec
+        dev = x.buf.device
+        B, H, W = x.B, x.H, x.W
+        gf = full.grad_for_read() if full is not None else None
+        gp = pooled.grad_for_read() if pooled is not None else None
+        gw, fin_w = self._param_grad(conv.weight)
+        gb, fin_b = self._param_grad(conv.bias) if conv.bias is not None else (None, None)
+        if gf is None and gp is None:
+            gw.zero_()
+            if gb is not None:
+                gb.zero_()
+            for f in (fin_w, fin_b):
+                if f:
+                    f()
+            return
+        ones, zeros = onez
+        if ones is None:
+            ones = torch.ones(cout_p, device=dev)
+            zeros = torch.zeros(cout_p, device=dev)
+        rows = _lib.lib.fsdet_bn_bwd_rows(B, H, W)
+        part = _empty(rows + 2, 2 * cout_p, device=dev)
+        dbp = _empty(cout_p, device=dev)
+        a_gf = (gf.ptr, gf.ld) if gf is not None else (None, 0)
+        a_gp = (gp.ptr, gp.ld) if gp is not None else (None, 0)
+        call('fsdet_bn_act_bwd_reduce', z.ptr, z.ld, a_gf[0], a_gf[1], a_gp[0], a_gp[1], ptr(ones), ptr(zeros), None, None,
+             s.slope, ptr(part), B, H, W, cout_p, 0, st)
+        call('fsdet_bn_bwd_finalize', ptr(part), rows, float(x.npix), None, None, None, ptr(dbp), None, cout_p, 0, st)
+        if full is z and gp is None:
+            dz = gf  # linear, unpooled: dZ is the incoming gradient itself
+        else:
+            dz = Act.new(B, H, W, cout_p, dev, False)
+            call('fsdet_bn_act_bwd_apply', z.ptr, z.ld, a_gf[0], a_gf[1], a_gp[0], a_gp[1], ptr(ones), ptr(zeros), None,
+                 None, None, s.slope, dz.ptr, dz.ld, B, H, W, cout_p, 0, st)
+        cin_p = x.C
+        kk = s.k * s.k
+        gwp = _empty(cout_p, kk, cin_p, device=dev)
+        self._wgrad(x, dz, gwp, cin_p, cout_p, s.k, st)
+        if cin_p != s.cin:
+            call('fsdet_pad_channels', ptr(gwp), cin_p, ptr(gw), s.cin, s.cout * kk, st)
+        else:
+            # rows [0, cout) of the padded gradient, OHWI order == gw's storage order
+            gw.permute(0, 2, 3, 1).copy_(gwp[:s.cout].view(s.cout, s.k, s.k, cin_p))
+        if gb is not None:
+            gb.copy_(dbp[:s.cout])
+        self._dgrad(x, dz, wp, cin_p, cout_p, s.k, st)
+        for f in (fin_w, fin_b):
+            if f:
+                f()
+
+    def _head_bwd(self, rec, gout, st):
+        _, s, head, x, rw2, weff, conv, n_cls, O, Npad = rec
+        dev = x.buf.device
+        K = x.C
+        N = n_cls * O
+        HW = x.H * x.W
+        dzh = Act.new(x.B, x.H, x.W, Npad, dev, False)
+        call('fsdet_nchw_to_nhwc', ptr(gout), N, None, 0, dzh.ptr, dzh.ld, Npad, x.B, HW, st)
+        gw, fin_w = self._param_grad(conv.weight)
+        gb, fin_b = self._param_grad(conv.bias) if conv.bias is not None else (None, None)
+        if gb is not None:
+            nws = _lib.lib.fsdet_head_bias_grad_workspace_floats(x.npix, n_cls, O)
+            ws = _empty(max(nws, 1), device=dev)
+            call('fsdet_head_bias_grad', dzh.ptr, dzh.ld, ptr(gb), ptr(ws), x.npix, n_cls, O, st)
+        dweff = _empty(Npad, K, device=dev)
+        self._wgrad(x, dzh, dweff, K, Npad, 1, st)
+        drw = _empty(n_cls, K, device=dev)
+        call('fsdet_head_param_grads', ptr(dweff), ptr(conv.weight), ptr(rw2), ptr(gw), ptr(drw), n_cls, O, K, st)
+        self._dgrad(x, dzh, weff, K, Npad, 1, st)
+        for f in (fin_w, fin_b):
+            if f:
+                f()
+        return drw
+
+
+class _NetFunction(torch.autograd.Function):
+    """Autograd boundary of one network. Parameters are passed so that autograd
+    schedules the backward; their gradients are written into `.grad` by the
+    executor (None is returned for them)."""
+
+    @staticmethod
+    def forward(ctx, runner, training, n_in, has_extra, *tensors):
+        inputs = list(tensors[:n_in])
+        extra = tensors[n_in] if has_extra else None
+        out, tape = runner.forward(inputs, extra, training=training, record=True)
+        ctx.runner = runner
+        ctx.tape = tape
+        ctx.n_in = n_in
+        ctx.has_extra = has_extra
+        ctx.n_tensors = len(tensors)
+        ctx.extra_shape = tuple(extra.shape) if has_extra else None
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        tape = ctx.tape
+        ctx.tape = None
+        drw = ctx.runner.backward(tape, gout)
+        grads = [None] * ctx.n_tensors
+        if ctx.has_extra and drw is not None:
+            grads[ctx.n_in] = drw.view(ctx.extra_shape)
+        return (None, None, None, None) + tuple(grads)
+
+
+def run_network(runner, inputs, extra, params, training):
+    """Forward through `runner`; differentiable when grad mode is on."""
+    need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or
+                                             (extra is not None and extra.requires_grad))
+    if not need_grad:
+        out, _ = runner.forward(list(inputs), extra, training=training, record=False)
+        return out
+    tensors = list(inputs) + ([extra] if extra is not None else []) + list(params)
+    return _NetFunction.apply(runner, training, len(inputs), extra is not None, *tensors)

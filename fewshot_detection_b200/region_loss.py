@@ -1,0 +1,206 @@
+"""RegionLoss / RegionLossV2 with the whole loss on the device.
+
+Same Python surface as the reference's region_loss.py: modules constructed with
+no arguments and attribute-assigned by the network builder
+(darknet_meta.py:322-334), `loss = region_loss(output, target)` with `target`
+a CPU float64 tensor ([B, n_cls, 250] for V2, [B, 250] or [B, n, 250] for the
+plain loss), `.seen` mutated by the training driver, `cfg.neg_ratio /
+cfg.metayolo / cfg.max_boxes` read at call time.
+
+What changed underneath: the reference decodes boxes with ~25 small kernels,
+copies pred_boxes to the host, runs `build_targets` as a Python double loop
+(region_loss.py:37-132), copies nine target tensors back and evaluates six
+losses with autograd.  Here three kernels do it all (csrc/region.cu):
+decode -> build_targets (bit-exact masks / indices) -> loss + d(loss)/d(output).
+`neg_filter` keeps its host RNG semantics (region_loss.py:15-34).
+"""
+from numbers import Number
+from random import random
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .cfg import cfg
+from ._lib import call, ptr
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def neg_filter(pred_boxes, target, withids=False):
+    """region_loss.py:15-34. `target` is the CPU float64 [rows, 250] label
+    matrix. Returns the kept row indices (python list, ascending); the rows
+    themselves are gathered on the device by the caller."""
+    assert pred_boxes.size(0) == target.size(0)
+    if cfg.neg_ratio == 'full':
+        inds = list(range(pred_boxes.size(0)))
+    elif isinstance(cfg.neg_ratio, Number):
+        flags = (torch.sum(target, 1) != 0).cpu().tolist()
+        ratio = cfg.neg_ratio * sum(flags) * 1. / (len(flags) - sum(flags))
+        if ratio >= 1:
+            inds = list(range(pred_boxes.size(0)))
+        else:
+            flags = [0 if f == 0 and random() > ratio else 1 for f in flags]
+            inds = [i for i, f in enumerate(flags) if f]
+    else:
+        raise NotImplementedError('neg_ratio not recognized')
+    if withids:
+        return pred_boxes, target, inds
+    return pred_boxes, target
+
+
+def _to_device_f64(target_rows, device):
+    if target_rows.is_cuda:
+        return target_rows.to(torch.float64).contiguous()
+    t = target_rows.to(torch.float64).contiguous()
+    if not t.is_pinned():
+        try:
+            t = t.pin_memory()
+        except RuntimeError:
+            pass
+    return t.to(device, non_blocking=True)
+
+
+def build_targets(pred_boxes, target, anchors, num_anchors, num_classes, nH, nW, noobject_scale, object_scale,
+                  sil_thresh, seen, sync=True):
+    """Device version of region_loss.py:37-132 with the reference's signature.
+
+    pred_boxes: float32 CUDA [nB*nA*nH*nW, 4]; target: float64 [nB, 250] (CPU or
+    CUDA). Returns (nGT, nCorrect, coord_mask, conf_mask, cls_mask, tx, ty, tw,
+    th, tconf, tcls) with the nine tensors float32 CUDA [nB, nA, nH, nW].  With
+    sync=False nGT/nCorrect are returned as a CUDA int32 tensor [4] instead of
+    Python ints (no host synchronisation)."""
+    dev = pred_boxes.device
+    if not pred_boxes.is_cuda:
+        raise TypeError('build_targets runs on the GPU only; pred_boxes must be a CUDA tensor')
+    nB = target.size(0)
+    nA = num_anchors
+    assert len(anchors) // num_anchors == 2, 'anchor_step must be 2'
+    tgt = _to_device_f64(target, dev)
+    out = torch.empty(9, nB, nA, nH, nW, device=dev)
+    counters = torch.empty(4, dtype=torch.int32, device=dev)
+    anc = torch.tensor([float(a) for a in anchors], dtype=torch.float64).to(dev)
+    pb = pred_boxes.contiguous()
+    call('fsdet_build_targets', ptr(pb), ptr(tgt), ptr(anc), nB, nA, nH, nW, int(cfg.max_boxes),
+         float(noobject_scale), float(object_scale), float(sil_thresh), int(seen),
+         *[ptr(out[i]) for i in range(9)], ptr(counters), _st())
+    if not sync:
+        return (counters,) + tuple(out[i] for i in range(9))
+    c = counters.tolist()
+    if c[2]:
+        raise ValueError('math domain error: %d ground-truth boxes with zero width/height or outside the grid' % c[2])
+    return (c[0], c[1]) + tuple(out[i] for i in range(9))
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, output, loss, grad):
+        ctx.save_for_backward(grad)
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        (grad,) = ctx.saved_tensors
+        return grad * gout, None, None
+
+
+class _RegionBase(nn.Module):
+    def __init__(self, num_classes=0, anchors=[], num_anchors=1):
+        super(_RegionBase, self).__init__()
+        self.num_classes = num_classes
+        self.anchors = anchors
+        self.num_anchors = num_anchors
+        self.anchor_step = len(anchors) // num_anchors
+        self.coord_scale = 1
+        self.noobject_scale = 1
+        self.object_scale = 5
+        self.class_scale = 1
+        self.thresh = 0.6
+        self.seen = 0
+        self.verbose = True   # print the reference's per-step log line (forces a host sync)
+        self.last = None      # dict with the logged scalars of the last call (device tensors when not verbose)
+
+    def _run(self, output, target2d, inds, mode, bs, cs, img_start):
+        if not output.is_cuda:
+            raise TypeError('the region loss runs on the GPU only (no CPU fallback)')
+        dev = output.device
+        st = _st()
+        out_c = output.detach().contiguous()
+        rows_total = out_c.size(0)
+        nA, nC = int(self.num_anchors), int(self.num_classes)
+        nH, nW = out_c.size(2), out_c.size(3)
+        assert out_c.size(1) == nA * (5 + nC)
+        nB = len(inds)
+        full = nB == rows_total
+        inds_t = None
+        if not full:
+            inds_t = torch.tensor(inds, dtype=torch.int32).to(dev, non_blocking=True)
+        if full:
+            tgt_rows = target2d
+        elif target2d.is_cuda:
+            tgt_rows = target2d[inds_t.long()]
+        else:
+            tgt_rows = target2d[torch.as_tensor(inds, dtype=torch.long)]
+        tgt = _to_device_f64(tgt_rows, dev)
+        anc32 = torch.tensor([float(a) for a in self.anchors], dtype=torch.float32).to(dev, non_blocking=True)
+        anc64 = torch.tensor([float(a) for a in self.anchors], dtype=torch.float64).to(dev, non_blocking=True)
+        pred = torch.empty(max(nB, 1) * nA * nH * nW, 4, device=dev)
+        call('fsdet_region_decode', ptr(out_c), ptr(inds_t), nB, nA, nC, nH, nW, ptr(anc32), ptr(pred), st)
+        tg = torch.empty(9, max(nB, 1), nA, nH, nW, device=dev)
+        counters = torch.empty(4, dtype=torch.int32, device=dev)
+        call('fsdet_build_targets', ptr(pred), ptr(tgt), ptr(anc64), nB, nA, nH, nW, int(cfg.max_boxes),
+             float(self.noobject_scale), float(self.object_scale), float(self.thresh), int(self.seen),
+             *[ptr(tg[i]) for i in range(9)], ptr(counters), st)
+        grad = torch.empty_like(out_c)
+        losses = torch.empty(8, dtype=torch.float64, device=dev)
+        imgs_t = None
+        if mode == 0:
+            imgs_t = torch.tensor(img_start, dtype=torch.int32).to(dev, non_blocking=True)
+        call('fsdet_region_loss_grad', ptr(out_c), ptr(grad), ptr(inds_t), None, ptr(imgs_t), rows_total, nB, bs, cs, nA,
+             nC, nH, nW, *[ptr(tg[i]) for i in range(9)], float(self.coord_scale), float(self.class_scale), mode,
+             1 if cfg.metayolo else 0, ptr(losses), st)
+        loss = losses[6].to(torch.float32)
+        self.last = {'losses': losses, 'counters': counters}
+        if self.verbose:
+            host = losses.tolist()
+            c = counters.tolist()
+            if c[2]:
+                raise ValueError('math domain error: %d ground-truth boxes with zero width/height or outside the grid'
+                                 % c[2])
+            print('%d: nGT %d, recall %d, proposals %d, loss: x %f, y %f, w %f, h %f, conf %f, cls %f, total %f' % (
+                self.seen, c[0], c[1], int(host[7]), host[0], host[1], host[2], host[3], host[4], host[5], host[6]))
+            self.last.update(nGT=c[0], nCorrect=c[1], nProposals=int(host[7]), loss_x=host[0], loss_y=host[1],
+                             loss_w=host[2], loss_h=host[3], loss_conf=host[4], loss_cls=host[5], loss=host[6])
+        if output.requires_grad and torch.is_grad_enabled():
+            return _LossFn.apply(output, loss, grad)
+        return loss
+
+
+class RegionLoss(_RegionBase):
+    """region_loss.py:134-232 (plain YOLOv2 region loss)."""
+
+    def forward(self, output, target):
+        if target.dim() == 3:
+            target = target.view(-1, target.size(-1))
+        _, _, inds = neg_filter(output, target, withids=True)
+        return self._run(output, target, inds, 1, 0, 0, None)
+
+
+class RegionLossV2(_RegionBase):
+    """region_loss.py:235-366: region loss + softmax classification across the
+    n_cls class branches of every image."""
+
+    def __init__(self, num_classes=0, anchors=[], num_anchors=1):
+        super(RegionLossV2, self).__init__(num_classes, anchors, num_anchors)
+        print('class_scale', self.class_scale)
+
+    def forward(self, output, target):
+        bs = target.size(0)
+        cs = target.size(1)
+        target2d = target.view(-1, target.size(-1))
+        _, _, inds = neg_filter(output, target2d, withids=True)
+        counts, _ = np.histogram(inds, bins=bs, range=(0, bs * cs))
+        img_start = [0] + [int(v) for v in np.cumsum(counts)]
+        return self._run(output, target2d, inds, 0, bs, cs, img_start)

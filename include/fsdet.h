@@ -1,0 +1,192 @@
+/*
+ * libfsdet.so — C ABI of the B200-native few-shot-detection training hot path.
+ *
+ * Drop-in boundary.  The reference (bingykang/Fewshot_Detection) reaches its
+ * device code through torch-0.3.1 library calls made from
+ * darknet_meta.py / dynamic_conv.py / region_loss.py; its only own FFI
+ * precedent is layers/batchnorm/src/batchnorm.h:1-6 (plain C symbols, caller
+ * allocates every output and workspace, launches on the current device).  This
+ * header keeps that contract:
+ *
+ *   - plain C, raw device pointers + sizes, no torch types;
+ *   - the caller owns all memory (outputs and workspaces are passed in); the
+ *     library never allocates, frees or synchronises;
+ *   - every function launches on `stream` (a cudaStream_t passed as void*) of the
+ *     CURRENT device and returns immediately;
+ *   - return value: 0 = ok, <0 = invalid argument (see fsdet_last_error()),
+ *     >0 = cudaError_t of the failed launch;
+ *   - re-entrant: no mutable global state (one thread per GPU or one process
+ *     per GPU are both fine).
+ *
+ * Layouts.  Activations inside the library are NHWC fp32: a 2-D array
+ * [B*H*W pixels][ld] of which `C` channels starting at the given pointer are
+ * used (ld >= C lets a layer write straight into a slice of a route/concat
+ * buffer).  Convolution weights are OHWI ([Cout][kh*kw][Cin], i.e. torch
+ * channels_last storage of the reference's OIHW nn.Conv2d.weight).  The
+ * reference-facing tensors (input images, head output, loss targets) are NCHW
+ * exactly as darknet_meta.Darknet.forward / RegionLossV2.forward exchange them.
+ *
+ * Each entry point cites the reference code it replaces (paths relative to
+ * /root/reference).
+ */
+#ifndef FSDET_H_
+#define FSDET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library info ----------------------------------------------------- */
+int fsdet_version(void);
+/* thread-local description of the last non-zero return value */
+const char* fsdet_last_error(void);
+/* compute capability the kernels were compiled for (100 = sm_100a) */
+int fsdet_compiled_arch(void);
+
+/* ---- layout conversion at the reference-facing boundary ---------------- */
+/* [B,C0,H,W] (+ optional second tensor [B,C1,H,W], the support branch's
+ * torch.cat([metax, mask], 1), darknet_meta.py:117-118) -> NHWC [B*H*W][ld],
+ * channels C0+C1..Cpad-1 zero filled. */
+int fsdet_nchw_to_nhwc(const float* in0, int C0, const float* in1, int C1, float* out, int ld, int Cpad,
+                       int B, int HW, void* stream);
+/* NHWC [B*HW][ld] (first C channels) (+ optional bias[C]) -> NCHW [B,C,HW] */
+int fsdet_nhwc_to_nchw(const float* in, int ld, const float* bias, float* out, int B, int C, int HW, void* stream);
+
+/* ---- convolution (nn.Conv2d stride 1, pad (k-1)/2; darknet_meta.py:219-259) */
+/* Implicit GEMM  z[p][n] = sum_{tap,ci} x[p+tap][ci] * w[n][tap][ci] (+bias[n])
+ * (+ previous z when accumulate != 0).  Used for forward (w = OHWI weights) and
+ * for the input gradient (x = dz, w = fsdet_weight_flip_transpose(weights)).
+ * stat_partial (optional): per-CTA partial column sums for train-mode
+ * BatchNorm, float [fsdet_conv_stat_rows(B*H*W) + 2][2*Cout] (sum, sum of
+ * squares; the two extra rows are scratch for fsdet_bn_finalize's
+ * double-precision totals).
+ * Requires Cin % 4 == 0, ldx % 4 == 0, 16-byte aligned pointers. */
+int fsdet_conv_fwd(const float* x, int ldx, const float* w, const float* bias, float* z, int ldz,
+                   float* stat_partial, int B, int H, int W, int Cin, int Cout, int ksize, int accumulate,
+                   void* stream);
+int fsdet_conv_stat_rows(int npix);
+/* Weight gradient dw[n][tap][ci] = sum_p dz[p][n] * x[p+tap][ci]  (OHWI).
+ * workspace: float [fsdet_conv_wgrad_workspace_floats(...)] (split-K partials,
+ * reduced in a fixed order: deterministic). */
+int fsdet_conv_wgrad(const float* x, int ldx, const float* dz, int lddz, float* dw, float* workspace,
+                     size_t workspace_floats, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
+size_t fsdet_conv_wgrad_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize);
+/* wt[ci][kk-1-tap][co] = w[co][tap][ci]  (weights for the input-gradient conv) */
+int fsdet_weight_flip_transpose(const float* w, float* wt, int Cout, int kk, int Cin, void* stream);
+/* copy [rows][cin] -> [rows][cout] channel-padded / -cropped (zero fill) */
+int fsdet_pad_channels(const float* in, int cin, float* out, int cout, size_t rows, void* stream);
+
+/* ---- BatchNorm2d(train/eval) + LeakyReLU(0.1) + MaxPool2d(2,2) -------- */
+/* nn.BatchNorm2d defaults (darknet_meta.py:247): eps 1e-5, momentum 0.1, biased
+ * batch variance for normalisation, unbiased for running_var.
+ * Reduces the conv kernel's partials; writes mean/invstd (saved for backward)
+ * and the fused per-channel scale/shift; updates running stats when
+ * training != 0.  In eval mode (training == 0) scale/shift come from the running
+ * statistics and stat_partial is ignored. */
+int fsdet_bn_finalize(const float* stat_partial, int nparts, double count, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float momentum, float eps, float* mean,
+                      float* invstd, float* scale, float* shift, int C, int training, void* stream);
+/* y = leaky(z*scale+shift, slope); optional full-resolution output y_full and
+ * optional MaxPool2d(2,2) (floor) output y_pool written in the same pass. */
+int fsdet_bn_act_fwd(const float* z, int ldz, const float* scale, const float* shift, float slope, float* y_full,
+                     int ld_full, float* y_pool, int ld_pool, int B, int H, int W, int C, void* stream);
+/* Backward of the block above.  dy_full / dy_pool: gradients w.r.t. the two
+ * outputs (either may be NULL).  Pass 1 reduces  sum(du), sum(du*xhat) into
+ * partials float [fsdet_bn_bwd_rows(B,H,W) + 2][2*C] (two scratch rows for
+ * the double-precision totals of fsdet_bn_bwd_finalize); pass 2 (after
+ * fsdet_bn_bwd_finalize) writes dz.  With has_bn == 0 (conv + bias + act):
+ * xhat terms are skipped, dbeta = bias gradient and dz = du. */
+int fsdet_bn_act_bwd_reduce(const float* z, int ldz, const float* dy_full, int ld_dyf, const float* dy_pool,
+                            int ld_dyp, const float* scale, const float* shift, const float* mean,
+                            const float* invstd, float slope, float* partial, int B, int H, int W, int C,
+                            int has_bn, void* stream);
+int fsdet_bn_bwd_rows(int B, int H, int W);
+/* dgamma, dbeta and the two per-channel coefficients used by the apply pass */
+int fsdet_bn_bwd_finalize(const float* partial, int nparts, double count, const float* gamma, const float* invstd,
+                          float* dgamma, float* dbeta, float* coef /* [2*C] */, int C, int has_bn, void* stream);
+int fsdet_bn_act_bwd_apply(const float* z, int ldz, const float* dy_full, int ld_dyf, const float* dy_pool,
+                           int ld_dyp, const float* scale, const float* shift, const float* mean,
+                           const float* invstd, const float* coef, float slope, float* dz, int lddz, int B, int H,
+                           int W, int C, int has_bn, void* stream);
+
+/* ---- stand-alone pooling / reorg / route (darknet_meta.py:47-74,157-171) */
+/* size 2; stride 2 (floor) or stride 1 with replicate pad right/bottom
+ * (MaxPoolStride1, darknet_meta.py:47-53) */
+int fsdet_maxpool_fwd(const float* x, int ldx, float* y, int ldy, int B, int H, int W, int C, int stride, void* stream);
+int fsdet_maxpool_bwd(const float* x, int ldx, const float* dy, int lddy, float* dx, int lddx, int B, int H, int W,
+                      int C, int stride, void* stream);
+/* Reorg(2): out[b,(i*2+j)*C+c,h,w] = x[b,c,2h+i,2w+j] (darknet_meta.py:55-74) */
+int fsdet_reorg_fwd(const float* x, int ldx, float* y, int ldy, int B, int H, int W, int C, void* stream);
+int fsdet_reorg_bwd(const float* dy, int lddy, float* dx, int lddx, int B, int H, int W, int C, void* stream);
+/* GlobalMaxPool2d (pooling.py:8-27): y[n][c] = max_p x[n][p][c]; argmax saved */
+int fsdet_globalmax_fwd(const float* x, int ldx, float* y, int32_t* argmax, int N, int HW, int C, void* stream);
+int fsdet_globalmax_bwd(const float* dy, const int32_t* argmax, float* dx, int lddx, int N, int HW, int C, void* stream);
+/* dst[p][0..C) = (accumulate ? dst : 0) + src[p][0..C)   (route/concat, grad sum) */
+int fsdet_copy_channels(const float* src, int ldsrc, float* dst, int lddst, size_t npix, int C, int accumulate,
+                        void* stream);
+
+/* ---- per-class reweighting fused into the 1x1 detection conv ----------- */
+/* dynamic_conv.DynamicConv2d.forward (dynamic_conv.py:125-164) followed by the
+ * head nn.Conv2d(1024, 30, 1):  out[b*n_cls+c] = (W (.) rw[c]) x[b] + bias.
+ * weff[(c*O+o)][k] = W[o][k]*rw[c][k]  (rows padded to Npad with zeros),
+ * bias_eff[c*O+o] = bias[o]. The GEMM itself runs through fsdet_conv_fwd. */
+int fsdet_head_weff(const float* W, const float* bias, const float* rw, float* weff, float* bias_eff, int n_cls,
+                    int O, int K, int Npad, void* stream);
+/* dW[o][k] = sum_c dweff[c*O+o][k]*rw[c][k]; drw[c][k] = sum_o dweff[c*O+o][k]*W[o][k] */
+int fsdet_head_param_grads(const float* dweff, const float* W, const float* rw, float* dW, float* drw, int n_cls,
+                           int O, int K, void* stream);
+/* column sums of an NHWC matrix folded over classes: dbias[o] = sum_{p,c} d[p][c*O+o] */
+int fsdet_head_bias_grad(const float* d, int ld, float* dbias, float* workspace /* [rows][n_cls*O] */,
+                         size_t npix, int n_cls, int O, void* stream);
+size_t fsdet_head_bias_grad_workspace_floats(size_t npix, int n_cls, int O);
+
+/* ---- region loss (region_loss.py) -------------------------------------- */
+/* RegionLoss(V2).forward prologue, region_loss.py:276-298: for the kept rows
+ * `inds` of output [rows_total, A*(5+nC), H, W] computes pred_boxes
+ * float32 [nB*A*H*W][4] = (sigmoid(tx)+col, sigmoid(ty)+row, exp(tw)*aw,
+ * exp(th)*ah) in grid units, with torch's float32 op order. */
+int fsdet_region_decode(const float* output, const int32_t* inds, int nB, int A, int nC, int H, int W,
+                        const float* anchors_f32 /* [2A] */, float* pred_boxes, void* stream);
+/* build_targets, region_loss.py:37-132 (+ utils.bbox_ious / bbox_iou,
+ * utils.py:21-83).  target: float64 [nB][250] rows already filtered.  Outputs:
+ * nine float32 [nB][A][H][W] tensors and counters int32[4] = {nGT, nCorrect,
+ * n_degenerate (GT with w or h == 0: the reference raises there), 0}.
+ * Index/mask outputs are bit-exact w.r.t. the reference; phase-1 IoUs are
+ * computed in float32 with the reference's operation order and no FMA
+ * contraction, phase 2 in float64. */
+int fsdet_build_targets(const float* pred_boxes, const double* target, const double* anchors_f64 /* [2A] */,
+                        int nB, int A, int H, int W, int max_boxes, float noobject_scale, float object_scale,
+                        float sil_thresh, long long seen, float* coord_mask, float* conf_mask, float* cls_mask,
+                        float* tx, float* ty, float* tw, float* th, float* tconf, float* tcls, int32_t* counters,
+                        void* stream);
+/* Loss terms + gradient w.r.t. the raw head output (region_loss.py:303-345).
+ * mode 0 = RegionLossV2 (softmax across the cs class rows of each image),
+ * mode 1 = RegionLoss (softmax across nC channels; tcls zeroed if metayolo).
+ * row_of[r] = kept-row slot of output row r or -1; img_start[bs+1] = prefix of
+ * kept rows per image (V2).  losses: double[8] = {x,y,w,h,conf,cls,total,nProposals}
+ * accumulated with atomics in double (zeroed by this call's first kernel). */
+int fsdet_region_loss_grad(const float* output, float* grad_output, const int32_t* inds, const int32_t* row_of,
+                           const int32_t* img_start, int rows_total, int nB, int bs, int cs, int A, int nC, int H,
+                           int W, const float* coord_mask, const float* conf_mask, const float* cls_mask,
+                           const float* tx, const float* ty, const float* tw, const float* th, const float* tconf,
+                           const float* tcls, float coord_scale, float class_scale, int mode, int metayolo,
+                           double* losses, void* stream);
+
+/* ---- optimiser (optim.SGD as configured in train_meta.py:143-147) ------ */
+/* One launch over a table of tensors: d = g + wd*p; m = first ? d : mom*m + (1-damp)*d;
+ * p -= lr*m.  ptr tables live in device memory: params/grads/moms [n] pointers,
+ * sizes [n] element counts, chunk table built by the caller (see optim.py). */
+int fsdet_sgd_step(float* const* params, const float* const* grads, float* const* moms, const long long* sizes,
+                   const int32_t* chunk_tensor, const long long* chunk_offset, int n_chunks, int chunk_elems,
+                   float lr, float momentum, float dampening, float weight_decay, int first_step, void* stream);
+
+/* ---- misc --------------------------------------------------------------- */
+int fsdet_fill(float* p, float v, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSDET_H_ */

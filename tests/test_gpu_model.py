@@ -1,0 +1,200 @@
+"""Whole-network parity through the reference-facing Python API on the GPU:
+golden fixtures from the reference, plus the CPU oracle on fresh seeded inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+TOL = 1e-3  # north-star tolerance for float paths (relative L2 per tensor)
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def _meta(det, ler, seed):
+    from fewshot_detection_b200.darknet_meta import Darknet
+    from seeding import seeded_init
+    m = Darknet([dict(b) for b in det], [dict(b) for b in ler])
+    seeded_init(m, seed)
+    return m.cuda().train()
+
+
+def _inputs(d, regen):
+    from seeding import synth_masks
+    seed = int(d['seed'])
+    bs, cs, side, ms = int(d['bs']), int(d['cs']), int(d['side']), int(d['meta_side'])
+    if regen:
+        g = torch.Generator().manual_seed(seed + 1)
+        x = torch.rand(bs, 3, side, side, generator=g)
+        metax = torch.rand(cs, 3, ms, ms, generator=g)
+        mask = torch.from_numpy(synth_masks(cs, ms, seed + 2))
+    else:
+        x, metax, mask = (torch.from_numpy(d[k]) for k in ('x', 'metax', 'mask'))
+    return x.cuda(), metax.cuda(), mask.cuda()
+
+
+def test_meta_mini_all_tensors_vs_reference():
+    from fewshot_detection_b200 import netcfg
+    d = np.load(os.path.join(G, 'meta_mini.npz'))
+    m = _meta(netcfg.mini_dynamic_blocks(128, 4), netcfg.mini_reweighting_blocks(64, 4, 128), int(d['seed']))
+    x, metax, mask = _inputs(d, False)
+    out = m(x, metax, mask)
+    assert rel(out.detach().cpu().numpy(), d['output']) < TOL
+    L = m.models[len(m.models) - 1]
+    L.seen = int(d['seen'])
+    loss = L(out, torch.from_numpy(d['target']))
+    loss.backward()
+    assert abs(loss.item() - float(d['loss'])) < TOL * abs(float(d['loss']))
+    worst = 0.0
+    for name, p in m.named_parameters():
+        assert p.grad is not None, name
+        e = rel(p.grad.detach().cpu().contiguous().numpy(), d['grad/' + name])
+        worst = max(worst, e)
+        assert e < TOL, (name, e)
+    with torch.no_grad():
+        dw = m.meta_forward(metax, mask)
+    assert rel(dw[0].cpu().numpy(), d['dynamic_weights_2nd_pass']) < TOL
+    for name, b in m.named_buffers():
+        if 'running' in name:
+            assert rel(b.cpu().numpy(), d['buf/' + name]) < TOL, name
+    print('worst grad rel err', worst)
+
+
+def test_meta_full416_digest_vs_reference():
+    from fewshot_detection_b200 import netcfg
+    d = np.load(os.path.join(G, 'meta_full416.npz'))
+    m = _meta(netcfg.darknet_dynamic_blocks(), netcfg.reweighting_net_blocks(), int(d['seed']))
+    x, metax, mask = _inputs(d, True)
+    out = m(x, metax, mask)
+    assert tuple(out.shape) == (2, 30, 13, 13)
+    assert rel(out.detach().cpu().numpy(), d['output']) < TOL
+    L = m.models[len(m.models) - 1]
+    L.seen = int(d['seen'])
+    loss = L(out, torch.from_numpy(d['target']))
+    loss.backward()
+    assert abs(loss.item() - float(d['loss'])) < TOL * abs(float(d['loss']))
+    for name, p in m.named_parameters():
+        gn = float(d['gradnorm/' + name])
+        g = p.grad.detach().cpu().contiguous()
+        assert abs(g.double().norm().item() - gn) < TOL * gn + 1e-12, name
+        assert rel(g.reshape(-1)[:64].numpy(), d['gradhead/' + name]) < 5 * TOL, name
+
+
+def test_tiny_yolo_416_config1_vs_reference():
+    from fewshot_detection_b200 import netcfg
+    from fewshot_detection_b200.darknet import Darknet
+    from seeding import seeded_init
+    d = np.load(os.path.join(G, 'tiny_yolo_416.npz'))
+    m = Darknet(netcfg.tiny_yolo_voc_blocks())
+    seeded_init(m, int(d['w_seed']))
+    m = m.cuda()
+    x = torch.rand(1, 3, 416, 416, generator=torch.Generator().manual_seed(int(d['x_seed']))).cuda()
+    m.eval()
+    with torch.no_grad():
+        y = m(x)
+    assert tuple(y.shape) == (1, 125, 13, 13)
+    assert rel(y.cpu().numpy(), d['y_eval']) < TOL
+    m.train()
+    assert rel(m(x).detach().cpu().numpy(), d['y_train']) < TOL
+
+
+def test_tiny_mini_train_step_vs_oracle():
+    """Plain Darknet + RegionLoss backward (maxpool stride 1, 125-channel head)."""
+    from fewshot_detection_b200 import netcfg
+    from fewshot_detection_b200.darknet import Darknet
+    from oracle import darknet as ODK, region_loss as ORL
+    from seeding import seeded_init, synth_targets
+    blocks = netcfg.mini_tiny_blocks(128, 8)
+    om = ODK.PlainDarknet([dict(b) for b in blocks])
+    seeded_init(om, 5)
+    om.train()
+    m = Darknet([dict(b) for b in blocks])
+    seeded_init(m, 5)
+    m = m.cuda().train()
+    x = torch.rand(3, 3, 128, 128, generator=torch.Generator().manual_seed(6))
+    tgt = torch.from_numpy(synth_targets(3, 1, 7, max_gt=4)[:, 0, :])
+    tgt[:, 0::5] = torch.floor(tgt[:, 0::5] * 0) + (torch.arange(50) % 20).double()  # class ids < 20
+    oo = om(x)
+    lo = ORL.region_loss_plain(oo, tgt, om.anchors, 5, 20, seen=20000, metayolo=False)
+    lo.backward()
+    from fewshot_detection_b200.cfg import cfg
+    cfg.metayolo = False
+    try:
+        out = m(x.cuda())
+        L = m.models[len(m.models) - 1]
+        L.seen = 20000
+        loss = L(out, tgt)
+        loss.backward()
+    finally:
+        cfg.metayolo = True
+    assert rel(out.detach().cpu().numpy(), oo.detach().numpy()) < TOL
+    assert abs(loss.item() - lo.item()) < TOL * abs(lo.item())
+    for (n1, p), (n2, q) in zip(m.named_parameters(), om.named_parameters()):
+        assert n1 == n2
+        assert rel(p.grad.detach().cpu().contiguous().numpy(), q.grad.numpy()) < TOL, n1
+
+
+def test_train_steps_match_oracle_sgd():
+    """Three full meta-training steps (forward, RegionLossV2, backward, FusedSGD)
+    against the oracle + torch.optim.SGD on the CPU."""
+    from fewshot_detection_b200 import netcfg
+    from fewshot_detection_b200.optim import FusedSGD
+    from oracle import darknet as ODK, region_loss as ORL
+    from seeding import seeded_init, synth_targets, synth_masks
+    det, ler = netcfg.mini_dynamic_blocks(128, 4), netcfg.mini_reweighting_blocks(64, 4, 128)
+    om = ODK.MetaDarknet([dict(b) for b in det], [dict(b) for b in ler])
+    seeded_init(om, 11)
+    om.train()
+    m = _meta(det, ler, 11)
+    oo = torch.optim.SGD(om.parameters(), lr=1e-3, momentum=0.9, dampening=0, weight_decay=5e-4)
+    og = FusedSGD(m.parameters(), lr=1e-3, momentum=0.9, dampening=0, weight_decay=5e-4)
+    L = m.models[len(m.models) - 1]
+    L.verbose = False
+    bs, cs = 4, 3
+    for it in range(3):
+        g = torch.Generator().manual_seed(100 + it)
+        x = torch.rand(bs, 3, 128, 128, generator=g)
+        metax = torch.rand(cs, 3, 64, 64, generator=g)
+        mask = torch.from_numpy(synth_masks(cs, 64, 200 + it))
+        tgt = torch.from_numpy(synth_targets(bs, cs, 300 + it, max_gt=4))
+        oo.zero_grad()
+        lo = ORL.region_loss_v2(om(x, metax, mask), tgt, om.anchors, 5, 1, seen=20000 + it * bs)
+        lo.backward()
+        oo.step()
+        og.zero_grad()
+        L.seen = 20000 + it * bs
+        lg = L(m(x.cuda(), metax.cuda(), mask.cuda()), tgt)
+        lg.backward()
+        og.step()
+        assert abs(lg.item() - lo.item()) < TOL * abs(lo.item()), it
+    for (n1, p), (n2, q) in zip(m.named_parameters(), om.named_parameters()):
+        assert rel(p.detach().cpu().contiguous().numpy(), q.detach().numpy()) < TOL, n1
+
+
+def test_weight_file_roundtrip(tmp_path):
+    from fewshot_detection_b200 import netcfg
+    from seeding import seeded_init
+    det, ler = netcfg.mini_dynamic_blocks(128, 4), netcfg.mini_reweighting_blocks(64, 4, 128)
+    m = _meta(det, ler, 21)
+    m.seen = 1234
+    f = str(tmp_path / 'w.weights')
+    m.save_weights(f)
+    m2 = _meta(det, ler, 22)
+    m2.load_weights(f)
+    assert m2.seen == 1234
+    for (n1, p), (n2, q) in zip(m.named_parameters(), m2.named_parameters()):
+        assert torch.equal(p.detach().cpu().contiguous(), q.detach().cpu().contiguous()), n1
+    # byte layout = the reference's: header int32[4], then bn.bias, bn.weight, mean, var, conv.weight(OIHW)
+    raw = np.fromfile(f, dtype=np.float32)[4:]
+    c0 = m.models[0]
+    n = c0[1].bias.numel()
+    assert np.array_equal(raw[:n], c0[1].bias.detach().cpu().numpy())
+    w = c0[0].weight.detach().cpu().contiguous().numpy().reshape(-1)
+    assert np.array_equal(raw[4 * n:4 * n + w.size], w)
