@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the few-shot-detection meta-training hot path (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host CPU
+
+One "step" = one meta-training iteration on one synthetic batch per GPU:
+Darknet(darknet_dynamic + reweighting_net).forward -> RegionLossV2 (decode,
+build_targets, loss) -> backward -> (gradient all-reduce) -> SGD, at the
+configuration BASELINE.json's metric is quoted on (configs[1]): 416x416, batch 64
+per GPU, 20 classes, 5 anchors.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden'))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = 'images/sec (416x416, 20-cls) meta-training step; build_targets ms/batch'
+# kernels launched per C-ABI call (lower bounds, for the gpu_launches claim)
+LAUNCHES = {'fsdet_conv_wgrad': 2, 'fsdet_bn_finalize': 2, 'fsdet_bn_bwd_finalize': 2, 'fsdet_head_bias_grad': 2,
+            'fsdet_region_loss_grad': 3}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='query images per GPU')
+    ap.add_argument('--ncls', type=int, default=20)
+    ap.add_argument('--side', type=int, default=416)
+    ap.add_argument('--ref-batch', type=int, default=8, help='query images per CPU reference step (bounded sample)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def synth_batch(B, ncls, side, seed):
+    from seeding import synth_targets, synth_masks
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, 3, side, side, generator=g)
+    metax = torch.rand(ncls, 3, 416, 416, generator=g)
+    mask = torch.from_numpy(synth_masks(ncls, 416, seed + 1))
+    target = torch.from_numpy(synth_targets(B, ncls, seed + 2, max_gt=5))
+    return x, metax, mask, target
+
+
+class ClockSampler(object):
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            f = [c.strip() for c in r.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_step_factory(ncls, side, B, threads):
+    """The reference's algorithm on the host CPU: oracle port (torch-CPU ops +
+    Python build_targets), one full training step."""
+    from fewshot_detection_b200 import netcfg
+    from oracle import darknet as ODK, region_loss as ORL
+    from seeding import seeded_init
+    torch.set_num_threads(threads)
+    m = ODK.MetaDarknet(netcfg.darknet_dynamic_blocks(side, side), netcfg.reweighting_net_blocks())
+    seeded_init(m, 0)
+    m.train()
+    factor = 15.0
+    opt = torch.optim.SGD(m.parameters(), lr=1e-3 / factor / B, momentum=0.9, dampening=0, weight_decay=0.0005 * B * factor)
+    x, metax, mask, target = synth_batch(B, ncls, side, 1234)
+    state = {'seen': 20000, 'bt_ms': None}
+
+    def step():
+        opt.zero_grad()
+        out = m(x, metax, mask)
+        state['seen'] += B
+        t0 = time.perf_counter()
+        loss = ORL.region_loss_v2(out, target, m.anchors, m.num_anchors, m.num_classes, seen=state['seen'])
+        state['loss_ms'] = (time.perf_counter() - t0) * 1e3
+        loss.backward()
+        opt.step()
+        return float(loss.item())
+    return step, state
+
+
+def cpu_build_targets_ms(B, ncls, G=13):
+    """Reference-side value of the metric's second half: build_targets on the host."""
+    from fewshot_detection_b200 import netcfg
+    from oracle import region_loss as ORL
+    from seeding import synth_targets
+    anchors = [float(a) for a in netcfg.VOC_ANCHORS.split(',')]
+    nB = B * ncls
+    tgt = synth_targets(B, ncls, 77, max_gt=5).reshape(nB, 250)
+    rs = np.random.RandomState(5)
+    n = nB * 5 * G * G
+    pred = np.abs(rs.randn(n, 4)).astype(np.float32) * 3 + 0.1
+    t0 = time.perf_counter()
+    ORL.build_targets(pred, tgt, anchors, 5, G, G, 1.0, 5.0, 0.6, 20000)
+    return (time.perf_counter() - t0) * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    B = args.ref_batch
+    step, state = cpu_step_factory(args.ncls, args.side, B, threads)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = B * args.steps / dt
+    sample = '%d query + %d support images per step (the full step is 64 query + %d support per GPU), oracle port, ' \
+             'torch %s CPU, %d threads' % (B, args.ncls, args.ncls, torch.__version__, threads)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'configs[1]: darknet_dynamic + reweighting_net base-train step, %dx%d, %d classes, 5 anchors'
+                               % (args.side, args.side, args.ncls), 'batch_per_step': B, 'n_cls': args.ncls,
+                   'neg': 'full', 'host': 'cpu'},
+        'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the hot path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    from fewshot_detection_b200 import netcfg, _lib
+    from fewshot_detection_b200.cfg import cfg
+    from fewshot_detection_b200.darknet_meta import Darknet
+    from fewshot_detection_b200.optim import FusedSGD
+    from fewshot_detection_b200.distributed import GradAllReducer
+    from fewshot_detection_b200.region_loss import build_targets
+    from seeding import seeded_init
+
+    B, ncls, side = args.batch, args.ncls, args.side
+    cfg.neg_ratio = 'full'
+    model = Darknet(netcfg.darknet_dynamic_blocks(side, side), netcfg.reweighting_net_blocks())
+    seeded_init(model, 0)            # identical replicas on every rank
+    model = model.to(dev).train()
+    region_loss = model.loss
+    region_loss.verbose = False
+    region_loss.seen = 20000
+    global_batch = B * world
+    factor = 15.0                    # train_meta.py:124-135 for neg='full'
+    opt = FusedSGD(model.parameters(), lr=1e-3 / factor / global_batch, momentum=0.9, dampening=0,
+                   weight_decay=0.0005 * global_batch * factor)
+    reducer = GradAllReducer(model, bucket_mb=32)
+
+    # two distinct host batches (pinned) per rank, alternated
+    host = []
+    for i in range(2):
+        x, metax, mask, target = synth_batch(B, ncls, side, 1000 * rank + 10 * i)
+        host.append((x.pin_memory(), metax.pin_memory(), mask.pin_memory(), target.pin_memory()))
+    resident = [tuple(t.to(dev) for t in hb) for hb in host]
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    def step(x, metax, mask, target):
+        reducer.begin_step()
+        out = model(x, metax, mask)
+        region_loss.seen += global_batch
+        loss = region_loss(out, target)
+        loss.backward()
+        reducer.finish()
+        opt.step()
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    # ---- device-resident throughput (value)
+    for i in range(args.warmup):
+        step(*resident[i % 2])
+    prof = {}
+    model._det.profile = prof
+    model._ler.profile = prof
+    calls0 = dict(_lib.CALLS)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda i: step(*resident[i % 2]), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    calls1 = dict(_lib.CALLS)
+    model._det.profile = None
+    model._ler.profile = None
+    launches = sum((calls1.get(k, 0) - calls0.get(k, 0)) * LAUNCHES.get(k, 1) for k in calls1)
+    value = global_batch * args.steps / (ms / 1e3)
+
+    # per-kernel roofline of the dominant kernel (CUDA events recorded on the launching stream)
+    kern = {}
+    for name, (flops, evs) in prof.items():
+        t = sum(a.elapsed_time(b) for a, b in evs)
+        kern[name] = {'launches_per_step': len(evs) / args.steps, 'ms_per_step': t / args.steps,
+                      'tflops_algorithmic': flops / (t / 1e3) / 1e12 if t > 0 else None}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.4 PF (B200_PROFILING.md)'
+    dom = max(kern, key=lambda k: kern[k]['ms_per_step']) if kern else None
+    roofline = None
+    if dom:
+        a = kern[dom]['tflops_algorithmic']
+        roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': a, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                    'frac': a / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                    'share_of_step': kern[dom]['ms_per_step'] / (ms / args.steps), 'kernels': kern,
+                    'note': 'fp32 SIMT implicit GEMM (exact-parity path) measured against the bf16 tensor-core peak'}
+
+    # ---- end-to-end through the public API with HOST buffers (e2e)
+    def e2e_step(i):
+        hb = host[i % 2]
+        x = hb[0].to(dev, non_blocking=True)
+        metax = hb[1].to(dev, non_blocking=True)
+        mask = hb[2].to(dev, non_blocking=True)
+        loss = step(x, metax, mask, hb[3])   # target stays on the host, as in train_meta.py:211
+        return loss.item()                    # device -> host read of the step's result
+    e2e_step(0)
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = global_batch * args.steps / (ms_e2e / 1e3)
+
+    # ---- build_targets ms/batch (decode output -> 9 target tensors + counters, device resident)
+    nB = B * ncls
+    G = side // 32
+    pred = torch.rand(nB * 5 * G * G, 4, device=dev) * 3 + 0.1
+    tgt_dev = resident[0][3].view(nB, 250)
+    anchors = model.anchors
+    for _ in range(3):
+        build_targets(pred, tgt_dev, anchors, 5, 1, G, G, 1.0, 5.0, 0.6, 20000, sync=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        build_targets(pred, tgt_dev, anchors, 5, 1, G, G, 1.0, 5.0, 0.6, 20000, sync=False)
+    e1.record()
+    torch.cuda.synchronize()
+    bt_gpu_ms = e0.elapsed_time(e1) / 20
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    bt_cpu_ms = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cstep, cstate = cpu_step_factory(ncls, side, args.ref_batch, threads)
+        t0 = time.perf_counter()
+        cstep()
+        dt = time.perf_counter() - t0
+        cpu_baseline = {'value': args.ref_batch / dt, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                        'sample': '1 full training step of %d query + %d support images at %dx%d (oracle port: torch-CPU '
+                                  'ops + Python build_targets), no warm-up' % (args.ref_batch, ncls, side, side)}
+        bt_cpu_ms = cpu_build_targets_ms(B, ncls, G)
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'configs[1]: darknet_dynamic + reweighting_net base-train step (fwd + RegionLossV2 + bwd + '
+                               'SGD), %dx%d, %d classes, 5 anchors' % (side, side, ncls),
+                   'batch_per_gpu': B, 'global_batch': global_batch, 'n_cls': ncls, 'neg': 'full',
+                   'parallelism': 'dp%d' % world, 'weights': 'seeded random init (no checkpoint offline)',
+                   'l2': 'inputs larger than L2: ~%.1f GB of activations are streamed per step (L2 = 126 MB)'
+                         % (B * 105e6 / 1e9)},
+        'e2e': {'value': e2e_value, 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
+                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': roofline,
+        'cpu_baseline': cpu_baseline,
+        'build_targets_ms': {'gpu': bt_gpu_ms, 'cpu_oracle': bt_cpu_ms, 'rows': nB, 'grid': G},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

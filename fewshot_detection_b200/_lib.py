@@ -4,6 +4,7 @@ There is NO fallback: if the shared library is missing or a symbol cannot be
 resolved the import fails loudly.  `call(name, *args)` raises RuntimeError with
 `fsdet_last_error()` on a non-zero return code.
 """
+import collections
 import ctypes
 import os
 
@@ -73,7 +74,11 @@ def last_error():
     return e.decode() if e else ''
 
 
+CALLS = collections.Counter()  # C-ABI calls made so far, by entry point (bench.py's gpu_launches)
+
+
 def call(name, *args):
+    CALLS[name] += 1
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError('%s failed (rc=%d): %s' % (name, rc, last_error()))

@@ -41,6 +41,23 @@ __global__ void __launch_bounds__(1024) colsum_double_kernel(const float* __rest
     }
 }
 
+// same reduction over double-precision partial rows (backward pass)
+__global__ void __launch_bounds__(1024) colsum_dd_kernel(const double* __restrict__ part, int nparts, int ncols,
+                                                         double* __restrict__ out) {
+    __shared__ double red[32][33];
+    int col = blockIdx.x * 32 + threadIdx.x;
+    double s = 0.0;
+    if (col < ncols)
+        for (int r = threadIdx.y; r < nparts; r += 32) s += part[(long long)r * ncols + col];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < ncols) {
+        double t = 0.0;
+        for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
+        out[col] = t;
+    }
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float momentum, float eps, float* __restrict__ mean,
@@ -143,9 +160,9 @@ struct BwdArgs {
     const float* shift;
     const float* mean;
     const float* invstd;
-    const float* coef;
+    const double* coef;
     float* dz;
-    float* partial;
+    double* partial;
     int ldz, ld_dyf, ld_dyp, lddz;
     int B, H, W, C;
     float slope;
@@ -162,14 +179,21 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BwdArgs a) {
     const int c = cv * 4;
     const long long nwin = (long long)a.B * H2 * W2;
 
-    float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0), mu = sh, is = sc, c1 = sh, c2 = sh;
+    // The BN-backward projection dz = scale*(du - mean(du) - xhat*mean(du*xhat)) cancels heavily when du is
+    // dominated by its per-channel mean; sums, coefficients and the combination are therefore carried in
+    // float64 (as torch's CPU batch_norm_backward does through acc_type<float> = double).
+    float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0), mu = sh, is = sc;
+    double c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};
     if (cok) {
         sc = ldg4(a.scale + c);
         sh = ldg4(a.shift + c);
         if (a.has_bn) { mu = ldg4(a.mean + c); is = ldg4(a.invstd + c); }
-        if (APPLY && a.has_bn) { c1 = ldg4(a.coef + c); c2 = ldg4(a.coef + a.C + c); }
+        if (APPLY && a.has_bn) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { c1[k] = a.coef[c + k]; c2[k] = a.coef[a.C + c + k]; }
+        }
     }
-    float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
 
     for (long long wi = (long long)blockIdx.x * blockDim.y + threadIdx.y; cok && wi < nwin;
          wi += (long long)gridDim.x * blockDim.y) {
@@ -229,14 +253,12 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BwdArgs a) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float d = du[q][k] * (yv[q][k] > 0.f ? 1.f : a.slope);
-                float xh = (zv[q][k] - muv[k]) * isv[k];
+                double xh = ((double)zv[q][k] - (double)muv[k]) * (double)isv[k];
                 if (APPLY) {
-                    o[k] = a.has_bn ? scv[k] * (d - (k == 0 ? c1.x : k == 1 ? c1.y : k == 2 ? c1.z : c1.w) -
-                                                xh * (k == 0 ? c2.x : k == 1 ? c2.y : k == 2 ? c2.z : c2.w))
-                                    : d;
+                    o[k] = a.has_bn ? (float)((double)scv[k] * ((double)d - c1[k] - xh * c2[k])) : d;
                 } else {
-                    s1[k] += d;
-                    s2[k] += d * xh;
+                    s1[k] += (double)d;
+                    s2[k] += (double)d * xh;
                 }
             }
             if (APPLY) *reinterpret_cast<float4*>(a.dz + pix[q] * a.lddz + c) = make_float4(o[0], o[1], o[2], o[3]);
@@ -245,36 +267,36 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BwdArgs a) {
 
     if (!APPLY) {
         // reduce over threadIdx.y -> one partial row per blockIdx.x
-        extern __shared__ float red[];  // [blockDim.y][TC*8]
-        float* mine = red + ((size_t)threadIdx.y * TC + threadIdx.x) * 8;
+        extern __shared__ double red[];  // [blockDim.y][TC*8]
+        double* mine = red + ((size_t)threadIdx.y * TC + threadIdx.x) * 8;
 #pragma unroll
         for (int k = 0; k < 4; ++k) { mine[k] = s1[k]; mine[4 + k] = s2[k]; }
         __syncthreads();
         if (threadIdx.y == 0 && cok) {
-            float t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
+            double t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
             for (int r = 0; r < blockDim.y; ++r) {
-                const float* o = red + ((size_t)r * TC + threadIdx.x) * 8;
+                const double* o = red + ((size_t)r * TC + threadIdx.x) * 8;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { t1[k] += o[k]; t2[k] += o[4 + k]; }
             }
-            float* dst = a.partial + (long long)blockIdx.x * 2 * a.C;
-            *reinterpret_cast<float4*>(dst + c) = make_float4(t1[0], t1[1], t1[2], t1[3]);
-            *reinterpret_cast<float4*>(dst + a.C + c) = make_float4(t2[0], t2[1], t2[2], t2[3]);
+            double* dst = a.partial + (long long)blockIdx.x * 2 * a.C;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { dst[c + k] = t1[k]; dst[a.C + c + k] = t2[k]; }
         }
     }
 }
 
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
                                        const float* __restrict__ invstd, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ coef, int C, int has_bn) {
+                                       float* __restrict__ dbeta, double* __restrict__ coef, int C, int has_bn) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double sdu = sums[c], sdux = sums[C + c];
     if (dbeta) dbeta[c] = (float)sdu;
     if (has_bn) {
         if (dgamma) dgamma[c] = (float)sdux;
-        coef[c] = (float)(sdu / count);
-        coef[C + c] = (float)(sdux / count);
+        coef[c] = sdu / count;
+        coef[C + c] = sdux / count;
     }
 }
 
@@ -352,7 +374,7 @@ static int launch_bwd(bool apply, const BwdArgs& a, cudaStream_t s) {
     if (apply) {
         bn_act_bwd_kernel<true><<<grid, block, 0, s>>>(a);
     } else {
-        size_t smem = (size_t)TY * TC * 8 * sizeof(float);  // 8 KB
+        size_t smem = (size_t)TY * TC * 8 * sizeof(double);  // 16 KB
         bn_act_bwd_kernel<false><<<grid, block, smem, s>>>(a);
     }
     return launch_status(apply ? "bn_act_bwd_apply" : "bn_act_bwd_reduce");
@@ -360,7 +382,7 @@ static int launch_bwd(bool apply, const BwdArgs& a, cudaStream_t s) {
 
 extern "C" int fsdet_bn_act_bwd_reduce(const float* z, int ldz, const float* dy_full, int ld_dyf, const float* dy_pool,
                                        int ld_dyp, const float* scale, const float* shift, const float* mean,
-                                       const float* invstd, float slope, float* partial, int B, int H, int W, int C,
+                                       const float* invstd, float slope, double* partial, int B, int H, int W, int C,
                                        int has_bn, void* stream) {
     FSDET_CHECK_ARG(z && scale && shift && partial && (dy_full || dy_pool), "bn_act_bwd_reduce: null pointer");
     FSDET_CHECK_ARG(!has_bn || (mean && invstd), "bn_act_bwd_reduce: BN needs mean/invstd");
@@ -372,14 +394,14 @@ extern "C" int fsdet_bn_act_bwd_reduce(const float* z, int ldz, const float* dy_
     return launch_bwd(false, a, (cudaStream_t)stream);
 }
 
-extern "C" int fsdet_bn_bwd_finalize(const float* partial, int nparts, double count, const float* gamma,
-                                     const float* invstd, float* dgamma, float* dbeta, float* coef, int C, int has_bn,
+extern "C" int fsdet_bn_bwd_finalize(const double* partial, int nparts, double count, const float* gamma,
+                                     const float* invstd, float* dgamma, float* dbeta, double* coef, int C, int has_bn,
                                      void* stream) {
     FSDET_CHECK_ARG(partial && nparts > 0 && C > 0 && (!has_bn || coef), "bn_bwd_finalize: bad args");
     cudaStream_t s = (cudaStream_t)stream;
-    double* sums = sums_area(partial, nparts, C);
+    double* sums = const_cast<double*>(partial) + (size_t)nparts * 2 * C;  // the extra row
     dim3 block(32, 32), grid(ceil_div(2 * C, 32));
-    colsum_double_kernel<<<grid, block, 0, s>>>(partial, nparts, 2 * C, sums);
+    colsum_dd_kernel<<<grid, block, 0, s>>>(partial, nparts, 2 * C, sums);
     int st = launch_status("bn_bwd_finalize/colsum");
     if (st) return st;
     bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(sums, count, gamma, invstd, dgamma, dbeta, coef, C, has_bn);
@@ -388,7 +410,7 @@ extern "C" int fsdet_bn_bwd_finalize(const float* partial, int nparts, double co
 
 extern "C" int fsdet_bn_act_bwd_apply(const float* z, int ldz, const float* dy_full, int ld_dyf, const float* dy_pool,
                                       int ld_dyp, const float* scale, const float* shift, const float* mean,
-                                      const float* invstd, const float* coef, float slope, float* dz, int lddz, int B,
+                                      const float* invstd, const double* coef, float slope, float* dz, int lddz, int B,
                                       int H, int W, int C, int has_bn, void* stream) {
     FSDET_CHECK_ARG(z && scale && shift && dz && (dy_full || dy_pool), "bn_act_bwd_apply: null pointer");
     FSDET_CHECK_ARG(!has_bn || (mean && invstd && coef), "bn_act_bwd_apply: BN needs mean/invstd/coef");

@@ -32,6 +32,13 @@ def _round_up(v, m):
     return (v + m - 1) // m * m
 
 
+def same_layout(a, b):
+    """Same shape and same strides on every dimension of extent > 1."""
+    if a.shape != b.shape:
+        return False
+    return all(sa == sb for n, sa, sb in zip(a.shape, a.stride(), b.stride()) if n > 1)
+
+
 class Act(object):
     """A view [B*H*W pixels] x [C channels at column `off`] of a 2-D NHWC buffer."""
     __slots__ = ('buf', 'off', 'C', 'B', 'H', 'W', 'g', 'needs_grad', 'parent')
@@ -213,6 +220,8 @@ class NetRunner(object):
         self.models = models  # nn.ModuleList aligned with spec.idx
         self.specs, self.out_ch, self.placement, self.in_ch = compile_blocks(blocks)
         self.in_cpad = _round_up(self.in_ch, 4)
+        self.grad_hook = None   # optional callable(param) invoked when a parameter gradient has been enqueued
+        self.profile = None     # optional dict name -> [flops, [(start_event, end_event), ...]]
 
     # -- helpers ---------------------------------------------------------
     @staticmethod
@@ -233,13 +242,34 @@ class NetRunner(object):
             w.data = w.data.contiguous(memory_format=torch.channels_last)
         return w
 
+    def _done(self, *params):
+        if self.grad_hook is not None:
+            for p in params:
+                if p is not None:
+                    self.grad_hook(p)
+
+    def _timed(self, name, flops, fn, *args):
+        """call() bracketed by CUDA events on the launching stream when profiling."""
+        if self.profile is None:
+            return call(fn, *args)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call(fn, *args)
+        e1.record()
+        ent = self.profile.setdefault(name, [0.0, []])
+        ent[0] += flops
+        ent[1].append((e0, e1))
+
     @staticmethod
     def _param_grad(p):
         """Returns (tensor to write the gradient into, finish callback)."""
+        if p.grad is not None and getattr(p, '_fsdet_overwrite', False) and same_layout(p.grad, p):
+            return p.grad, None
         if p.grad is None:
             p.grad = torch.empty_like(p)  # preserve_format: same (OHWI) strides as p
             return p.grad, None
-        if p.grad.stride() != p.stride():
+        if not same_layout(p.grad, p):
             p.grad = p.grad.contiguous(memory_format=torch.channels_last if p.dim() == 4 else torch.contiguous_format)
         tmp = torch.empty_like(p)
         return tmp, (lambda: p.grad.add_(tmp))
@@ -387,7 +417,8 @@ class NetRunner(object):
             use_batch_stats = training or not bn.track_running_stats
             rows = _lib.lib.fsdet_conv_stat_rows(npix)
             stat = _empty(rows + 2, 2 * s.cout, device=dev) if use_batch_stats else None
-            call('fsdet_conv_fwd', x.ptr, x.ld, ptr(wuse), None, z.ptr, z.ld, ptr(stat), B, H, W, cin_p, s.cout, s.k, 0, st)
+            self._timed('conv_igemm', 2.0 * npix * s.cout * kk * cin_p, 'fsdet_conv_fwd', x.ptr, x.ld, ptr(wuse), None,
+                        z.ptr, z.ld, ptr(stat), B, H, W, cin_p, s.cout, s.k, 0, st)
             vec = _empty(4, s.cout, device=dev)  # mean, invstd, scale, shift
             upd = training and bn.track_running_stats
             call('fsdet_bn_finalize', ptr(stat), rows, float(npix), ptr(bn.weight), ptr(bn.bias),
@@ -421,7 +452,8 @@ class NetRunner(object):
             wp = wuse
             bp = conv.bias
         z = Act.new(B, H, W, cout_p, dev)
-        call('fsdet_conv_fwd', x.ptr, x.ld, ptr(wp), ptr(bp), z.ptr, z.ld, None, B, H, W, cin_p, cout_p, s.k, 0, st)
+        self._timed('conv_igemm', 2.0 * npix * cout_p * kk * cin_p, 'fsdet_conv_fwd', x.ptr, x.ld, ptr(wp), ptr(bp), z.ptr,
+                    z.ld, None, B, H, W, cin_p, cout_p, s.k, 0, st)
         ones = zeros = None
         if s.slope != 1.0:
             ones = torch.ones(cout_p, device=dev)
@@ -464,7 +496,8 @@ class NetRunner(object):
         beff = _empty(Npad, device=dev)
         call('fsdet_head_weff', ptr(W), ptr(conv.bias), ptr(rw2), ptr(weff), ptr(beff), n_cls, O, K, Npad, st)
         z = Act.new(x.B, x.H, x.W, Npad, dev)
-        call('fsdet_conv_fwd', x.ptr, x.ld, ptr(weff), ptr(beff), z.ptr, z.ld, None, x.B, x.H, x.W, K, Npad, 1, 0, st)
+        self._timed('conv_igemm', 2.0 * x.npix * Npad * K, 'fsdet_conv_fwd', x.ptr, x.ld, ptr(weff), ptr(beff), z.ptr, z.ld,
+                    None, x.B, x.H, x.W, K, Npad, 1, 0, st)
         out = _empty(x.B * n_cls, O, x.H, x.W, device=dev)
         call('fsdet_nhwc_to_nchw', z.ptr, z.ld, None, ptr(out), x.B, N, x.H * x.W, st)
         rec = ('head', s, head, x, rw2, weff, conv, n_cls, O, Npad)
@@ -544,13 +577,15 @@ class NetRunner(object):
         wt = _empty(cin_p, kk, cout, device=dev)
         call('fsdet_weight_flip_transpose', ptr(w_ohwi), ptr(wt), cout, kk, cin_p, st)
         g, acc = x.grad_for_write()
-        call('fsdet_conv_fwd', dz.ptr, dz.ld, ptr(wt), None, g.ptr, g.ld, None, x.B, x.H, x.W, cout, cin_p, k, acc, st)
+        self._timed('conv_igemm', 2.0 * x.npix * cout * kk * cin_p, 'fsdet_conv_fwd', dz.ptr, dz.ld, ptr(wt), None, g.ptr,
+                    g.ld, None, x.B, x.H, x.W, cout, cin_p, k, acc, st)
 
     def _wgrad(self, x, dz, out_tensor, cin_p, cout, k, st):
         dev = x.buf.device
         nws = _lib.lib.fsdet_conv_wgrad_workspace_floats(x.B, x.H, x.W, cin_p, cout, k)
         ws = _empty(max(nws, 4), device=dev)
-        call('fsdet_conv_wgrad', x.ptr, x.ld, dz.ptr, dz.ld, ptr(out_tensor), ptr(ws), nws, x.B, x.H, x.W, cin_p, cout, k, st)
+        self._timed('conv_wgrad', 2.0 * x.npix * cout * k * k * cin_p, 'fsdet_conv_wgrad', x.ptr, x.ld, dz.ptr, dz.ld,
+                    ptr(out_tensor), ptr(ws), nws, x.B, x.H, x.W, cin_p, cout, k, st)
 
     def _convbn_bwd(self, rec, st):
         _, s, x, wuse, z, vec, full, pooled, conv, bn = rec
@@ -567,10 +602,11 @@ class NetRunner(object):
             for f in (fin_w, fin_g, fin_b):
                 if f:
                     f()
+            self._done(conv.weight, bn.weight, bn.bias)
             return
         rows = _lib.lib.fsdet_bn_bwd_rows(B, H, W)
-        part = _empty(rows + 2, 2 * s.cout, device=dev)
-        coef = _empty(2, s.cout, device=dev)
+        part = _empty(rows + 1, 2 * s.cout, dtype=torch.float64, device=dev)
+        coef = _empty(2, s.cout, dtype=torch.float64, device=dev)
         a_gf = (gf.ptr, gf.ld) if gf is not None else (None, 0)
         a_gp = (gp.ptr, gp.ld) if gp is not None else (None, 0)
         call('fsdet_bn_act_bwd_reduce', z.ptr, z.ld, a_gf[0], a_gf[1], a_gp[0], a_gp[1], ptr(vec[2]), ptr(vec[3]),
@@ -587,10 +623,11 @@ class NetRunner(object):
             call('fsdet_pad_channels', ptr(gwp), cin_p, ptr(gw), s.cin, s.cout * s.k * s.k, st)
         else:
             self._wgrad(x, dz, gw, cin_p, s.cout, s.k, st)
-        self._dgrad(x, dz, wuse, cin_p, s.cout, s.k, st)
         for f in (fin_w, fin_g, fin_b):
             if f:
                 f()
+        self._done(conv.weight, bn.weight, bn.bias)
+        self._dgrad(x, dz, wuse, cin_p, s.cout, s.k, st)
 
     def _convbias_bwd(self, rec, st):
         _, s, x, wp, z, onez, full, pooled, conv, cout_p = rec
@@ -607,13 +644,14 @@ class NetRunner(object):
             for f in (fin_w, fin_b):
                 if f:
                     f()
+            self._done(conv.weight, conv.bias)
             return
         ones, zeros = onez
         if ones is None:
             ones = torch.ones(cout_p, device=dev)
             zeros = torch.zeros(cout_p, device=dev)
         rows = _lib.lib.fsdet_bn_bwd_rows(B, H, W)
-        part = _empty(rows + 2, 2 * cout_p, device=dev)
+        part = _empty(rows + 1, 2 * cout_p, dtype=torch.float64, device=dev)
         dbp = _empty(cout_p, device=dev)
         a_gf = (gf.ptr, gf.ld) if gf is not None else (None, 0)
         a_gp = (gp.ptr, gp.ld) if gp is not None else (None, 0)
@@ -637,10 +675,11 @@ class NetRunner(object):
             gw.permute(0, 2, 3, 1).copy_(gwp[:s.cout].view(s.cout, s.k, s.k, cin_p))
         if gb is not None:
             gb.copy_(dbp[:s.cout])
-        self._dgrad(x, dz, wp, cin_p, cout_p, s.k, st)
         for f in (fin_w, fin_b):
             if f:
                 f()
+        self._done(conv.weight, conv.bias)
+        self._dgrad(x, dz, wp, cin_p, cout_p, s.k, st)
 
     def _head_bwd(self, rec, gout, st):
         _, s, head, x, rw2, weff, conv, n_cls, O, Npad = rec
@@ -660,10 +699,11 @@ class NetRunner(object):
         self._wgrad(x, dzh, dweff, K, Npad, 1, st)
         drw = _empty(n_cls, K, device=dev)
         call('fsdet_head_param_grads', ptr(dweff), ptr(conv.weight), ptr(rw2), ptr(gw), ptr(drw), n_cls, O, K, st)
-        self._dgrad(x, dzh, weff, K, Npad, 1, st)
         for f in (fin_w, fin_b):
             if f:
                 f()
+        self._done(conv.weight, conv.bias)
+        self._dgrad(x, dzh, weff, K, Npad, 1, st)
         return drw
 
 

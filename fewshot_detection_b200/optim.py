@@ -10,6 +10,7 @@ pointwise passes per tensor.  State: `state[p]['momentum_buffer']`, as torch.
 import torch
 
 from ._lib import call, ptr
+from .engine import same_layout
 
 _CHUNK = 65536
 
@@ -55,26 +56,22 @@ class FusedSGD(torch.optim.Optimizer):
                 loss = closure()
         st = torch.cuda.current_stream().cuda_stream
         for gi, group in enumerate(self.param_groups):
-            for first in (True, False):
-                plist = []
-                for p in group['params']:
-                    if p.grad is None:
-                        continue
-                    if not p.is_cuda:
-                        raise TypeError('FusedSGD updates CUDA parameters only (no CPU fallback)')
-                    is_first = 'momentum_buffer' not in self.state[p]
-                    if is_first != first:
-                        continue
-                    if p.grad.stride() != p.stride():
-                        p.grad = p.grad.contiguous(
-                            memory_format=torch.channels_last if p.is_contiguous(memory_format=torch.channels_last)
-                            and p.dim() == 4 else torch.contiguous_format)
-                    plist.append(p)
+            fresh, seasoned = [], []
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda:
+                    raise TypeError('FusedSGD updates CUDA parameters only (no CPU fallback)')
+                if not same_layout(p.grad, p):
+                    p.grad = p.grad.contiguous(
+                        memory_format=torch.channels_last if p.is_contiguous(memory_format=torch.channels_last)
+                        and p.dim() == 4 else torch.contiguous_format)
+                (fresh if 'momentum_buffer' not in self.state[p] else seasoned).append(p)
+            for p in fresh:
+                self.state[p]['momentum_buffer'] = torch.empty_like(p)
+            for first, plist in ((True, fresh), (False, seasoned)):
                 if not plist:
                     continue
-                if first:
-                    for p in plist:
-                        self.state[p]['momentum_buffer'] = torch.empty_like(p)
                 tab = self._table((gi, first), plist)
                 call('fsdet_sgd_step', ptr(tab['params']), ptr(tab['grads']), ptr(tab['moms']), ptr(tab['sizes']),
                      ptr(tab['chunk_tensor']), ptr(tab['chunk_offset']), tab['n_chunks'], _CHUNK, float(group['lr']),

@@ -95,21 +95,24 @@ int fsdet_bn_act_fwd(const float* z, int ldz, const float* scale, const float* s
                      int ld_full, float* y_pool, int ld_pool, int B, int H, int W, int C, void* stream);
 /* Backward of the block above.  dy_full / dy_pool: gradients w.r.t. the two
  * outputs (either may be NULL).  Pass 1 reduces  sum(du), sum(du*xhat) into
- * partials float [fsdet_bn_bwd_rows(B,H,W) + 2][2*C] (two scratch rows for
- * the double-precision totals of fsdet_bn_bwd_finalize); pass 2 (after
- * fsdet_bn_bwd_finalize) writes dz.  With has_bn == 0 (conv + bias + act):
- * xhat terms are skipped, dbeta = bias gradient and dz = du. */
+ * partials double [fsdet_bn_bwd_rows(B,H,W) + 1][2*C] (the extra row receives
+ * the totals in fsdet_bn_bwd_finalize); pass 2 (after fsdet_bn_bwd_finalize)
+ * writes dz.  Sums, coefficients and the projection
+ * dz = scale*(du - mean(du) - xhat*mean(du*xhat)) are evaluated in float64: the
+ * projection cancels heavily and float32 sums lose 2-3 digits there (torch's
+ * CPU kernel uses double accumulators for the same reason).  With has_bn == 0
+ * (conv + bias + act): xhat terms are skipped, dbeta = bias gradient, dz = du. */
 int fsdet_bn_act_bwd_reduce(const float* z, int ldz, const float* dy_full, int ld_dyf, const float* dy_pool,
                             int ld_dyp, const float* scale, const float* shift, const float* mean,
-                            const float* invstd, float slope, float* partial, int B, int H, int W, int C,
+                            const float* invstd, float slope, double* partial, int B, int H, int W, int C,
                             int has_bn, void* stream);
 int fsdet_bn_bwd_rows(int B, int H, int W);
 /* dgamma, dbeta and the two per-channel coefficients used by the apply pass */
-int fsdet_bn_bwd_finalize(const float* partial, int nparts, double count, const float* gamma, const float* invstd,
-                          float* dgamma, float* dbeta, float* coef /* [2*C] */, int C, int has_bn, void* stream);
+int fsdet_bn_bwd_finalize(const double* partial, int nparts, double count, const float* gamma, const float* invstd,
+                          float* dgamma, float* dbeta, double* coef /* [2*C] */, int C, int has_bn, void* stream);
 int fsdet_bn_act_bwd_apply(const float* z, int ldz, const float* dy_full, int ld_dyf, const float* dy_pool,
                            int ld_dyp, const float* scale, const float* shift, const float* mean,
-                           const float* invstd, const float* coef, float slope, float* dz, int lddz, int B, int H,
+                           const float* invstd, const double* coef, float slope, float* dz, int lddz, int B, int H,
                            int W, int C, int has_bn, void* stream);
 
 /* ---- stand-alone pooling / reorg / route (darknet_meta.py:47-74,157-171) */

@@ -10,6 +10,13 @@ for p in (ROOT, os.path.join(ROOT, 'tests', 'golden')):
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
+try:  # torch reference ops must be true fp32 (cuDNN/cuBLAS default to TF32 for convs)
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+except Exception:  # pragma: no cover
+    pass
+
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: test needs a CUDA device (run on the B200 box with -m gpu)')

@@ -145,8 +145,8 @@ def test_bn_act_pool_fwd_bwd(L, B, H, W, C, pool, full):
     if pool:
         gp = nhwc(gouts[gi])
     rows = L.lib.fsdet_bn_bwd_rows(B, H, W)
-    part = torch.empty(rows + 2, 2 * C, device='cuda')
-    coef = torch.empty(2, C, device='cuda')
+    part = torch.empty(rows + 1, 2 * C, dtype=torch.float64, device='cuda')
+    coef = torch.empty(2, C, dtype=torch.float64, device='cuda')
     dgam, dbet = torch.empty(C, device='cuda'), torch.empty(C, device='cuda')
     a = (zb.data_ptr(), C, gf.data_ptr() if full else None, C, gp.data_ptr() if pool else None, C, vec[2].data_ptr(),
          vec[3].data_ptr(), vec[0].data_ptr(), vec[1].data_ptr())
