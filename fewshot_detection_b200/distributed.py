@@ -28,7 +28,8 @@ class GradAllReducer(object):
         # backward produces gradients roughly in reverse parameter order:
         # lay the flat buffer out in that order so that buckets fill front to back
         order = list(reversed(self.params))
-        total = sum(p.numel() for p in order)
+        align = 32  # floats: every gradient view starts on a 128-byte boundary (kernels need 16-byte alignment)
+        total = sum((p.numel() + align - 1) // align * align for p in order)
         dev = order[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.bucket_of = {}
@@ -46,7 +47,7 @@ class GradAllReducer(object):
             p.grad = g
             p._fsdet_overwrite = True  # the engine may overwrite .grad in place (no accumulate)
             self.bucket_of[id(p)] = len(self.buckets)
-            off += n
+            off += (n + align - 1) // align * align
             cur_n += 1
             if off - cur_start >= cap:
                 self.buckets.append([cur_start, off, cur_n, cur_n])
