@@ -28,6 +28,12 @@ SIGNATURES = {
     'fsdet_conv_wgrad_workspace_floats': ('iiiiii', 'z'),
     'fsdet_weight_flip_transpose': ('ppiiip', 'i'),
     'fsdet_pad_channels': ('pipizp', 'i'),
+    'fsdet_conv_tc_supported': ('iii', 'i'),
+    'fsdet_conv_tc_fwd': ('pppppiiiiiiiip', 'i'),
+    'fsdet_split_bf16': ('piizppp', 'i'),
+    'fsdet_colstats': ('pizipp', 'i'),
+    'fsdet_colstats_rows': ('z', 'i'),
+    'fsdet_debug_im2col_tile': ('piiiiiqiipp', 'i'),
     'fsdet_bn_finalize': ('pidppppffppppiip', 'i'),
     'fsdet_bn_act_fwd': ('pippfpipiiiiip', 'i'),
     'fsdet_bn_act_bwd_reduce': ('pipipippppfpiiiiip', 'i'),

@@ -1,0 +1,499 @@
+// tcgen05 implicit-GEMM convolution for sm_100a (forward and input-gradient).
+//
+//   z[p][n] = sum_{tap,ci} x[p+tap][ci] * w[n][tap][ci]      (stride 1, "same" padding, k in {1,3})
+//
+// Tensor-core path of nn.Conv2d (darknet_meta.py:236-252) for every layer with Cin % 64 == 0.
+//
+// Precision: the reference is fp32 end to end and the parity bar is 1e-3 relative through a 23-layer
+// train-mode-BN stack, which single-pass bf16/tf32 operands do not meet.  Operands are therefore split into
+// two bf16 planes (hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits, the same 4 B/element as fp32) and
+// each K step issues three MMAs  Ahi*Bhi + Alo*Bhi + Ahi*Blo  into one fp32 TMEM accumulator ("3xBF16").
+//
+// Structure (one CTA = one 128-pixel x BN-channel output tile, 192 threads):
+//   warp 0   : TMA producer.  A tiles come straight from the NHWC activation planes through an *im2col*
+//              tensor map (cp.async.bulk.tensor.4d...im2col: 128 consecutive output pixels x 64 channels of
+//              one filter tap, zero-filled halo), B tiles from the [Cout][K] weight planes (2-D tiled map);
+//              both land in shared memory in the 128-byte-swizzled K-major layout tcgen05 consumes.
+//   warp 1   : allocates TMEM, issues tcgen05.mma (one elected thread), commits to mbarriers.
+//   warps 2-5: epilogue, tcgen05.ld the fp32 accumulator (lane = pixel) and store z rows.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace fsdet {
+
+// ------------------------------------------------------------------ operand split
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ src, int ld, int C4, long long rows,
+                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * C4) return;
+    long long r = i / C4;
+    int c = (int)(i - r * C4) * 4;
+    float4 v = ldg4(src + r * ld + c);
+    float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        h[k] = __float2bfloat16_rn(f[k]);
+        l[k] = __float2bfloat16_rn(f[k] - __bfloat162float(h[k]));
+    }
+    long long o = r * (long long)(C4 * 4) + c;
+    *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(l);
+}
+
+// ------------------------------------------------------------------ column statistics of z (BN partials)
+// one CTA per strip of `strip` pixels: partial[blockIdx.x][c] = sum z, [C + c] = sum z^2
+__global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ z, int ld, long long npix, int C, int strip,
+                                                       float* __restrict__ part) {
+    // threads: x = channel vector lane (float4), y = pixel lane
+    const int C4 = C >> 2;
+    const int TC = blockDim.x, TY = blockDim.y;
+    long long p0 = (long long)blockIdx.x * strip, p1 = p0 + strip < npix ? p0 + strip : npix;
+    extern __shared__ float red[];  // [TY][TC*8]
+    for (int cv0 = 0; cv0 < C4; cv0 += TC) {
+        int cv = cv0 + threadIdx.x;
+        float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+        if (cv < C4)
+            for (long long p = p0 + threadIdx.y; p < p1; p += TY) {
+                float4 v = ldg4(z + p * ld + cv * 4);
+                s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+                q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+            }
+        float* mine = red + ((size_t)threadIdx.y * TC + threadIdx.x) * 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { mine[k] = s[k]; mine[4 + k] = q[k]; }
+        __syncthreads();
+        if (threadIdx.y == 0 && cv < C4) {
+            float ts[4] = {0, 0, 0, 0}, tq[4] = {0, 0, 0, 0};
+            for (int r = 0; r < TY; ++r) {
+                const float* o = red + ((size_t)r * TC + threadIdx.x) * 8;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { ts[k] += o[k]; tq[k] += o[4 + k]; }
+            }
+            float* dst = part + (long long)blockIdx.x * 2 * C;
+            *reinterpret_cast<float4*>(dst + cv * 4) = make_float4(ts[0], ts[1], ts[2], ts[3]);
+            *reinterpret_cast<float4*>(dst + C + cv * 4) = make_float4(tq[0], tq[1], tq[2], tq[3]);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h,
+                                                   int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (tile rows of 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);       // start address  [0,14)
+    d |= (uint64_t)1 << 16;                        // leading byte offset (ignored for swizzled K-major) [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows x 128 B            [32,46)
+    d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)               [46,48)
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B                                  [61,64)
+    return d;
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+        "%25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ the kernel
+struct TcArgs {
+    float* z;
+    int ldz;
+    int H, W, Cin, Cout, ks, pad;
+    long long M;  // B*H*W
+    int accumulate;
+};
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;                       // bf16 elements per stage row = 128 B
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB per plane
+
+template <int BN>
+struct TcCfg {
+    static constexpr int B_BYTES = BN * TC_BK * 2;
+    static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcArgs p) {
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x;
+    const long long m0 = (long long)blockIdx.y * TC_BM;
+    const int kchunks = p.Cin / TC_BK;
+    const int nk = p.ks * p.ks * kchunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmAhi);
+        tma_prefetch_desc(&tmAlo);
+        tma_prefetch_desc(&tmBhi);
+        tma_prefetch_desc(&tmBlo);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {  // whole warp: allocate BN fp32 accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int HW = p.H * p.W;
+            const int img = (int)(m0 / HW);
+            const int rem = (int)(m0 - (long long)img * HW);
+            const int ph = rem / p.W, pw = rem - ph * p.W;
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+                uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                const int tap = kb / kchunks;
+                const int c0 = (kb - tap * kchunks) * TC_BK;
+                const int r = tap / p.ks, sx = tap - r * p.ks;
+                tma_load_im2col_4d(st, &tmAhi, &full_bar[s], c0, pw - p.pad, ph - p.pad, img, (uint16_t)sx, (uint16_t)r);
+                tma_load_im2col_4d(st + TC_A_BYTES, &tmAlo, &full_bar[s], c0, pw - p.pad, ph - p.pad, img, (uint16_t)sx, (uint16_t)r);
+                tma_load_2d(st + 2 * TC_A_BYTES, &tmBhi, &full_bar[s], tap * p.Cin + c0, n_tile * BN);
+                tma_load_2d(st + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmBlo, &full_bar[s], tap * p.Cin + c0, n_tile * BN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint64_t ahi = umma_desc_k_sw128(sa), alo = umma_desc_k_sw128(sa + TC_A_BYTES);
+                const uint64_t bhi = umma_desc_k_sw128(sa + 2 * TC_A_BYTES), blo = umma_desc_k_sw128(sa + 2 * TC_A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 bf16 = 32 B along K inside the swizzle atom
+                    umma_bf16(tmem_base, ahi + adv, bhi + adv, idesc, (kb | k) ? 1u : 0u);
+                    umma_bf16(tmem_base, alo + adv, bhi + adv, idesc, 1u);
+                    umma_bf16(tmem_base, ahi + adv, blo + adv, idesc, 1u);
+                }
+                umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);      // accumulator complete
+        }
+    } else {
+        // epilogue warps 2..5 -> TMEM lane quarters (warp % 4)
+        const int quarter = warp & 3;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const long long m = m0 + quarter * 32 + lane;
+        const bool row_ok = m < p.M;
+        float* zr = p.z + (row_ok ? m : 0) * p.ldz;
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32, r);
+            const int n0 = n_tile * BN + ch * 32;
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = n0 + j;
+                    if (n + 3 < p.Cout) {
+                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                               __uint_as_float(r[j + 3]));
+                        if (p.accumulate) {
+                            float4 o = *reinterpret_cast<const float4*>(zr + n);
+                            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                        }
+                        *reinterpret_cast<float4*>(zr + n) = v;
+                    } else {
+                        for (int t = 0; t < 4; ++t)
+                            if (n + t < p.Cout) zr[n + t] = __uint_as_float(r[j + t]) + (p.accumulate ? zr[n + t] : 0.f);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+    }
+}
+
+// debug: dump one im2col A tile (un-swizzled) to global memory
+__global__ void __launch_bounds__(128) debug_im2col_kernel(const __grid_constant__ CUtensorMap tmA, int H, int W, int pad, long long m0,
+                                                           int c0, int tap, int ks, uint16_t* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TC_A_BYTES);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int HW = H * W;
+        const int img = (int)(m0 / HW);
+        const int rem = (int)(m0 - (long long)img * HW);
+        const int ph = rem / W, pw = rem - ph * W;
+        mbar_expect_tx(bar, TC_A_BYTES);
+        const int r = tap / ks, sx = tap - r * ks;
+        tma_load_im2col_4d(smem, &tmA, bar, c0, pw - pad, ph - pad, img, (uint16_t)sx, (uint16_t)r);
+    }
+    mbar_wait(bar, 0);
+    // row = threadIdx.x; un-swizzle: 16-byte chunk j of row r is stored at chunk (j ^ (r & 7))
+    const int row = threadIdx.x;
+    for (int j = 0; j < 8; ++j) {
+        const uint4 v = *reinterpret_cast<const uint4*>(smem + row * 128 + ((j ^ (row & 7)) << 4));
+        *reinterpret_cast<uint4*>(out + row * 64 + j * 8) = v;
+    }
+}
+
+// ------------------------------------------------------------------ host side: tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled g_encodeTiled = nullptr;
+static PFN_encodeIm2col g_encodeIm2col = nullptr;
+
+static int load_driver_fns() {
+    if (g_encodeTiled && g_encodeIm2col) return 0;
+    void* f1 = nullptr;
+    void* f2 = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f1, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !f1) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return -2;
+    }
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f2, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !f2) {
+        set_error("cuTensorMapEncodeIm2col entry point unavailable");
+        return -2;
+    }
+    g_encodeTiled = (PFN_encodeTiled)f1;
+    g_encodeIm2col = (PFN_encodeIm2col)f2;
+    return 0;
+}
+
+// activation plane [B][H][W][C] bf16 -> im2col map: 128 pixels x 64 channels per load
+static int make_im2col_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int ks, int pixels) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const int pad = (ks - 1) / 2;
+    int lower[2] = {-pad, -pad};
+    int upper[2] = {pad - (ks - 1), pad - (ks - 1)};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encodeIm2col(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
+                                (cuuint32_t)TC_BK, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeIm2col failed (%d) for B=%d H=%d W=%d C=%d ks=%d", (int)r, B, H, W, C, ks);
+        return -3;
+    }
+    // Driver quirk handled the same way by CUTLASS (copy_traits_sm90_im2col.hpp): for tensors smaller than
+    // 128 KiB, drivers <= 13.1 set a bit that must be cleared.
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    if (drv <= 13010 && (size_t)B * H * W * C * 2 < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+    return 0;
+}
+
+// weight plane [rows][K] bf16 -> 2-D tiled map with box 64 x box_rows
+static int make_tiled_map(CUtensorMap* map, const void* base, long long rows, long long K, int box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld", (int)r, rows, K);
+        return -3;
+    }
+    return 0;
+}
+
+template <int BN>
+static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* w_hi, const void* w_lo, const TcArgs& a,
+                     cudaStream_t s) {
+    CUtensorMap b_hi, b_lo;
+    const long long K = (long long)a.ks * a.ks * a.Cin;
+    int rc = make_tiled_map(&b_hi, w_hi, a.Cout, K, BN);
+    if (rc) return rc;
+    rc = make_tiled_map(&b_lo, w_lo, a.Cout, K, BN);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr_done = true;
+    }
+    dim3 grid(ceil_div(a.Cout, BN), ceil_div(a.M, TC_BM));
+    conv_tc_kernel<BN><<<grid, 192, TcCfg<BN>::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, a);
+    return launch_status("conv_tc");
+}
+
+}  // namespace fsdet
+
+using namespace fsdet;
+
+extern "C" int fsdet_split_bf16(const float* src, int ld, int C, size_t rows, void* hi, void* lo, void* stream) {
+    FSDET_CHECK_ARG(src && hi && lo && C % 4 == 0 && ld % 4 == 0 && ld >= C, "split_bf16: C=%d ld=%d", C, ld);
+    FSDET_CHECK_ARG(aligned16(src) && ((uintptr_t)hi % 8 == 0) && ((uintptr_t)lo % 8 == 0), "split_bf16: alignment");
+    long long n = (long long)rows * (C / 4);
+    if (n == 0) return 0;
+    split_bf16_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, ld, C / 4, (long long)rows, (__nv_bfloat16*)hi,
+                                                                          (__nv_bfloat16*)lo);
+    return launch_status("split_bf16");
+}
+
+static const int kStatStrip = 256;
+extern "C" int fsdet_colstats_rows(size_t npix) { return ceil_div((long long)npix, kStatStrip); }
+
+extern "C" int fsdet_colstats(const float* z, int ld, size_t npix, int C, float* partial, void* stream) {
+    FSDET_CHECK_ARG(z && partial && C % 4 == 0 && ld % 4 == 0 && aligned16(z), "colstats: C=%d ld=%d", C, ld);
+    if (npix == 0) return 0;
+    int C4 = C / 4;
+    int TCx = C4 >= 32 ? 32 : (C4 >= 16 ? 16 : (C4 >= 8 ? 8 : (C4 >= 4 ? 4 : (C4 >= 2 ? 2 : 1))));
+    int TY = 256 / TCx;
+    dim3 block(TCx, TY);
+    size_t smem = (size_t)TY * TCx * 8 * sizeof(float);
+    colstats_kernel<<<fsdet_colstats_rows(npix), block, smem, (cudaStream_t)stream>>>(z, ld, (long long)npix, C, kStatStrip, partial);
+    return launch_status("colstats");
+}
+
+extern "C" int fsdet_conv_tc_supported(int Cin, int Cout, int ksize) {
+    return (Cin % TC_BK == 0) && (Cout >= 64) && (Cout % 4 == 0) && (ksize == 1 || ksize == 3);
+}
+
+extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* z, int ldz, int B,
+                                 int H, int W, int Cin, int Cout, int ksize, int accumulate, void* stream) {
+    FSDET_CHECK_ARG(x_hi && x_lo && w_hi && w_lo && z, "conv_tc_fwd: null pointer");
+    FSDET_CHECK_ARG(fsdet_conv_tc_supported(Cin, Cout, ksize), "conv_tc_fwd: unsupported Cin=%d Cout=%d k=%d", Cin, Cout, ksize);
+    FSDET_CHECK_ARG(ldz % 4 == 0 && aligned16(z) && aligned16(x_hi) && aligned16(x_lo) && aligned16(w_hi) && aligned16(w_lo),
+                    "conv_tc_fwd: alignment");
+    int rc = load_driver_fns();
+    if (rc) return rc;
+    TcArgs a;
+    a.z = z; a.ldz = ldz; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ks = ksize; a.pad = (ksize - 1) / 2;
+    a.M = (long long)B * H * W; a.accumulate = accumulate;
+    if (a.M == 0) return 0;
+    CUtensorMap a_hi, a_lo;
+    rc = make_im2col_map(&a_hi, x_hi, B, H, W, Cin, ksize, TC_BM);
+    if (rc) return rc;
+    rc = make_im2col_map(&a_lo, x_lo, B, H, W, Cin, ksize, TC_BM);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (Cout >= 128) return launch_tc<128>(a_hi, a_lo, w_hi, w_lo, a, s);
+    return launch_tc<64>(a_hi, a_lo, w_hi, w_lo, a, s);
+}
+
+extern "C" int fsdet_debug_im2col_tile(const void* x_plane, int B, int H, int W, int C, int ksize, long long m0, int c0, int tap,
+                                       void* out_tile, void* stream) {
+    int rc = load_driver_fns();
+    if (rc) return rc;
+    CUtensorMap m;
+    rc = make_im2col_map(&m, x_plane, B, H, W, C, ksize, TC_BM);
+    if (rc) return rc;
+    debug_im2col_kernel<<<1, 128, TC_A_BYTES + 1024 + 64, (cudaStream_t)stream>>>(m, H, W, (ksize - 1) / 2, m0, c0, tap, ksize,
+                                                                                 (uint16_t*)out_tile);
+    return launch_status("debug_im2col_tile");
+}

@@ -79,6 +79,27 @@ int fsdet_weight_flip_transpose(const float* w, float* wt, int Cout, int kk, int
 /* copy [rows][cin] -> [rows][cout] channel-padded / -cropped (zero fill) */
 int fsdet_pad_channels(const float* in, int cin, float* out, int cout, size_t rows, void* stream);
 
+/* ---- tensor-core convolution (tcgen05 + TMA im2col), csrc/conv_tc.cu ---- */
+/* Same contraction as fsdet_conv_fwd for layers with Cin % 64 == 0, Cout >= 64
+ * (fsdet_conv_tc_supported).  Operands are bf16 hi/lo planes produced by
+ * fsdet_split_bf16 (hi = bf16(x), lo = bf16(x - hi); three MMAs per K step keep
+ * ~16 mantissa bits so the 1e-3 parity bar against the fp32 reference holds):
+ * x_hi/x_lo dense NHWC [B*H*W][Cin] bf16, w_hi/w_lo [Cout][k*k*Cin] bf16.
+ * Output fp32 z[p][n] (+ previous z when accumulate != 0).  BatchNorm partial
+ * sums are produced by fsdet_colstats in the layout fsdet_bn_finalize reads. */
+int fsdet_conv_tc_supported(int Cin, int Cout, int ksize);
+int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* z, int ldz, int B,
+                      int H, int W, int Cin, int Cout, int ksize, int accumulate, void* stream);
+/* fp32 [rows][ld] (first C columns) -> two dense bf16 planes [rows][C] */
+int fsdet_split_bf16(const float* src, int ld, int C, size_t rows, void* hi, void* lo, void* stream);
+/* per-strip column sums / sums of squares of z: float [fsdet_colstats_rows(npix) + 2][2*C] */
+int fsdet_colstats(const float* z, int ld, size_t npix, int C, float* partial, void* stream);
+int fsdet_colstats_rows(size_t npix);
+/* test hook: one im2col TMA tile (128 pixels x 64 channels of filter tap `tap`,
+ * starting at output pixel m0, channel c0) un-swizzled to out_tile [128][64] bf16 */
+int fsdet_debug_im2col_tile(const void* x_plane, int B, int H, int W, int C, int ksize, long long m0, int c0, int tap,
+                            void* out_tile, void* stream);
+
 /* ---- BatchNorm2d(train/eval) + LeakyReLU(0.1) + MaxPool2d(2,2) -------- */
 /* nn.BatchNorm2d defaults (darknet_meta.py:247): eps 1e-5, momentum 0.1, biased
  * batch variance for normalisation, unbiased for running_var.
