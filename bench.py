@@ -207,7 +207,9 @@ def main():
 
     B, ncls, side = args.batch, args.ncls, args.side
     cfg.neg_ratio = 'full'
-    model = Darknet(netcfg.darknet_dynamic_blocks(side, side), netcfg.reweighting_net_blocks())
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # the reference's RegionLossV2.__init__ prints 'class_scale'
+        model = Darknet(netcfg.darknet_dynamic_blocks(side, side), netcfg.reweighting_net_blocks())
     seeded_init(model, 0)            # identical replicas on every rank
     model = model.to(dev).train()
     region_loss = model.loss

@@ -24,13 +24,14 @@
 namespace fsdet {
 
 // ------------------------------------------------------------------ operand split
-__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ src, int ld, int C4, long long rows,
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ src, int ld, int C, int Cpad4, long long rows,
                                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * C4) return;
-    long long r = i / C4;
-    int c = (int)(i - r * C4) * 4;
-    float4 v = ldg4(src + r * ld + c);
+    if (i >= rows * Cpad4) return;
+    long long r = i / Cpad4;
+    int c = (int)(i - r * Cpad4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) v = ldg4(src + r * ld + c);  // C % 4 == 0; channels C..Cpad-1 are zero filled
     float f[4] = {v.x, v.y, v.z, v.w};
     __nv_bfloat16 h[4], l[4];
 #pragma unroll
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
         h[k] = __float2bfloat16_rn(f[k]);
         l[k] = __float2bfloat16_rn(f[k] - __bfloat162float(h[k]));
     }
-    long long o = r * (long long)(C4 * 4) + c;
+    long long o = r * (long long)(Cpad4 * 4) + c;
     *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<uint2*>(h);
     *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(l);
 }
@@ -309,6 +310,183 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     }
 }
 
+// ------------------------------------------------------------------ weight gradient
+//   dw[co][tap][ci] = sum_p dz[p][co] * x[p + tap][ci]
+// GEMM with the pixel index as K: both operands are "MN-major" in shared memory (a row = one pixel, 64 channels
+// = 128 B), A = dz tile via a 2-D tiled map, B = x tile of ONE filter tap via the im2col map (zero-filled halo).
+// One CTA = 128 co x BN ci x one tap over a range of pixels (split-K across blockIdx.z).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;         // next 64-channel block along M/N
+    d |= (uint64_t)(1024 >> 4) << 32;              // next group of 8 pixels along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+
+struct TcWgArgs {
+    float* out;  // [splits][Cout][K]
+    int H, W, Cin, Cout, ks, pad;
+    long long M;              // pixels
+    long long pix_per_split;  // multiple of 64
+};
+
+constexpr int WG_BP = 64;                      // pixels per stage
+constexpr int WG_BLK = WG_BP * 128;            // one [64 pixels][64 channels] bf16 block = 8 KB
+
+template <int BN>
+struct WgCfg {
+    static constexpr int A_BYTES = 2 * WG_BLK;            // 128 co
+    static constexpr int B_BYTES = (BN / 64) * WG_BLK;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (BN == 128) ? 3 : 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant__ CUtensorMap tmDlo,
+                const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__ CUtensorMap tmXlo, const TcWgArgs p) {
+    using Cfg = WgCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int ci_tiles = (p.Cin + BN - 1) / BN;
+    const int tap = blockIdx.x / ci_tiles;
+    const int ci0 = (blockIdx.x - tap * ci_tiles) * BN;
+    const int co0 = blockIdx.y * 128;
+    const long long pbeg = (long long)blockIdx.z * p.pix_per_split;
+    long long pend = pbeg + p.pix_per_split;
+    if (pend > p.M) pend = p.M;
+    const int nk = pend > pbeg ? (int)((pend - pbeg + WG_BP - 1) / WG_BP) : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmDhi);
+        tma_prefetch_desc(&tmDlo);
+        tma_prefetch_desc(&tmXhi);
+        tma_prefetch_desc(&tmXlo);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int HW = p.H * p.W;
+            const int r = tap / p.ks, sx = tap - r * p.ks;
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+                uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                const long long p0 = pbeg + (long long)kb * WG_BP;
+                const int img = (int)(p0 / HW);
+                const int rem = (int)(p0 - (long long)img * HW);
+                const int ph = rem / p.W, pw = rem - ph * p.W;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    tma_load_2d(st + j * WG_BLK, &tmDhi, &full_bar[s], co0 + 64 * j, (int)p0);
+                    tma_load_2d(st + Cfg::A_BYTES + j * WG_BLK, &tmDlo, &full_bar[s], co0 + 64 * j, (int)p0);
+                }
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j) {
+                    tma_load_im2col_4d(st + 2 * Cfg::A_BYTES + j * WG_BLK, &tmXhi, &full_bar[s], ci0 + 64 * j, pw - p.pad,
+                                       ph - p.pad, img, (uint16_t)sx, (uint16_t)r);
+                    tma_load_im2col_4d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + j * WG_BLK, &tmXlo, &full_bar[s], ci0 + 64 * j,
+                                       pw - p.pad, ph - p.pad, img, (uint16_t)sx, (uint16_t)r);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // D=f32, A=B=bf16, both MN-major, N=BN, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)(128 >> 4) << 24);
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                const uint64_t ahi = umma_desc_mn_sw128(sa, WG_BLK), alo = umma_desc_mn_sw128(sa + Cfg::A_BYTES, WG_BLK);
+                const uint64_t bhi = umma_desc_mn_sw128(sa + 2 * Cfg::A_BYTES, WG_BLK);
+                const uint64_t blo = umma_desc_mn_sw128(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, WG_BLK);
+#pragma unroll
+                for (int k = 0; k < WG_BP / 16; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 2048 >> 4);  // 16 pixels = two 8-row groups of 1024 B
+                    umma_bf16(tmem_base, ahi + adv, bhi + adv, idesc, (kb | k) ? 1u : 0u);
+                    umma_bf16(tmem_base, alo + adv, bhi + adv, idesc, 1u);
+                    umma_bf16(tmem_base, ahi + adv, blo + adv, idesc, 1u);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int co = co0 + quarter * 32 + lane;
+        const long long K = (long long)p.ks * p.ks * p.Cin;
+        float* orow = p.out + ((long long)blockIdx.z * p.Cout + (co < p.Cout ? co : 0)) * K + (long long)tap * p.Cin;
+        if (nk > 0) {
+            mbar_wait(tmem_full_bar, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+            uint32_t r[32];
+            if (nk > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32, r);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            const int c = ci0 + ch * 32;
+            if (co < p.Cout) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    if (c + j < p.Cin)  // Cin % 4 == 0
+                        *reinterpret_cast<float4*>(orow + c + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+    }
+}
+
+__global__ void splitk_reduce4_kernel(const float4* __restrict__ ws, float4* __restrict__ out, long long n4, int splits) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 s = ws[i];
+    for (int k = 1; k < splits; ++k) {
+        float4 v = ws[(long long)k * n4 + i];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    out[i] = s;
+}
+
 // debug: dump one im2col A tile (un-swizzled) to global memory
 __global__ void __launch_bounds__(128) debug_im2col_kernel(const __grid_constant__ CUtensorMap tmA, int H, int W, int pad, long long m0,
                                                            int c0, int tap, int ks, uint16_t* __restrict__ out) {
@@ -435,12 +613,13 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const voi
 
 using namespace fsdet;
 
-extern "C" int fsdet_split_bf16(const float* src, int ld, int C, size_t rows, void* hi, void* lo, void* stream) {
-    FSDET_CHECK_ARG(src && hi && lo && C % 4 == 0 && ld % 4 == 0 && ld >= C, "split_bf16: C=%d ld=%d", C, ld);
+extern "C" int fsdet_split_bf16(const float* src, int ld, int C, int Cpad, size_t rows, void* hi, void* lo, void* stream) {
+    FSDET_CHECK_ARG(src && hi && lo && C % 4 == 0 && ld % 4 == 0 && ld >= C && Cpad >= C && Cpad % 4 == 0,
+                    "split_bf16: C=%d Cpad=%d ld=%d", C, Cpad, ld);
     FSDET_CHECK_ARG(aligned16(src) && ((uintptr_t)hi % 8 == 0) && ((uintptr_t)lo % 8 == 0), "split_bf16: alignment");
-    long long n = (long long)rows * (C / 4);
+    long long n = (long long)rows * (Cpad / 4);
     if (n == 0) return 0;
-    split_bf16_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, ld, C / 4, (long long)rows, (__nv_bfloat16*)hi,
+    split_bf16_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, ld, C, Cpad / 4, (long long)rows, (__nv_bfloat16*)hi,
                                                                           (__nv_bfloat16*)lo);
     return launch_status("split_bf16");
 }
@@ -461,7 +640,7 @@ extern "C" int fsdet_colstats(const float* z, int ld, size_t npix, int C, float*
 }
 
 extern "C" int fsdet_conv_tc_supported(int Cin, int Cout, int ksize) {
-    return (Cin % TC_BK == 0) && (Cout >= 64) && (Cout % 4 == 0) && (ksize == 1 || ksize == 3);
+    return (Cin % TC_BK == 0) && (Cout >= 8) && (Cout % 4 == 0) && (ksize == 1 || ksize == 3);
 }
 
 extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* z, int ldz, int B,
@@ -484,6 +663,96 @@ extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void*
     cudaStream_t s = (cudaStream_t)stream;
     if (Cout >= 128) return launch_tc<128>(a_hi, a_lo, w_hi, w_lo, a, s);
     return launch_tc<64>(a_hi, a_lo, w_hi, w_lo, a, s);
+}
+
+static int wg_splits(long long M, int Cin, int Cout, int ks, int bn) {
+    long long tiles = (long long)((Cin + bn - 1) / bn) * ks * ks * ((Cout + 127) / 128);
+    long long want = (2LL * kNumSMs + tiles - 1) / tiles;
+    long long maxs = (M + 511) / 512;  // at least 512 pixels (8 stages) per split
+    if (want > maxs) want = maxs;
+    if (want < 1) want = 1;
+    if (want > 512) want = 512;
+    return (int)want;
+}
+
+extern "C" int fsdet_conv_tc_wgrad_supported(int Cin, int Cout, int ksize) {
+    return (Cin % 64 == 0) && (Cout % 64 == 0) && (ksize == 1 || ksize == 3);
+}
+
+extern "C" size_t fsdet_conv_tc_wgrad_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize) {
+    int bn = Cin >= 128 ? 128 : 64;
+    int splits = wg_splits((long long)B * H * W, Cin, Cout, ksize, bn);
+    return splits > 1 ? (size_t)splits * Cout * ksize * ksize * Cin : 0;
+}
+
+template <int BN>
+static int launch_wg(const CUtensorMap& dhi, const CUtensorMap& dlo, const CUtensorMap& xhi, const CUtensorMap& xlo,
+                     const TcWgArgs& a, int splits, cudaStream_t s) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<BN>::SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr_done = true;
+    }
+    dim3 grid(((a.Cin + BN - 1) / BN) * a.ks * a.ks, (a.Cout + 127) / 128, splits);
+    wgrad_tc_kernel<BN><<<grid, 192, WgCfg<BN>::SMEM_BYTES, s>>>(dhi, dlo, xhi, xlo, a);
+    return launch_status("conv_tc_wgrad");
+}
+
+extern "C" int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const void* dz_hi, const void* dz_lo, float* dw,
+                                   float* workspace, size_t workspace_floats, int B, int H, int W, int Cin, int Cout, int ksize,
+                                   void* stream) {
+    FSDET_CHECK_ARG(x_hi && x_lo && dz_hi && dz_lo && dw, "conv_tc_wgrad: null pointer");
+    FSDET_CHECK_ARG(fsdet_conv_tc_wgrad_supported(Cin, Cout, ksize), "conv_tc_wgrad: unsupported Cin=%d Cout=%d k=%d", Cin, Cout, ksize);
+    FSDET_CHECK_ARG(aligned16(dw) && aligned16(x_hi) && aligned16(x_lo) && aligned16(dz_hi) && aligned16(dz_lo), "conv_tc_wgrad: alignment");
+    int rc = load_driver_fns();
+    if (rc) return rc;
+    const long long M = (long long)B * H * W;
+    FSDET_CHECK_ARG(M < (1ll << 31), "conv_tc_wgrad: too many pixels");
+    const int bn = Cin >= 128 ? 128 : 64;
+    const int splits = wg_splits(M, Cin, Cout, ksize, bn);
+    const size_t need = splits > 1 ? (size_t)splits * Cout * ksize * ksize * Cin : 0;
+    FSDET_CHECK_ARG(workspace_floats >= need && (need == 0 || (workspace && aligned16(workspace))),
+                    "conv_tc_wgrad: workspace too small (%zu < %zu floats)", workspace_floats, need);
+    TcWgArgs a;
+    a.out = splits > 1 ? workspace : dw;
+    a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ks = ksize; a.pad = (ksize - 1) / 2; a.M = M;
+    long long pps = (M + splits - 1) / splits;
+    a.pix_per_split = (pps + WG_BP - 1) / WG_BP * WG_BP;
+    CUtensorMap dhi, dlo, xhi, xlo;
+    // dz planes [M][Cout] bf16: 2-D tiled map, box = 64 channels x 64 pixels
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)Cout, (cuuint64_t)M};
+        cuuint64_t strides[1] = {(cuuint64_t)Cout * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)WG_BP};
+        cuuint32_t estr[2] = {1, 1};
+        for (int t = 0; t < 2; ++t) {
+            CUresult r = g_encodeTiled(t ? &dlo : &dhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(t ? dz_lo : dz_hi), dims,
+                                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) {
+                set_error("conv_tc_wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r);
+                return -3;
+            }
+        }
+    }
+    rc = make_im2col_map(&xhi, x_hi, B, H, W, Cin, ksize, WG_BP);
+    if (rc) return rc;
+    rc = make_im2col_map(&xlo, x_lo, B, H, W, Cin, ksize, WG_BP);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = (bn == 128) ? launch_wg<128>(dhi, dlo, xhi, xlo, a, splits, s) : launch_wg<64>(dhi, dlo, xhi, xlo, a, splits, s);
+    if (rc) return rc;
+    if (splits > 1) {
+        long long n4 = (long long)Cout * ksize * ksize * Cin / 4;
+        splitk_reduce4_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(workspace),
+                                                               reinterpret_cast<float4*>(dw), n4, splits);
+        rc = launch_status("conv_tc_wgrad_reduce");
+    }
+    return rc;
 }
 
 extern "C" int fsdet_debug_im2col_tile(const void* x_plane, int B, int H, int W, int C, int ksize, long long m0, int c0, int tap,

@@ -15,6 +15,12 @@ import torch
 from . import _lib
 from ._lib import call, ptr
 
+import os
+
+# tensor-core (tcgen05) convolution path for layers with Cin % 64 == 0; FSDET_TC=0 selects the exact-fp32 SIMT kernels
+USE_TC = os.environ.get('FSDET_TC', '1') != '0'
+TC_PARTS = set(os.environ.get('FSDET_TC_PARTS', 'fwd,dgrad,wgrad,head').split(','))  # debugging: which GEMMs may use it
+
 LEAKY_SLOPE = 0.1
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -41,13 +47,14 @@ def same_layout(a, b):
 
 class Act(object):
     """A view [B*H*W pixels] x [C channels at column `off`] of a 2-D NHWC buffer."""
-    __slots__ = ('buf', 'off', 'C', 'B', 'H', 'W', 'g', 'needs_grad', 'parent')
+    __slots__ = ('buf', 'off', 'C', 'B', 'H', 'W', 'g', 'needs_grad', 'parent', 'planes')
 
     def __init__(self, buf, off, C, B, H, W, needs_grad=True, parent=None):
         self.buf, self.off, self.C, self.B, self.H, self.W = buf, off, C, B, H, W
         self.g = None            # gradient Act (same geometry) once some consumer wrote it
         self.needs_grad = needs_grad
         self.parent = parent     # concat buffer this view is a slice of
+        self.planes = None       # (hi, lo) bf16 planes of this activation for the tensor-core path
 
     @property
     def ld(self):
@@ -242,6 +249,46 @@ class NetRunner(object):
             w.data = w.data.contiguous(memory_format=torch.channels_last)
         return w
 
+    # -- tensor-core helpers ------------------------------------------------
+    @staticmethod
+    def _tc_ok(cin, cout, k):
+        """Tensor-core path: >= 32 input channels (planes are zero-padded to a multiple of 64)."""
+        return USE_TC and cin >= 32 and cin % 4 == 0 and cout % 4 == 0 and bool(
+            _lib.lib.fsdet_conv_tc_supported(_round_up(cin, 64), cout, k))
+
+    @staticmethod
+    def _split_tensor(t2d_ptr, ld, C, rows, dev, st, cpad=None):
+        cpad = cpad or C
+        hi = torch.empty(rows, cpad, dtype=torch.bfloat16, device=dev)
+        lo = torch.empty(rows, cpad, dtype=torch.bfloat16, device=dev)
+        call('fsdet_split_bf16', t2d_ptr, ld, C, cpad, rows, ptr(hi), ptr(lo), st)
+        return hi, lo
+
+    def _planes(self, act, st):
+        """bf16 hi/lo planes [npix][round_up(C, 64)] of an activation (cached: the forward / input-gradient
+        GEMM and the weight-gradient GEMM read the same planes)."""
+        if act.planes is None:
+            act.planes = self._split_tensor(act.ptr, act.ld, act.C, act.npix, act.buf.device, st, _round_up(act.C, 64))
+        return act.planes
+
+    def _conv(self, name, x, w_ohwi, bias, z, stat_rows_out, cin, cout, k, acc, st):
+        """z = conv(x, w) through the tensor-core kernel when the shape allows, else SIMT.
+        Returns the number of BN partial rows written to `stat_rows_out` (a float tensor or None)."""
+        flops = 2.0 * x.npix * cout * k * k * cin
+        if bias is None and name in TC_PARTS and self._tc_ok(cin, cout, k):
+            cpad = _round_up(cin, 64)
+            xh, xl = self._planes(x, st)
+            wh, wl = self._split_tensor(ptr(w_ohwi), cin, cin, cout * k * k, x.buf.device, st, cpad)
+            self._timed('conv_tc', flops, 'fsdet_conv_tc_fwd', ptr(xh), ptr(xl), ptr(wh), ptr(wl), z.ptr, z.ld, x.B, x.H, x.W,
+                        cpad, cout, k, acc, st)
+            if stat_rows_out is not None:
+                call('fsdet_colstats', z.ptr, z.ld, x.npix, cout, ptr(stat_rows_out), st)
+                return _lib.lib.fsdet_colstats_rows(x.npix)
+            return 0
+        self._timed('conv_igemm', flops, 'fsdet_conv_fwd', x.ptr, x.ld, ptr(w_ohwi), ptr(bias), z.ptr, z.ld,
+                    ptr(stat_rows_out), x.B, x.H, x.W, cin, cout, k, acc, st)
+        return _lib.lib.fsdet_conv_stat_rows(x.npix) if stat_rows_out is not None else 0
+
     def _done(self, *params):
         if self.grad_hook is not None:
             for p in params:
@@ -415,10 +462,9 @@ class NetRunner(object):
             assert cout_p == s.cout, 'BatchNorm conv with Cout % 4 != 0 is unsupported'
             z = Act.new(B, H, W, s.cout, dev)
             use_batch_stats = training or not bn.track_running_stats
-            rows = _lib.lib.fsdet_conv_stat_rows(npix)
-            stat = _empty(rows + 2, 2 * s.cout, device=dev) if use_batch_stats else None
-            self._timed('conv_igemm', 2.0 * npix * s.cout * kk * cin_p, 'fsdet_conv_fwd', x.ptr, x.ld, ptr(wuse), None,
-                        z.ptr, z.ld, ptr(stat), B, H, W, cin_p, s.cout, s.k, 0, st)
+            rows_cap = max(_lib.lib.fsdet_conv_stat_rows(npix), _lib.lib.fsdet_colstats_rows(npix))
+            stat = _empty(rows_cap + 2, 2 * s.cout, device=dev) if use_batch_stats else None
+            rows = self._conv('fwd', x, wuse, None, z, stat, cin_p, s.cout, s.k, 0, st)
             vec = _empty(4, s.cout, device=dev)  # mean, invstd, scale, shift
             upd = training and bn.track_running_stats
             call('fsdet_bn_finalize', ptr(stat), rows, float(npix), ptr(bn.weight), ptr(bn.bias),
@@ -490,16 +536,15 @@ class NetRunner(object):
         rw2 = rw.detach().reshape(n_cls, K).contiguous()
         O = head.cout
         N = n_cls * O
-        Npad = _round_up(N, 32)
+        Npad = _round_up(N, 64)
         W = conv.weight  # [O, K, 1, 1]: OIHW == OHWI storage for 1x1
         weff = _empty(Npad, K, device=dev)
         beff = _empty(Npad, device=dev)
         call('fsdet_head_weff', ptr(W), ptr(conv.bias), ptr(rw2), ptr(weff), ptr(beff), n_cls, O, K, Npad, st)
         z = Act.new(x.B, x.H, x.W, Npad, dev)
-        self._timed('conv_igemm', 2.0 * x.npix * Npad * K, 'fsdet_conv_fwd', x.ptr, x.ld, ptr(weff), ptr(beff), z.ptr, z.ld,
-                    None, x.B, x.H, x.W, K, Npad, 1, 0, st)
+        self._conv('head', x, weff, None, z, None, K, Npad, 1, 0, st)
         out = _empty(x.B * n_cls, O, x.H, x.W, device=dev)
-        call('fsdet_nhwc_to_nchw', z.ptr, z.ld, None, ptr(out), x.B, N, x.H * x.W, st)
+        call('fsdet_nhwc_to_nchw', z.ptr, z.ld, ptr(beff), ptr(out), x.B, N, x.H * x.W, st)  # + bias[o]
         rec = ('head', s, head, x, rw2, weff, conv, n_cls, O, Npad)
         return out, rec
 
@@ -577,15 +622,28 @@ class NetRunner(object):
         wt = _empty(cin_p, kk, cout, device=dev)
         call('fsdet_weight_flip_transpose', ptr(w_ohwi), ptr(wt), cout, kk, cin_p, st)
         g, acc = x.grad_for_write()
-        self._timed('conv_igemm', 2.0 * x.npix * cout * kk * cin_p, 'fsdet_conv_fwd', dz.ptr, dz.ld, ptr(wt), None, g.ptr,
-                    g.ld, None, x.B, x.H, x.W, cout, cin_p, k, acc, st)
+        self._conv('dgrad', dz, wt, None, g, None, cout, cin_p, k, acc, st)
 
     def _wgrad(self, x, dz, out_tensor, cin_p, cout, k, st):
         dev = x.buf.device
+        flops = 2.0 * x.npix * cout * k * k * cin_p
+        ci64, co64 = _round_up(cin_p, 64), _round_up(cout, 64)
+        if USE_TC and 'wgrad' in TC_PARTS and cin_p >= 32 and cout >= 32 and _lib.lib.fsdet_conv_tc_wgrad_supported(ci64, co64, k):
+            xh, xl = self._planes(x, st)
+            dh, dl = self._planes(dz, st)
+            nws = _lib.lib.fsdet_conv_tc_wgrad_workspace_floats(x.B, x.H, x.W, ci64, co64, k)
+            ws = _empty(max(nws, 4), device=dev)
+            padded = (ci64 != cin_p) or (co64 != cout)
+            tgt = _empty(co64, k * k, ci64, device=dev) if padded else out_tensor
+            self._timed('wgrad_tc', flops, 'fsdet_conv_tc_wgrad', ptr(xh), ptr(xl), ptr(dh), ptr(dl), ptr(tgt), ptr(ws),
+                        nws, x.B, x.H, x.W, ci64, co64, k, st)
+            if padded:  # crop the zero channels / rows: rows [0, cout) are contiguous, channels via pad_channels
+                call('fsdet_pad_channels', ptr(tgt), ci64, ptr(out_tensor), cin_p, cout * k * k, st)
+            return
         nws = _lib.lib.fsdet_conv_wgrad_workspace_floats(x.B, x.H, x.W, cin_p, cout, k)
         ws = _empty(max(nws, 4), device=dev)
-        self._timed('conv_wgrad', 2.0 * x.npix * cout * k * k * cin_p, 'fsdet_conv_wgrad', x.ptr, x.ld, dz.ptr, dz.ld,
-                    ptr(out_tensor), ptr(ws), nws, x.B, x.H, x.W, cin_p, cout, k, st)
+        self._timed('conv_wgrad', flops, 'fsdet_conv_wgrad', x.ptr, x.ld, dz.ptr, dz.ld, ptr(out_tensor), ptr(ws), nws, x.B,
+                    x.H, x.W, cin_p, cout, k, st)
 
     def _convbn_bwd(self, rec, st):
         _, s, x, wuse, z, vec, full, pooled, conv, bn = rec

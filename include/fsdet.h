@@ -90,8 +90,19 @@ int fsdet_pad_channels(const float* in, int cin, float* out, int cout, size_t ro
 int fsdet_conv_tc_supported(int Cin, int Cout, int ksize);
 int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* z, int ldz, int B,
                       int H, int W, int Cin, int Cout, int ksize, int accumulate, void* stream);
-/* fp32 [rows][ld] (first C columns) -> two dense bf16 planes [rows][C] */
-int fsdet_split_bf16(const float* src, int ld, int C, size_t rows, void* hi, void* lo, void* stream);
+/* Weight gradient on the tensor cores (pixels are the GEMM K dimension; both
+ * operands are consumed MN-major straight from the NHWC planes).  Needs
+ * Cin % 64 == 0 and Cout % 64 == 0.  dw [Cout][k*k][Cin] fp32 (OHWI);
+ * workspace float [fsdet_conv_tc_wgrad_workspace_floats(...)] for the split-K
+ * partials (reduced in a fixed order). */
+int fsdet_conv_tc_wgrad_supported(int Cin, int Cout, int ksize);
+size_t fsdet_conv_tc_wgrad_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize);
+int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const void* dz_hi, const void* dz_lo, float* dw,
+                        float* workspace, size_t workspace_floats, int B, int H, int W, int Cin, int Cout, int ksize,
+                        void* stream);
+/* fp32 [rows][ld] (first C columns) -> two dense bf16 planes [rows][Cpad]
+ * (columns C..Cpad-1 zero: lets 32-channel layers use the 64-channel K tiles) */
+int fsdet_split_bf16(const float* src, int ld, int C, int Cpad, size_t rows, void* hi, void* lo, void* stream);
 /* per-strip column sums / sums of squares of z: float [fsdet_colstats_rows(npix) + 2][2*C] */
 int fsdet_colstats(const float* z, int ld, size_t npix, int C, float* partial, void* stream);
 int fsdet_colstats_rows(size_t npix);

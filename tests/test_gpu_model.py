@@ -8,6 +8,24 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+# Two arithmetic paths are tested (engine.USE_TC):
+#   'fp32' : exact-fp32 SIMT kernels (per-op rounding ~1e-7)  -> the strict bars below
+#   'tc'   : tcgen05 tensor-core kernels with 3xBF16 operand splitting (measured per-op rounding 5e-6..4e-5,
+#            tools/tc_precision.py).  Forward outputs and losses meet the same 1e-3 bar.  Gradients of these
+#            tiny synthetic problems are ill-conditioned (DESIGN.md "Parity"): every implementation's distance
+#            from a float64 evaluation is (condition number) x (its per-op rounding), so the tensor-core path is
+#            held to TC_GRAD_FACTOR x the distance of the float32 references instead of 2 x.
+TC_GRAD_FACTOR = 16.0
+
+
+@pytest.fixture(params=['fp32', 'tc'])
+def path(request):
+    from fewshot_detection_b200 import engine
+    old = engine.USE_TC
+    engine.USE_TC = request.param == 'tc'
+    yield request.param
+    engine.USE_TC = old
+
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 TOL = 1e-3  # north-star tolerance for float paths (relative L2 per tensor)
 
@@ -40,7 +58,7 @@ def _inputs(d, regen):
     return x.cuda(), metax.cuda(), mask.cuda()
 
 
-def test_meta_mini_all_tensors_vs_reference():
+def test_meta_mini_all_tensors_vs_reference(path):
     from fewshot_detection_b200 import netcfg
     d = np.load(os.path.join(G, 'meta_mini.npz'))
     m = _meta(netcfg.mini_dynamic_blocks(128, 4), netcfg.mini_reweighting_blocks(64, 4, 128), int(d['seed']))
@@ -57,7 +75,7 @@ def test_meta_mini_all_tensors_vs_reference():
         assert p.grad is not None, name
         e = rel(p.grad.detach().cpu().contiguous().numpy(), d['grad/' + name])
         worst = max(worst, e)
-        assert e < TOL, (name, e)
+        assert e < (TOL if path == 'fp32' else TC_GRAD_FACTOR * TOL), (name, e)
     with torch.no_grad():
         dw = m.meta_forward(metax, mask)
     assert rel(dw[0].cpu().numpy(), d['dynamic_weights_2nd_pass']) < TOL
@@ -67,7 +85,7 @@ def test_meta_mini_all_tensors_vs_reference():
     print('worst grad rel err', worst)
 
 
-def test_meta_full416_digest_vs_reference():
+def test_meta_full416_digest_vs_reference(path):
     from fewshot_detection_b200 import netcfg
     d = np.load(os.path.join(G, 'meta_full416.npz'))
     m = _meta(netcfg.darknet_dynamic_blocks(), netcfg.reweighting_net_blocks(), int(d['seed']))
@@ -86,8 +104,9 @@ def test_meta_full416_digest_vs_reference():
     for name, p in m.named_parameters():
         gn = float(d['gradnorm/' + name])
         g = p.grad.detach().cpu().contiguous()
-        assert abs(g.double().norm().item() - gn) < 1e-2 * gn + 1e-12, name
-        assert rel(g.reshape(-1)[:64].numpy(), d['gradhead/' + name]) < 3e-2, name
+        f = 1.0 if path == 'fp32' else TC_GRAD_FACTOR / 2
+        assert abs(g.double().norm().item() - gn) < f * 1e-2 * gn + 1e-12, name
+        assert rel(g.reshape(-1)[:64].numpy(), d['gradhead/' + name]) < f * 3e-2, name
 
 
 def _oracle_grads(det, ler, seed, x, metax, mask, tgt, dtype, seen=20000, device='cpu'):
@@ -111,7 +130,7 @@ def relt(a, b):
 
 
 @pytest.mark.parametrize('bs,cs', [(1, 2), (4, 5)])
-def test_meta_full416_vs_float64_truth(bs, cs):
+def test_meta_full416_vs_float64_truth(bs, cs, path):
     """Every parameter gradient of the real 416x416 architectures against a float64 evaluation of the
     oracle.  The loss is not smooth (max-pool arg-max, LeakyReLU kinks): a float32 evaluation flips a few
     arg-max decisions w.r.t. float64 and each flip moves a whole gradient entry, so ANY float32
@@ -142,13 +161,13 @@ def test_meta_full416_vs_float64_truth(bs, cs):
     for n, p in m.named_parameters():
         e_ours = relt(p.grad.detach().cpu().contiguous(), g64[n])
         e_ref = max(relt(g32[n], g64[n]), relt(g32c[n], g64[n]))
-        bar = max(TOL, 2 * e_ref)
+        bar = max(TOL, (2 if path == 'fp32' else TC_GRAD_FACTOR) * e_ref)
         worst = max(worst, (e_ours / bar, n))
         assert e_ours < bar, (n, e_ours, e_ref)
     print('worst (error / bar):', worst)
 
 
-def test_tiny_yolo_416_config1_vs_reference():
+def test_tiny_yolo_416_config1_vs_reference(path):
     from fewshot_detection_b200 import netcfg
     from fewshot_detection_b200.darknet import Darknet
     from seeding import seeded_init
@@ -166,25 +185,33 @@ def test_tiny_yolo_416_config1_vs_reference():
     assert rel(m(x).detach().cpu().numpy(), d['y_train']) < TOL
 
 
-def test_tiny_mini_train_step_vs_oracle():
-    """Plain Darknet + RegionLoss backward (maxpool stride 1, 125-channel head)."""
+def test_tiny_mini_train_step_vs_oracle(path):
+    """Plain Darknet + RegionLoss backward (maxpool stride 1, 125-channel head) vs the oracle (float64 truth)."""
     from fewshot_detection_b200 import netcfg
     from fewshot_detection_b200.darknet import Darknet
     from oracle import darknet as ODK, region_loss as ORL
     from seeding import seeded_init, synth_targets
     blocks = netcfg.mini_tiny_blocks(128, 8)
-    om = ODK.PlainDarknet([dict(b) for b in blocks])
-    seeded_init(om, 5)
-    om.train()
-    m = Darknet([dict(b) for b in blocks])
-    seeded_init(m, 5)
-    m = m.cuda().train()
     x = torch.rand(3, 3, 128, 128, generator=torch.Generator().manual_seed(6))
     tgt = torch.from_numpy(synth_targets(3, 1, 7, max_gt=4)[:, 0, :])
     tgt[:, 0::5] = torch.floor(tgt[:, 0::5] * 0) + (torch.arange(50) % 20).double()  # class ids < 20
-    oo = om(x)
-    lo = ORL.region_loss_plain(oo, tgt, om.anchors, 5, 20, seen=20000, metayolo=False)
-    lo.backward()
+
+    def run_oracle(dtype):
+        om = ODK.PlainDarknet([dict(b) for b in blocks])
+        seeded_init(om, 5)
+        om = om.to(dtype).train()
+        oo = om(x.to(dtype))
+        o32 = oo.detach().float().requires_grad_(True)
+        lo = ORL.region_loss_plain(o32, tgt, om.anchors, 5, 20, seen=20000, metayolo=False)
+        lo.backward()
+        oo.backward(o32.grad.to(dtype))
+        return oo.detach().double(), lo.item(), {n: p.grad.detach().double() for n, p in om.named_parameters()}
+
+    o64, l64, g64 = run_oracle(torch.float64)
+    o32, l32, g32 = run_oracle(torch.float32)
+    m = Darknet([dict(b) for b in blocks])
+    seeded_init(m, 5)
+    m = m.cuda().train()
     from fewshot_detection_b200.cfg import cfg
     cfg.metayolo = False
     try:
@@ -195,14 +222,15 @@ def test_tiny_mini_train_step_vs_oracle():
         loss.backward()
     finally:
         cfg.metayolo = True
-    assert rel(out.detach().cpu().numpy(), oo.detach().numpy()) < TOL
-    assert abs(loss.item() - lo.item()) < TOL * abs(lo.item())
-    for (n1, p), (n2, q) in zip(m.named_parameters(), om.named_parameters()):
-        assert n1 == n2
-        assert rel(p.grad.detach().cpu().contiguous().numpy(), q.grad.numpy()) < TOL, n1
+    assert relt(out.detach().cpu(), o64) < TOL
+    assert abs(loss.item() - l64) < TOL * abs(l64)
+    for n, p in m.named_parameters():
+        e_ours = relt(p.grad.detach().cpu().contiguous(), g64[n])
+        e_ref = relt(g32[n], g64[n])
+        assert e_ours < max(TOL, (2 if path == 'fp32' else TC_GRAD_FACTOR) * max(e_ref, 1e-4)), (n, e_ours, e_ref)
 
 
-def test_train_steps_match_oracle_sgd():
+def test_train_steps_match_oracle_sgd(path):
     """Three full meta-training steps (forward, RegionLossV2, backward, FusedSGD) against the oracle +
     torch.optim.SGD on the CPU. Parameters are compared with a float64 run of the oracle as ground truth
     (bar: 1e-3, or twice the float32 oracle's own distance where float32 cannot do better)."""
@@ -255,7 +283,7 @@ def test_train_steps_match_oracle_sgd():
         # compare the parameter *update* (p - p0 is what training computes); p itself trivially matches
         e_ours = relt(p.detach().cpu().contiguous(), p64[n])
         e_ref = relt(p32[n], p64[n])
-        assert e_ours < max(TOL, 2 * e_ref), (n, e_ours, e_ref)
+        assert e_ours < max(TOL, (2 if path == 'fp32' else TC_GRAD_FACTOR) * e_ref), (n, e_ours, e_ref)
 
 
 def test_weight_file_roundtrip(tmp_path):
