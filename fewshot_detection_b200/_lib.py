@@ -29,11 +29,12 @@ SIGNATURES = {
     'fsdet_weight_flip_transpose': ('ppiiip', 'i'),
     'fsdet_pad_channels': ('pipizp', 'i'),
     'fsdet_conv_tc_supported': ('iii', 'i'),
-    'fsdet_conv_tc_fwd': ('pppppiiiiiiiip', 'i'),
+    'fsdet_conv_tc_fwd': ('pppppppiiiiiiiip', 'i'),
     'fsdet_conv_tc_wgrad_supported': ('iii', 'i'),
     'fsdet_conv_tc_wgrad_workspace_floats': ('iiiiii', 'z'),
-    'fsdet_conv_tc_wgrad': ('ppppppziiiiiip', 'i'),
-    'fsdet_split_bf16': ('piiizppp', 'i'),
+    'fsdet_conv_tc_wgrad': ('ppppppppziiiiiip', 'i'),
+    'fsdet_amax': ('piizpp', 'i'),
+    'fsdet_split_f16': ('piiizpppp', 'i'),
     'fsdet_colstats': ('pizipp', 'i'),
     'fsdet_colstats_rows': ('z', 'i'),
     'fsdet_debug_im2col_tile': ('piiiiiqiipp', 'i'),

@@ -5,9 +5,12 @@
 // Tensor-core path of nn.Conv2d (darknet_meta.py:236-252) for every layer with Cin % 64 == 0.
 //
 // Precision: the reference is fp32 end to end and the parity bar is 1e-3 relative through a 23-layer
-// train-mode-BN stack, which single-pass bf16/tf32 operands do not meet.  Operands are therefore split into
-// two bf16 planes (hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits, the same 4 B/element as fp32) and
-// each K step issues three MMAs  Ahi*Bhi + Alo*Bhi + Ahi*Blo  into one fp32 TMEM accumulator ("3xBF16").
+// train-mode-BN stack with max-pool / LeakyReLU kinks (every rounding error also flips arg-max decisions), which
+// single-pass bf16/tf32 operands do not meet.  Operands are therefore split into two fp16 planes of the tensor
+// scaled by a power of two so that its max lies in [512, 1024)  (hi = fp16(s*x), lo = fp16(s*x - hi): 22 mantissa
+// bits in the same 4 B/element as fp32) and each K step issues three MMAs  Ahi*Bhi + Alo*Bhi + Ahi*Blo  into fp32
+// TMEM accumulators; the k-blocks rotate over four accumulators (summed in the epilogue) because the tensor
+// core's fp32 accumulation truncates and its error grows with the number of accumulation steps.
 //
 // Structure (one CTA = one 128-pixel x BN-channel output tile, 192 threads):
 //   warp 0   : TMA producer.  A tiles come straight from the NHWC activation planes through an *im2col*
@@ -17,27 +20,58 @@
 //   warp 1   : allocates TMEM, issues tcgen05.mma (one elected thread), commits to mbarriers.
 //   warps 2-5: epilogue, tcgen05.ld the fp32 accumulator (lane = pixel) and store z rows.
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
 namespace fsdet {
 
 // ------------------------------------------------------------------ operand split
-__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ src, int ld, int C, int Cpad4, long long rows,
-                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+// power-of-two scale that maps a tensor with absolute maximum `a` into [512, 1024)
+__device__ __forceinline__ float scale_from_amax(float a) {
+    if (!(a > 0.f) || !isfinite(a)) return 1.f;
+    int ex = (int)((__float_as_uint(a) >> 23) & 0xff) - 126;  // a = m * 2^ex, m in [0.5, 1)
+    int e = 10 - ex;
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+    return __uint_as_float((uint32_t)(e + 127) << 23);
+}
+
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ src, int ld, int C4, long long rows, float* __restrict__ out) {
+    float m = 0.f;
+    const long long n = rows * C4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / C4;
+        int c = (int)(i - r * C4) * 4;
+        float4 v = ldg4(src + r * ld + c);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        if (isfinite(m)) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));  // non-negative floats order as ints
+    }
+}
+
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ src, int ld, int C, int Cpad4, long long rows,
+                                                        const float* __restrict__ amax, __half* __restrict__ hi,
+                                                        __half* __restrict__ lo) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * Cpad4) return;
+    const float sc = amax ? scale_from_amax(__ldg(amax)) : 1.f;
     long long r = i / Cpad4;
     int c = (int)(i - r * Cpad4) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < C) v = ldg4(src + r * ld + c);  // C % 4 == 0; channels C..Cpad-1 are zero filled
-    float f[4] = {v.x, v.y, v.z, v.w};
-    __nv_bfloat16 h[4], l[4];
+    float f[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
+    __half h[4], l[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        h[k] = __float2bfloat16_rn(f[k]);
-        l[k] = __float2bfloat16_rn(f[k] - __bfloat162float(h[k]));
+        h[k] = __float2half_rn(f[k]);
+        l[k] = __float2half_rn(f[k] - __half2float(h[k]));
     }
     long long o = r * (long long)(Cpad4 * 4) + c;
     *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<uint2*>(h);
@@ -138,7 +172,7 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
     return d;
 }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -166,8 +200,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // ------------------------------------------------------------------ the kernel
+constexpr int NACC = 4;   // TMEM accumulators: NHI for the hi*hi products (k-blocks rotate over them) + one for the lo terms
+constexpr int NHI = 3;    // (the lo terms are 2^-11 smaller, so their accumulation error is negligible)
+
 struct TcArgs {
     float* z;
+    const float* amax_a;
+    const float* amax_b;
     int ldz;
     int H, W, Cin, Cout, ks, pad;
     long long M;  // B*H*W
@@ -218,8 +257,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) {  // whole warp: allocate BN fp32 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN));
+    if (warp == 1) {  // whole warp: allocate NACC x BN fp32 accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(NACC * BN)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
@@ -249,8 +288,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            // instruction descriptor: D=f32, A=B=f16, both K-major, N=BN, M=128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             for (int kb = 0; kb < nk; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait(&full_bar[s], (kb / STAGES) & 1);
@@ -260,10 +299,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 const uint64_t bhi = umma_desc_k_sw128(sa + 2 * TC_A_BYTES), blo = umma_desc_k_sw128(sa + 2 * TC_A_BYTES + Cfg::B_BYTES);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 bf16 = 32 B along K inside the swizzle atom
-                    umma_bf16(tmem_base, ahi + adv, bhi + adv, idesc, (kb | k) ? 1u : 0u);
-                    umma_bf16(tmem_base, alo + adv, bhi + adv, idesc, 1u);
-                    umma_bf16(tmem_base, ahi + adv, blo + adv, idesc, 1u);
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 halves = 32 B along K inside the swizzle atom
+                    const uint32_t dhi = tmem_base + (uint32_t)((kb % NHI) * BN);
+                    const uint32_t dlo = tmem_base + (uint32_t)(NHI * BN);
+                    umma_f16(dhi, ahi + adv, bhi + adv, idesc, (kb >= NHI || k > 0) ? 1u : 0u);
+                    umma_f16(dlo, alo + adv, bhi + adv, idesc, (kb | k) ? 1u : 0u);
+                    umma_f16(dlo, ahi + adv, blo + adv, idesc, 1u);
                 }
                 umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs have read it
             }
@@ -277,18 +318,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         const long long m = m0 + quarter * 32 + lane;
         const bool row_ok = m < p.M;
         float* zr = p.z + (row_ok ? m : 0) * p.ldz;
+        const float inv = 1.f / (scale_from_amax(p.amax_a ? __ldg(p.amax_a) : 0.f) * scale_from_amax(p.amax_b ? __ldg(p.amax_b) : 0.f));
+        const int nhi = nk < NHI ? nk : NHI;
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
             uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32, r);
+            float acc[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32;
+            tmem_ld32(taddr + NHI * BN, r);  // lo terms first (small), then the hi*hi partial sums
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+            for (int a = nhi - 1; a >= 0; --a) {
+                tmem_ld32(taddr + a * BN, r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+            }
             const int n0 = n_tile * BN + ch * 32;
             if (row_ok) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int n = n0 + j;
                     if (n + 3 < p.Cout) {
-                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                               __uint_as_float(r[j + 3]));
+                        float4 v = make_float4(acc[j] * inv, acc[j + 1] * inv, acc[j + 2] * inv, acc[j + 3] * inv);
                         if (p.accumulate) {
                             float4 o = *reinterpret_cast<const float4*>(zr + n);
                             v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -296,7 +347,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                         *reinterpret_cast<float4*>(zr + n) = v;
                     } else {
                         for (int t = 0; t < 4; ++t)
-                            if (n + t < p.Cout) zr[n + t] = __uint_as_float(r[j + t]) + (p.accumulate ? zr[n + t] : 0.f);
+                            if (n + t < p.Cout) zr[n + t] = acc[j + t] * inv + (p.accumulate ? zr[n + t] : 0.f);
                     }
                 }
             }
@@ -306,7 +357,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NACC * BN)));
     }
 }
 
@@ -327,6 +378,8 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t 
 
 struct TcWgArgs {
     float* out;  // [splits][Cout][K]
+    const float* amax_a;  // of dz
+    const float* amax_b;  // of x
     int H, W, Cin, Cout, ks, pad;
     long long M;              // pixels
     long long pix_per_split;  // multiple of 64
@@ -381,7 +434,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(NACC * BN)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
@@ -418,9 +471,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // D=f32, A=B=bf16, both MN-major, N=BN, M=128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) |
-                                   ((uint32_t)(128 >> 4) << 24);
+            // D=f32, A=B=f16, both MN-major, N=BN, M=128
+            const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             for (int kb = 0; kb < nk; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait(&full_bar[s], (kb / STAGES) & 1);
@@ -432,9 +484,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
 #pragma unroll
                 for (int k = 0; k < WG_BP / 16; ++k) {
                     const uint64_t adv = (uint64_t)(k * 2048 >> 4);  // 16 pixels = two 8-row groups of 1024 B
-                    umma_bf16(tmem_base, ahi + adv, bhi + adv, idesc, (kb | k) ? 1u : 0u);
-                    umma_bf16(tmem_base, alo + adv, bhi + adv, idesc, 1u);
-                    umma_bf16(tmem_base, ahi + adv, blo + adv, idesc, 1u);
+                    const uint32_t dhi = tmem_base + (uint32_t)((kb % NHI) * BN);
+                    const uint32_t dlo = tmem_base + (uint32_t)(NHI * BN);
+                    umma_f16(dhi, ahi + adv, bhi + adv, idesc, (kb >= NHI || k > 0) ? 1u : 0u);
+                    umma_f16(dlo, alo + adv, bhi + adv, idesc, (kb | k) ? 1u : 0u);
+                    umma_f16(dlo, ahi + adv, blo + adv, idesc, 1u);
                 }
                 umma_commit(&empty_bar[s]);
             }
@@ -449,22 +503,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
             mbar_wait(tmem_full_bar, 0);
             tc_fence_after();
         }
+        const float inv = 1.f / (scale_from_amax(p.amax_a ? __ldg(p.amax_a) : 0.f) * scale_from_amax(p.amax_b ? __ldg(p.amax_b) : 0.f));
+        const int nhi = nk < NHI ? nk : NHI;
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
             uint32_t r[32];
-            if (nk > 0) {
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32, r);
-            } else {
+            float acc[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32;
+            if (nk > 0) {
+                tmem_ld32(taddr + NHI * BN, r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+            }
+            for (int a = nhi - 1; a >= 0; --a) {
+                tmem_ld32(taddr + a * BN, r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
             }
             const int c = ci0 + ch * 32;
             if (co < p.Cout) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     if (c + j < p.Cin)  // Cin % 4 == 0
-                        *reinterpret_cast<float4*>(orow + c + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        *reinterpret_cast<float4*>(orow + c + j) = make_float4(acc[j] * inv, acc[j + 1] * inv, acc[j + 2] * inv, acc[j + 3] * inv);
             }
         }
     }
@@ -472,7 +535,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NACC * BN)));
     }
 }
 
@@ -555,7 +618,7 @@ static int make_im2col_map(CUtensorMap* map, const void* base, int B, int H, int
     int lower[2] = {-pad, -pad};
     int upper[2] = {pad - (ks - 1), pad - (ks - 1)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encodeIm2col(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
+    CUresult r = g_encodeIm2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
                                 (cuuint32_t)TC_BK, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -576,7 +639,7 @@ static int make_tiled_map(CUtensorMap* map, const void* base, long long rows, lo
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = g_encodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -613,15 +676,29 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const voi
 
 using namespace fsdet;
 
-extern "C" int fsdet_split_bf16(const float* src, int ld, int C, int Cpad, size_t rows, void* hi, void* lo, void* stream) {
+extern "C" int fsdet_amax(const float* src, int ld, int C, size_t rows, float* amax_out, void* stream) {
+    FSDET_CHECK_ARG(src && amax_out && C % 4 == 0 && ld % 4 == 0 && ld >= C && aligned16(src), "amax: C=%d ld=%d", C, ld);
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(amax_out, 0, sizeof(float), s);
+    if (e != cudaSuccess) { set_error("amax: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    long long n = (long long)rows * (C / 4);
+    if (n == 0) return 0;
+    int blocks = ceil_div(n, 256 * 8);
+    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    amax_kernel<<<blocks, 256, 0, s>>>(src, ld, C / 4, (long long)rows, amax_out);
+    return launch_status("amax");
+}
+
+extern "C" int fsdet_split_f16(const float* src, int ld, int C, int Cpad, size_t rows, const float* amax, void* hi, void* lo,
+                               void* stream) {
     FSDET_CHECK_ARG(src && hi && lo && C % 4 == 0 && ld % 4 == 0 && ld >= C && Cpad >= C && Cpad % 4 == 0,
-                    "split_bf16: C=%d Cpad=%d ld=%d", C, Cpad, ld);
-    FSDET_CHECK_ARG(aligned16(src) && ((uintptr_t)hi % 8 == 0) && ((uintptr_t)lo % 8 == 0), "split_bf16: alignment");
+                    "split_f16: C=%d Cpad=%d ld=%d", C, Cpad, ld);
+    FSDET_CHECK_ARG(aligned16(src) && ((uintptr_t)hi % 8 == 0) && ((uintptr_t)lo % 8 == 0), "split_f16: alignment");
     long long n = (long long)rows * (Cpad / 4);
     if (n == 0) return 0;
-    split_bf16_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, ld, C, Cpad / 4, (long long)rows, (__nv_bfloat16*)hi,
-                                                                          (__nv_bfloat16*)lo);
-    return launch_status("split_bf16");
+    split_f16_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, ld, C, Cpad / 4, (long long)rows, amax, (__half*)hi,
+                                                                         (__half*)lo);
+    return launch_status("split_f16");
 }
 
 static const int kStatStrip = 256;
@@ -643,8 +720,9 @@ extern "C" int fsdet_conv_tc_supported(int Cin, int Cout, int ksize) {
     return (Cin % TC_BK == 0) && (Cout >= 8) && (Cout % 4 == 0) && (ksize == 1 || ksize == 3);
 }
 
-extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* z, int ldz, int B,
-                                 int H, int W, int Cin, int Cout, int ksize, int accumulate, void* stream) {
+extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* amax_x,
+                                 const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin, int Cout, int ksize,
+                                 int accumulate, void* stream) {
     FSDET_CHECK_ARG(x_hi && x_lo && w_hi && w_lo && z, "conv_tc_fwd: null pointer");
     FSDET_CHECK_ARG(fsdet_conv_tc_supported(Cin, Cout, ksize), "conv_tc_fwd: unsupported Cin=%d Cout=%d k=%d", Cin, Cout, ksize);
     FSDET_CHECK_ARG(ldz % 4 == 0 && aligned16(z) && aligned16(x_hi) && aligned16(x_lo) && aligned16(w_hi) && aligned16(w_lo),
@@ -652,8 +730,8 @@ extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void*
     int rc = load_driver_fns();
     if (rc) return rc;
     TcArgs a;
-    a.z = z; a.ldz = ldz; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ks = ksize; a.pad = (ksize - 1) / 2;
-    a.M = (long long)B * H * W; a.accumulate = accumulate;
+    a.z = z; a.amax_a = amax_x; a.amax_b = amax_w; a.ldz = ldz; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ks = ksize;
+    a.pad = (ksize - 1) / 2; a.M = (long long)B * H * W; a.accumulate = accumulate;
     if (a.M == 0) return 0;
     CUtensorMap a_hi, a_lo;
     rc = make_im2col_map(&a_hi, x_hi, B, H, W, Cin, ksize, TC_BM);
@@ -702,9 +780,9 @@ static int launch_wg(const CUtensorMap& dhi, const CUtensorMap& dlo, const CUten
     return launch_status("conv_tc_wgrad");
 }
 
-extern "C" int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const void* dz_hi, const void* dz_lo, float* dw,
-                                   float* workspace, size_t workspace_floats, int B, int H, int W, int Cin, int Cout, int ksize,
-                                   void* stream) {
+extern "C" int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const void* dz_hi, const void* dz_lo, const float* amax_x,
+                                   const float* amax_dz, float* dw, float* workspace, size_t workspace_floats, int B, int H,
+                                   int W, int Cin, int Cout, int ksize, void* stream) {
     FSDET_CHECK_ARG(x_hi && x_lo && dz_hi && dz_lo && dw, "conv_tc_wgrad: null pointer");
     FSDET_CHECK_ARG(fsdet_conv_tc_wgrad_supported(Cin, Cout, ksize), "conv_tc_wgrad: unsupported Cin=%d Cout=%d k=%d", Cin, Cout, ksize);
     FSDET_CHECK_ARG(aligned16(dw) && aligned16(x_hi) && aligned16(x_lo) && aligned16(dz_hi) && aligned16(dz_lo), "conv_tc_wgrad: alignment");
@@ -719,6 +797,7 @@ extern "C" int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const voi
                     "conv_tc_wgrad: workspace too small (%zu < %zu floats)", workspace_floats, need);
     TcWgArgs a;
     a.out = splits > 1 ? workspace : dw;
+    a.amax_a = amax_dz; a.amax_b = amax_x;
     a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ks = ksize; a.pad = (ksize - 1) / 2; a.M = M;
     long long pps = (M + splits - 1) / splits;
     a.pix_per_split = (pps + WG_BP - 1) / WG_BP * WG_BP;
@@ -730,7 +809,7 @@ extern "C" int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const voi
         cuuint32_t box[2] = {64, (cuuint32_t)WG_BP};
         cuuint32_t estr[2] = {1, 1};
         for (int t = 0; t < 2; ++t) {
-            CUresult r = g_encodeTiled(t ? &dlo : &dhi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(t ? dz_lo : dz_hi), dims,
+            CUresult r = g_encodeTiled(t ? &dlo : &dhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(t ? dz_lo : dz_hi), dims,
                                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) {

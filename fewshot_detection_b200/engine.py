@@ -258,15 +258,18 @@ class NetRunner(object):
 
     @staticmethod
     def _split_tensor(t2d_ptr, ld, C, rows, dev, st, cpad=None):
+        """fp32 [rows][ld] -> (hi, lo, amax): scaled fp16 planes [rows][cpad] + the device scalar they were scaled by."""
         cpad = cpad or C
-        hi = torch.empty(rows, cpad, dtype=torch.bfloat16, device=dev)
-        lo = torch.empty(rows, cpad, dtype=torch.bfloat16, device=dev)
-        call('fsdet_split_bf16', t2d_ptr, ld, C, cpad, rows, ptr(hi), ptr(lo), st)
-        return hi, lo
+        amax = torch.empty(1, dtype=torch.float32, device=dev)
+        call('fsdet_amax', t2d_ptr, ld, C, rows, ptr(amax), st)
+        hi = torch.empty(rows, cpad, dtype=torch.float16, device=dev)
+        lo = torch.empty(rows, cpad, dtype=torch.float16, device=dev)
+        call('fsdet_split_f16', t2d_ptr, ld, C, cpad, rows, ptr(amax), ptr(hi), ptr(lo), st)
+        return hi, lo, amax
 
     def _planes(self, act, st):
-        """bf16 hi/lo planes [npix][round_up(C, 64)] of an activation (cached: the forward / input-gradient
-        GEMM and the weight-gradient GEMM read the same planes)."""
+        """fp16 hi/lo planes [npix][round_up(C, 64)] (+ amax) of an activation (cached: the forward /
+        input-gradient GEMM and the weight-gradient GEMM read the same planes)."""
         if act.planes is None:
             act.planes = self._split_tensor(act.ptr, act.ld, act.C, act.npix, act.buf.device, st, _round_up(act.C, 64))
         return act.planes
@@ -277,10 +280,10 @@ class NetRunner(object):
         flops = 2.0 * x.npix * cout * k * k * cin
         if bias is None and name in TC_PARTS and self._tc_ok(cin, cout, k):
             cpad = _round_up(cin, 64)
-            xh, xl = self._planes(x, st)
-            wh, wl = self._split_tensor(ptr(w_ohwi), cin, cin, cout * k * k, x.buf.device, st, cpad)
-            self._timed('conv_tc', flops, 'fsdet_conv_tc_fwd', ptr(xh), ptr(xl), ptr(wh), ptr(wl), z.ptr, z.ld, x.B, x.H, x.W,
-                        cpad, cout, k, acc, st)
+            xh, xl, xa = self._planes(x, st)
+            wh, wl, wa = self._split_tensor(ptr(w_ohwi), cin, cin, cout * k * k, x.buf.device, st, cpad)
+            self._timed('conv_tc', flops, 'fsdet_conv_tc_fwd', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(xa), ptr(wa), z.ptr, z.ld,
+                        x.B, x.H, x.W, cpad, cout, k, acc, st)
             if stat_rows_out is not None:
                 call('fsdet_colstats', z.ptr, z.ld, x.npix, cout, ptr(stat_rows_out), st)
                 return _lib.lib.fsdet_colstats_rows(x.npix)
@@ -629,14 +632,14 @@ class NetRunner(object):
         flops = 2.0 * x.npix * cout * k * k * cin_p
         ci64, co64 = _round_up(cin_p, 64), _round_up(cout, 64)
         if USE_TC and 'wgrad' in TC_PARTS and cin_p >= 32 and cout >= 32 and _lib.lib.fsdet_conv_tc_wgrad_supported(ci64, co64, k):
-            xh, xl = self._planes(x, st)
-            dh, dl = self._planes(dz, st)
+            xh, xl, xa = self._planes(x, st)
+            dh, dl, da = self._planes(dz, st)
             nws = _lib.lib.fsdet_conv_tc_wgrad_workspace_floats(x.B, x.H, x.W, ci64, co64, k)
             ws = _empty(max(nws, 4), device=dev)
             padded = (ci64 != cin_p) or (co64 != cout)
             tgt = _empty(co64, k * k, ci64, device=dev) if padded else out_tensor
-            self._timed('wgrad_tc', flops, 'fsdet_conv_tc_wgrad', ptr(xh), ptr(xl), ptr(dh), ptr(dl), ptr(tgt), ptr(ws),
-                        nws, x.B, x.H, x.W, ci64, co64, k, st)
+            self._timed('wgrad_tc', flops, 'fsdet_conv_tc_wgrad', ptr(xh), ptr(xl), ptr(dh), ptr(dl), ptr(xa), ptr(da),
+                        ptr(tgt), ptr(ws), nws, x.B, x.H, x.W, ci64, co64, k, st)
             if padded:  # crop the zero channels / rows: rows [0, cout) are contiguous, channels via pad_channels
                 call('fsdet_pad_channels', ptr(tgt), ci64, ptr(out_tensor), cin_p, cout * k * k, st)
             return

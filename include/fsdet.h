@@ -80,16 +80,22 @@ int fsdet_weight_flip_transpose(const float* w, float* wt, int Cout, int kk, int
 int fsdet_pad_channels(const float* in, int cin, float* out, int cout, size_t rows, void* stream);
 
 /* ---- tensor-core convolution (tcgen05 + TMA im2col), csrc/conv_tc.cu ---- */
-/* Same contraction as fsdet_conv_fwd for layers with Cin % 64 == 0, Cout >= 64
- * (fsdet_conv_tc_supported).  Operands are bf16 hi/lo planes produced by
- * fsdet_split_bf16 (hi = bf16(x), lo = bf16(x - hi); three MMAs per K step keep
- * ~16 mantissa bits so the 1e-3 parity bar against the fp32 reference holds):
- * x_hi/x_lo dense NHWC [B*H*W][Cin] bf16, w_hi/w_lo [Cout][k*k*Cin] bf16.
- * Output fp32 z[p][n] (+ previous z when accumulate != 0).  BatchNorm partial
- * sums are produced by fsdet_colstats in the layout fsdet_bn_finalize reads. */
+/* Same contraction as fsdet_conv_fwd for layers with Cin % 64 == 0 (pad the
+ * planes with zero channels otherwise), Cout % 4 == 0 (fsdet_conv_tc_supported).
+ * Operands are fp16 hi/lo planes produced by fsdet_amax + fsdet_split_f16:
+ * the tensor is scaled by the power of two that maps its absolute maximum
+ * into [512, 1024), hi = fp16(s*x), lo = fp16(s*x - hi); three MMAs per K step
+ * (hi*hi + lo*hi + hi*lo) keep ~22 mantissa bits so that the fp32 reference's
+ * results - including its max-pool arg-max decisions - are reproduced.
+ * x_hi/x_lo dense NHWC [B*H*W][Cin] fp16, w_hi/w_lo [Cout][k*k*Cin] fp16,
+ * amax_x / amax_w: device floats holding the tensors' absolute maxima (NULL =
+ * planes are unscaled).  Output fp32 z[p][n] (+ previous z when accumulate
+ * != 0).  BatchNorm partial sums are produced by fsdet_colstats in the layout
+ * fsdet_bn_finalize reads. */
 int fsdet_conv_tc_supported(int Cin, int Cout, int ksize);
-int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* z, int ldz, int B,
-                      int H, int W, int Cin, int Cout, int ksize, int accumulate, void* stream);
+int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* amax_x,
+                      const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin, int Cout, int ksize,
+                      int accumulate, void* stream);
 /* Weight gradient on the tensor cores (pixels are the GEMM K dimension; both
  * operands are consumed MN-major straight from the NHWC planes).  Needs
  * Cin % 64 == 0 and Cout % 64 == 0.  dw [Cout][k*k][Cin] fp32 (OHWI);
@@ -97,12 +103,16 @@ int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, cons
  * partials (reduced in a fixed order). */
 int fsdet_conv_tc_wgrad_supported(int Cin, int Cout, int ksize);
 size_t fsdet_conv_tc_wgrad_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize);
-int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const void* dz_hi, const void* dz_lo, float* dw,
-                        float* workspace, size_t workspace_floats, int B, int H, int W, int Cin, int Cout, int ksize,
-                        void* stream);
-/* fp32 [rows][ld] (first C columns) -> two dense bf16 planes [rows][Cpad]
- * (columns C..Cpad-1 zero: lets 32-channel layers use the 64-channel K tiles) */
-int fsdet_split_bf16(const float* src, int ld, int C, int Cpad, size_t rows, void* hi, void* lo, void* stream);
+int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const void* dz_hi, const void* dz_lo, const float* amax_x,
+                        const float* amax_dz, float* dw, float* workspace, size_t workspace_floats, int B, int H,
+                        int W, int Cin, int Cout, int ksize, void* stream);
+/* absolute maximum of fp32 [rows][ld] (first C columns) -> *amax_out (device float) */
+int fsdet_amax(const float* src, int ld, int C, size_t rows, float* amax_out, void* stream);
+/* fp32 [rows][ld] (first C columns) -> two dense fp16 planes [rows][Cpad] of the
+ * tensor scaled as described above (amax NULL: no scaling); columns C..Cpad-1
+ * are zero (lets 32-channel layers use the 64-channel K tiles) */
+int fsdet_split_f16(const float* src, int ld, int C, int Cpad, size_t rows, const float* amax, void* hi, void* lo,
+                    void* stream);
 /* per-strip column sums / sums of squares of z: float [fsdet_colstats_rows(npix) + 2][2*C] */
 int fsdet_colstats(const float* z, int ld, size_t npix, int C, float* partial, void* stream);
 int fsdet_colstats_rows(size_t npix);

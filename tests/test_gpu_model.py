@@ -10,12 +10,13 @@ pytestmark = pytest.mark.gpu
 
 # Two arithmetic paths are tested (engine.USE_TC):
 #   'fp32' : exact-fp32 SIMT kernels (per-op rounding ~1e-7)  -> the strict bars below
-#   'tc'   : tcgen05 tensor-core kernels with 3xBF16 operand splitting (measured per-op rounding 5e-6..4e-5,
-#            tools/tc_precision.py).  Forward outputs and losses meet the same 1e-3 bar.  Gradients of these
-#            tiny synthetic problems are ill-conditioned (DESIGN.md "Parity"): every implementation's distance
-#            from a float64 evaluation is (condition number) x (its per-op rounding), so the tensor-core path is
-#            held to TC_GRAD_FACTOR x the distance of the float32 references instead of 2 x.
-TC_GRAD_FACTOR = 16.0
+#   'tc'   : tcgen05 tensor-core kernels with scaled fp16 hi/lo operand splitting (measured per-op rounding
+#            1e-7..4e-6 vs 2e-7..2e-6 for the fp32 FMA kernels, tools/tc_precision.py).  Forward outputs and
+#            losses meet the same 1e-3 bar.  Gradients of these tiny synthetic problems are ill-conditioned
+#            (DESIGN.md "Parity"): every implementation's distance from a float64 evaluation is
+#            (condition number) x (its per-op rounding) + arg-max flips, so the tensor-core path is held to
+#            TC_GRAD_FACTOR x the distance of the float32 references instead of 2 x.
+TC_GRAD_FACTOR = 4.0
 
 
 @pytest.fixture(params=['fp32', 'tc'])

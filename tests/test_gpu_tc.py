@@ -5,6 +5,8 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
+TOL_TC = 1e-5  # vs float64: scaled fp16 hi/lo split (22 bits), hi*hi products spread over 3 fp32 TMEM accumulators
+
 
 def rel(a, b):
     a = a.detach().double().cpu()
@@ -27,21 +29,39 @@ def nhwc(x):
     return x.permute(0, 2, 3, 1).contiguous().view(-1, x.shape[1])
 
 
+class Planes(object):
+    """scaled fp16 hi/lo planes + the device amax scalar (fsdet_amax + fsdet_split_f16)"""
+
+    def __init__(self, L, t2d, cpad=None, scaled=True):
+        rows, C = t2d.shape
+        cpad = cpad or C
+        self.src = t2d
+        self.amax = torch.zeros(1, device='cuda')
+        if scaled:
+            L.call('fsdet_amax', t2d.data_ptr(), C, C, rows, self.amax.data_ptr(), st())
+        self.hi = torch.empty(rows, cpad, dtype=torch.float16, device='cuda')
+        self.lo = torch.empty(rows, cpad, dtype=torch.float16, device='cuda')
+        L.call('fsdet_split_f16', t2d.data_ptr(), C, C, cpad, rows, self.amax.data_ptr() if scaled else None,
+               self.hi.data_ptr(), self.lo.data_ptr(), st())
+        self.a = self.amax.data_ptr() if scaled else None
+
+
 def split(L, t2d, cpad=None):
-    rows, C = t2d.shape
-    cpad = cpad or C
-    hi = torch.empty(rows, cpad, dtype=torch.bfloat16, device='cuda')
-    lo = torch.empty(rows, cpad, dtype=torch.bfloat16, device='cuda')
-    L.call('fsdet_split_bf16', t2d.data_ptr(), C, C, cpad, rows, hi.data_ptr(), lo.data_ptr(), st())
-    return hi, lo
+    return Planes(L, t2d, cpad)
 
 
-def test_split_bf16(L):
-    x = torch.randn(1000, 64, device='cuda') * 3
-    hi, lo = split(L, x)
-    assert torch.equal(hi, x.to(torch.bfloat16))
-    assert rel(hi.float() + lo.float(), x) < 2e-5
-    assert torch.equal(lo, (x - hi.float()).to(torch.bfloat16))
+def test_amax_split_f16(L):
+    x = torch.randn(1000, 64, device='cuda') * 3e-4
+    p = Planes(L, x)
+    assert p.amax.item() == x.abs().max().item()
+    import math
+    sc = 2.0 ** (10 - math.frexp(p.amax.item())[1])
+    assert 512 <= p.amax.item() * sc < 1024
+    assert torch.equal(p.hi, (x * sc).to(torch.float16))
+    assert torch.equal(p.lo, (x * sc - p.hi.float()).to(torch.float16))
+    assert rel((p.hi.float() + p.lo.float()) / sc, x) < 1e-6
+    q = Planes(L, x * 1e4, scaled=False)
+    assert torch.equal(q.hi, (x * 1e4).to(torch.float16))
 
 
 @pytest.mark.parametrize('B,H,W,C,ks,m0,c0,tap', [
@@ -49,13 +69,13 @@ def test_split_bf16(L):
     (3, 26, 26, 64, 1, 640, 0, 0), (1, 52, 52, 64, 3, 2560, 0, 2), (5, 6, 6, 64, 3, 128, 0, 6), (1, 8, 8, 64, 3, 0, 0, 5)])
 def test_tma_im2col_tile(L, B, H, W, C, ks, m0, c0, tap):
     g = torch.Generator(device='cuda').manual_seed(m0 + tap)
-    x = torch.randn(B, H, W, C, device='cuda', generator=g).to(torch.bfloat16)
-    out = torch.zeros(128, 64, dtype=torch.bfloat16, device='cuda')
+    x = torch.randn(B, H, W, C, device='cuda', generator=g).to(torch.float16)
+    out = torch.zeros(128, 64, dtype=torch.float16, device='cuda')
     L.call('fsdet_debug_im2col_tile', x.data_ptr(), B, H, W, C, ks, m0, c0, tap, out.data_ptr(), st())
     torch.cuda.synchronize()
     pad = (ks - 1) // 2
     r, s = tap // ks, tap % ks
-    exp = torch.zeros(128, 64, dtype=torch.bfloat16, device='cuda')
+    exp = torch.zeros(128, 64, dtype=torch.float16, device='cuda')
     for i in range(128):
         m = m0 + i
         n, rem = divmod(m, H * W)
@@ -79,22 +99,22 @@ def test_conv_tc_fwd(L, B, H, W, Cin, Cout, k):
     g = torch.Generator(device='cuda').manual_seed(B + H + Cin + Cout)
     x = torch.randn(B, Cin, H, W, device='cuda', generator=g)
     w = torch.randn(Cout, Cin, k, k, device='cuda', generator=g) * 0.05
-    ref = F.conv2d(x, w, None, 1, (k - 1) // 2)
-    xh, xl = split(L, nhwc(x))
-    wh, wl = split(L, w.permute(0, 2, 3, 1).contiguous().view(Cout, -1))
+    ref = F.conv2d(x.double(), w.double(), None, 1, (k - 1) // 2)
+    X = split(L, nhwc(x))
+    Wp = split(L, w.permute(0, 2, 3, 1).contiguous().view(Cout, -1))
     assert L.lib.fsdet_conv_tc_supported(Cin, Cout, k)
     ld = Cout + 4
     z = torch.zeros(B * H * W, ld, device='cuda')
-    L.call('fsdet_conv_tc_fwd', xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), z.data_ptr(), ld, B, H, W, Cin, Cout,
-           k, 0, st())
+    L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), X.lo.data_ptr(), Wp.hi.data_ptr(), Wp.lo.data_ptr(), X.a, Wp.a, z.data_ptr(), ld,
+           B, H, W, Cin, Cout, k, 0, st())
     torch.cuda.synchronize()
     got = z[:, :Cout].contiguous().view(B, H, W, Cout).permute(0, 3, 1, 2)
-    assert rel(got, ref) < 5e-5
+    assert rel(got, ref) < TOL_TC
     assert (z[:, Cout:] == 0).all()
-    L.call('fsdet_conv_tc_fwd', xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), z.data_ptr(), ld, B, H, W, Cin, Cout,
-           k, 1, st())
+    L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), X.lo.data_ptr(), Wp.hi.data_ptr(), Wp.lo.data_ptr(), X.a, Wp.a, z.data_ptr(), ld,
+           B, H, W, Cin, Cout, k, 1, st())
     got2 = z[:, :Cout].contiguous().view(B, H, W, Cout).permute(0, 3, 1, 2)
-    assert rel(got2, 2 * ref) < 5e-5
+    assert rel(got2, 2 * ref) < TOL_TC
 
 
 def test_colstats(L):
@@ -121,19 +141,20 @@ WG_CASES = [
 def test_conv_tc_wgrad(L, B, H, W, Cin, Cout, k):
     g = torch.Generator(device='cuda').manual_seed(B + H + Cin + Cout + 1)
     x = torch.randn(B, Cin, H, W, device='cuda', generator=g)
-    w = (torch.randn(Cout, Cin, k, k, device='cuda', generator=g) * 0.05).requires_grad_(True)
+    w0 = torch.randn(Cout, Cin, k, k, device='cuda', generator=g) * 0.05
+    w = w0.double().requires_grad_(True)
     dz = torch.randn(B, Cout, H, W, device='cuda', generator=g)
-    F.conv2d(x, w, None, 1, (k - 1) // 2).backward(dz)
-    xh, xl = split(L, nhwc(x))
-    dh, dl = split(L, nhwc(dz))
+    F.conv2d(x.double(), w, None, 1, (k - 1) // 2).backward(dz.double())   # float64 reference
+    X = split(L, nhwc(x))
+    D = split(L, nhwc(dz))
     assert L.lib.fsdet_conv_tc_wgrad_supported(Cin, Cout, k)
     nws = L.lib.fsdet_conv_tc_wgrad_workspace_floats(B, H, W, Cin, Cout, k)
     ws = torch.empty(max(nws, 4), device='cuda')
     dw = torch.full((Cout, k * k, Cin), 7.0, device='cuda')
-    L.call('fsdet_conv_tc_wgrad', xh.data_ptr(), xl.data_ptr(), dh.data_ptr(), dl.data_ptr(), dw.data_ptr(), ws.data_ptr(), nws,
-           B, H, W, Cin, Cout, k, st())
+    L.call('fsdet_conv_tc_wgrad', X.hi.data_ptr(), X.lo.data_ptr(), D.hi.data_ptr(), D.lo.data_ptr(), X.a, D.a, dw.data_ptr(),
+           ws.data_ptr(), nws, B, H, W, Cin, Cout, k, st())
     torch.cuda.synchronize()
-    assert rel(dw.view(Cout, k, k, Cin).permute(0, 3, 1, 2), w.grad) < 5e-5
+    assert rel(dw.view(Cout, k, k, Cin).permute(0, 3, 1, 2), w.grad) < TOL_TC
 
 
 def test_conv_tc_padded_channels_and_small_cout(L):
@@ -142,27 +163,29 @@ def test_conv_tc_padded_channels_and_small_cout(L):
     g = torch.Generator(device='cuda').manual_seed(3)
     x = torch.randn(B, Cin, H, W, device='cuda', generator=g, requires_grad=True)
     w = (torch.randn(Cout, Cin, k, k, device='cuda', generator=g) * 0.05).requires_grad_(True)
-    dz = torch.randn(B, Cout, H, W, device='cuda', generator=g)
+    dz = torch.randn(B, Cout, H, W, device='cuda', generator=g) * 1e-5   # tiny gradients: exercises the scaling
     ref = F.conv2d(x, w, None, 1, 1)
     ref.backward(dz)
-    xh, xl = split(L, nhwc(x.detach()), 64)
-    wrows = w.detach().permute(0, 2, 3, 1).contiguous().view(Cout * k * k, Cin)
-    wh, wl = split(L, wrows, 64)
+    X = split(L, nhwc(x.detach()), 64)
+    Wp = split(L, w.detach().permute(0, 2, 3, 1).contiguous().view(Cout * k * k, Cin), 64)
     z = torch.zeros(B * H * W, Cout, device='cuda')
-    L.call('fsdet_conv_tc_fwd', xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), z.data_ptr(), Cout, B, H, W, 64, Cout, k, 0, st())
-    assert rel(z.view(B, H, W, Cout).permute(0, 3, 1, 2), ref) < 5e-5
+    L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), X.lo.data_ptr(), Wp.hi.data_ptr(), Wp.lo.data_ptr(), X.a, Wp.a, z.data_ptr(), Cout,
+           B, H, W, 64, Cout, k, 0, st())
+    assert rel(z.view(B, H, W, Cout).permute(0, 3, 1, 2), ref) < TOL_TC
     # dgrad: GEMM Cin = 64 (dz channels), Cout = 32
     wt = torch.empty(Cin, k * k, Cout, device='cuda')
     L.call('fsdet_weight_flip_transpose', w.detach().permute(0, 2, 3, 1).contiguous().data_ptr(), wt.data_ptr(), Cout, k * k, Cin, st())
-    th, tl = split(L, wt.view(Cin, k * k * Cout))
-    dh, dl = split(L, nhwc(dz))
+    T = split(L, wt.view(Cin, k * k * Cout))
+    D = split(L, nhwc(dz))
     dx = torch.zeros(B * H * W, Cin, device='cuda')
-    L.call('fsdet_conv_tc_fwd', dh.data_ptr(), dl.data_ptr(), th.data_ptr(), tl.data_ptr(), dx.data_ptr(), Cin, B, H, W, Cout, Cin, k, 0, st())
-    assert rel(dx.view(B, H, W, Cin).permute(0, 3, 1, 2), x.grad) < 5e-5
+    L.call('fsdet_conv_tc_fwd', D.hi.data_ptr(), D.lo.data_ptr(), T.hi.data_ptr(), T.lo.data_ptr(), D.a, T.a, dx.data_ptr(), Cin,
+           B, H, W, Cout, Cin, k, 0, st())
+    assert rel(dx.view(B, H, W, Cin).permute(0, 3, 1, 2), x.grad) < TOL_TC
     # wgrad with padded input channels: result [Cout][9][64], first 32 channels valid, rest zero
     nws = L.lib.fsdet_conv_tc_wgrad_workspace_floats(B, H, W, 64, Cout, k)
     ws = torch.empty(max(nws, 4), device='cuda')
     dw = torch.full((Cout, k * k, 64), 7.0, device='cuda')
-    L.call('fsdet_conv_tc_wgrad', xh.data_ptr(), xl.data_ptr(), dh.data_ptr(), dl.data_ptr(), dw.data_ptr(), ws.data_ptr(), nws, B, H, W, 64, Cout, k, st())
-    assert rel(dw[:, :, :32].reshape(Cout, k, k, Cin).permute(0, 3, 1, 2), w.grad) < 5e-5
+    L.call('fsdet_conv_tc_wgrad', X.hi.data_ptr(), X.lo.data_ptr(), D.hi.data_ptr(), D.lo.data_ptr(), X.a, D.a, dw.data_ptr(),
+           ws.data_ptr(), nws, B, H, W, 64, Cout, k, st())
+    assert rel(dw[:, :, :32].reshape(Cout, k, k, Cin).permute(0, 3, 1, 2), w.grad) < TOL_TC
     assert (dw[:, :, 32:] == 0).all()
