@@ -26,6 +26,8 @@ SIGNATURES = {
     'fsdet_conv_stat_rows': ('i', 'i'),
     'fsdet_conv_wgrad': ('pipippz iiiiii p'.replace(' ', ''), 'i'),
     'fsdet_conv_wgrad_workspace_floats': ('iiiiii', 'z'),
+    'fsdet_conv_first_wgrad': ('ppippziiiip', 'i'),
+    'fsdet_conv_first_wgrad_workspace_floats': ('iiii', 'z'),
     'fsdet_weight_flip_transpose': ('ppiiip', 'i'),
     'fsdet_pad_channels': ('pipizp', 'i'),
     'fsdet_conv_tc_supported': ('iii', 'i'),
@@ -58,7 +60,7 @@ SIGNATURES = {
     'fsdet_region_decode': ('ppiiiiippp', 'i'),
     'fsdet_build_targets': ('pppiiiiifffqppppppppppp', 'i'),
     'fsdet_region_loss_grad': ('ppppp iiiiiiii ppppppppp ff ii p p'.replace(' ', ''), 'i'),
-    'fsdet_sgd_step': ('ppppppiiffffip', 'i'),
+    'fsdet_sgd_step': ('ppppppiiffffipp', 'i'),
     'fsdet_fill': ('pfzp', 'i'),
 }
 

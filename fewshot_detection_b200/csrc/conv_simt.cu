@@ -405,6 +405,50 @@ __global__ void pad_channels_kernel(const float* __restrict__ in, int cin, float
     out[i] = c < cin ? in[r * cin + c] : 0.f;
 }
 
+// ---------------------------------------------------------------------------
+// First-layer weight gradient (Cin padded to 4, Cout <= 32, 3x3): dw[co][tap][ci] = sum_p dz[p][co] * x[p+tap][ci]
+// HBM-bound (reads dz once, 128 B per pixel).  One CTA walks image rows: the dz row and the three x rows
+// it needs are staged in shared memory; thread (tap, co) keeps its 4 input-channel sums in registers for all
+// rows of the CTA, partials are reduced in a fixed order afterwards.
+__global__ void __launch_bounds__(288) conv_first_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, int lddz,
+                                                               float* __restrict__ part, int B, int H, int W, int Cout) {
+    extern __shared__ __align__(16) float sm[];
+    float4* xs = reinterpret_cast<float4*>(sm);              // [3][W + 2] pixels of 4 channels (zero halo)
+    float* ds = sm + 3 * (W + 2) * 4;                        // [W][32]
+    const int tid = threadIdx.x;
+    const int co = tid & 31, tap = tid >> 5;                 // 9 warps = 9 taps
+    const int ty = tap / 3, tx = tap - ty * 3;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long rows = (long long)B * H;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int b = (int)(row / H), h = (int)(row - (long long)b * H);
+        __syncthreads();
+        for (int i = tid; i < 3 * (W + 2); i += blockDim.x) {
+            int r = i / (W + 2), c = i - r * (W + 2);
+            int hh = h + r - 1, ww = c - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = ldg4(x + (((long long)b * H + hh) * W + ww) * 4);
+            xs[i] = v;
+        }
+        const float* drow = dz + (row * W) * lddz;
+        for (int i = tid; i < W * 8; i += blockDim.x) {      // 8 float4 per pixel (32 channels, zero beyond Cout)
+            int pw = i >> 3, c4 = (i & 7) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c4 < Cout) v = ldg4(drow + (long long)pw * lddz + c4);
+            *reinterpret_cast<float4*>(ds + pw * 32 + c4) = v;
+        }
+        __syncthreads();
+        const float4* xr = xs + ty * (W + 2) + tx;           // x[h + ty - 1][w + tx - 1] for w = 0
+#pragma unroll 4
+        for (int w = 0; w < W; ++w) {
+            const float d = ds[w * 32 + co];
+            const float4 v = xr[w];
+            acc.x = fmaf(d, v.x, acc.x); acc.y = fmaf(d, v.y, acc.y); acc.z = fmaf(d, v.z, acc.z); acc.w = fmaf(d, v.w, acc.w);
+        }
+    }
+    if (co < Cout) *reinterpret_cast<float4*>(part + ((long long)blockIdx.x * Cout + co) * 36 + tap * 4) = acc;
+}
+
 static int wgrad_splits(long long M, int Cin, int Cout, int ks, int bmc) {
     int K = ks * ks * Cin;
     long long tiles = (long long)ceil_div(K, 128) * ceil_div(Cout, bmc);
@@ -506,4 +550,41 @@ extern "C" int fsdet_pad_channels(const float* in, int cin, float* out, int cout
     if (n == 0) return 0;
     pad_channels_kernel<<<ceil_div((long long)n, 256), 256, 0, (cudaStream_t)stream>>>(in, cin, out, cout, rows);
     return launch_status("pad_channels");
+}
+
+static int first_wgrad_ctas(int B, int H) {
+    long long rows = (long long)B * H;
+    long long n = 3LL * kNumSMs;
+    return (int)(rows < n ? rows : n);
+}
+
+extern "C" size_t fsdet_conv_first_wgrad_workspace_floats(int B, int H, int W, int Cout) {
+    (void)W;
+    return (size_t)first_wgrad_ctas(B, H) * Cout * 36;
+}
+
+extern "C" int fsdet_conv_first_wgrad(const float* x, const float* dz, int lddz, float* dw, float* workspace,
+                                      size_t workspace_floats, int B, int H, int W, int Cout, void* stream) {
+    FSDET_CHECK_ARG(x && dz && dw && workspace, "conv_first_wgrad: null pointer");
+    FSDET_CHECK_ARG(Cout > 0 && Cout <= 32 && Cout % 4 == 0 && lddz % 4 == 0, "conv_first_wgrad: Cout=%d lddz=%d", Cout, lddz);
+    FSDET_CHECK_ARG(aligned16(x) && aligned16(dz) && aligned16(dw) && aligned16(workspace), "conv_first_wgrad: alignment");
+    const int ctas = first_wgrad_ctas(B, H);
+    FSDET_CHECK_ARG(workspace_floats >= (size_t)ctas * Cout * 36, "conv_first_wgrad: workspace too small");
+    if (ctas == 0) return 0;
+    const size_t smem = ((size_t)3 * (W + 2) * 4 + (size_t)W * 32) * sizeof(float);
+    FSDET_CHECK_ARG(smem <= 200 * 1024, "conv_first_wgrad: image width %d too large", W);
+    cudaStream_t s = (cudaStream_t)stream;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_first_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("conv_first_wgrad: %s", cudaGetErrorString(e)); return (int)e; }
+        smem_set = smem;
+    }
+    conv_first_wgrad_kernel<<<ctas, 288, smem, s>>>(x, dz, lddz, workspace, B, H, W, Cout);
+    int st = launch_status("conv_first_wgrad");
+    if (st) return st;
+    long long n4 = (long long)Cout * 36 / 4;
+    splitk_reduce_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(workspace), reinterpret_cast<float4*>(dw),
+                                                          n4, ctas);
+    return launch_status("conv_first_wgrad_reduce");
 }

@@ -12,7 +12,11 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(float* const* __restrict
                                                         float* const* __restrict__ moms, const long long* __restrict__ sizes,
                                                         const int32_t* __restrict__ chunk_tensor,
                                                         const long long* __restrict__ chunk_offset, int chunk_elems, float lr,
-                                                        float momentum, float dampening, float wd, int first) {
+                                                        float momentum, float dampening, float wd, int first,
+                                                        const float* __restrict__ hyper) {
+    if (hyper) {  // CUDA-graph mode: lr / momentum / dampening / weight decay live in device memory
+        lr = hyper[0]; momentum = hyper[1]; dampening = hyper[2]; wd = hyper[3];
+    }
     const int t = chunk_tensor[blockIdx.x];
     const long long off = chunk_offset[blockIdx.x];
     float* __restrict__ p = params[t] + off;
@@ -57,11 +61,12 @@ using namespace fsdet;
 
 extern "C" int fsdet_sgd_step(float* const* params, const float* const* grads, float* const* moms, const long long* sizes,
                               const int32_t* chunk_tensor, const long long* chunk_offset, int n_chunks, int chunk_elems,
-                              float lr, float momentum, float dampening, float weight_decay, int first_step, void* stream) {
+                              float lr, float momentum, float dampening, float weight_decay, int first_step,
+                              const float* hyper_dev, void* stream) {
     FSDET_CHECK_ARG(params && grads && moms && sizes && chunk_tensor && chunk_offset, "sgd_step: null table");
     FSDET_CHECK_ARG(chunk_elems > 0 && chunk_elems % 4 == 0, "sgd_step: chunk_elems must be a positive multiple of 4");
     if (n_chunks == 0) return 0;
     sgd_multi_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(params, grads, moms, sizes, chunk_tensor, chunk_offset,
-                                                                 chunk_elems, lr, momentum, dampening, weight_decay, first_step);
+                                                                 chunk_elems, lr, momentum, dampening, weight_decay, first_step, hyper_dev);
     return launch_status("sgd_step");
 }

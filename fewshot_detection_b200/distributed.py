@@ -55,6 +55,7 @@ class GradAllReducer(object):
         if cur_n:
             self.buckets.append([cur_start, off, cur_n, cur_n])
         self.handles = []
+        self.overlap = True   # launch bucket all-reduces from inside backward (False: one call in finish())
         self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         for r in (getattr(model, '_det', None), getattr(model, '_ler', None), getattr(model, '_net', None)):
             if r is not None:
@@ -71,12 +72,14 @@ class GradAllReducer(object):
             return
         b = self.buckets[bi]
         b[2] -= 1
-        if b[2] == 0 and self.world > 1:
+        if b[2] == 0 and self.world > 1 and self.overlap:
             self.handles.append(dist.all_reduce(self.flat[b[0]:b[1]], op=dist.ReduceOp.SUM, group=self.group,
                                                 async_op=True))
 
     def finish(self):
         """Wait (on the compute stream) for every bucket launched during backward."""
+        if self.world > 1 and not self.overlap:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         for h in self.handles:
             h.wait()
         self.handles = []

@@ -643,6 +643,12 @@ class NetRunner(object):
             if padded:  # crop the zero channels / rows: rows [0, cout) are contiguous, channels via pad_channels
                 call('fsdet_pad_channels', ptr(tgt), ci64, ptr(out_tensor), cin_p, cout * k * k, st)
             return
+        if cin_p == 4 and x.ld == 4 and k == 3 and cout <= 32 and cout % 4 == 0:
+            nws = _lib.lib.fsdet_conv_first_wgrad_workspace_floats(x.B, x.H, x.W, cout)
+            ws = _empty(max(nws, 4), device=dev)
+            self._timed('first_wgrad', flops, 'fsdet_conv_first_wgrad', x.ptr, dz.ptr, dz.ld, ptr(out_tensor), ptr(ws), nws,
+                        x.B, x.H, x.W, cout, st)
+            return
         nws = _lib.lib.fsdet_conv_wgrad_workspace_floats(x.B, x.H, x.W, cin_p, cout, k)
         ws = _empty(max(nws, 4), device=dev)
         self._timed('conv_wgrad', flops, 'fsdet_conv_wgrad', x.ptr, x.ld, dz.ptr, dz.ld, ptr(out_tensor), ptr(ws), nws, x.B,

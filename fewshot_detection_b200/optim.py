@@ -22,6 +22,8 @@ class FusedSGD(torch.optim.Optimizer):
         defaults = dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay)
         super(FusedSGD, self).__init__(params, defaults)
         self._tables = {}
+        self._hyper = {}       # group index -> (device float[4], pinned host float[4]) for CUDA-graph mode
+        self.capturable = False
 
     def _table(self, gi, plist):
         """Device pointer/size/chunk tables for one param group (rebuilt when any pointer changes)."""
@@ -47,6 +49,30 @@ class FusedSGD(torch.optim.Optimizer):
             chunk_offset=torch.tensor(co, dtype=torch.int64).to(dev), n_chunks=len(ct))
         self._tables[gi] = (key, tab)
         return tab
+
+    def prepare(self):
+        """Build the device pointer tables now (they are uploaded with host->device copies, which must not happen
+        inside a CUDA-graph capture). Needs gradients and momentum buffers to exist already."""
+        for gi, group in enumerate(self.param_groups):
+            plist = [p for p in group['params'] if p.grad is not None and 'momentum_buffer' in self.state[p]]
+            if plist:
+                self._table((gi, False), plist)
+
+    def sync_hyper(self):
+        """Graph mode: push lr / momentum / dampening / weight decay of every group to device memory
+        (call outside the captured region, before each replay; a copy is issued only when a value changed)."""
+        for gi, group in enumerate(self.param_groups):
+            dev = group['params'][0].device
+            vals = (float(group['lr']), float(group['momentum']), float(group['dampening']), float(group['weight_decay']))
+            if gi not in self._hyper:
+                self._hyper[gi] = [torch.zeros(4, device=dev), torch.zeros(4).pin_memory(), None]
+            d, h, last = self._hyper[gi]
+            if last != vals:
+                torch.cuda.current_stream().synchronize()   # the previous async copy out of `h` must have completed
+                for i, v in enumerate(vals):
+                    h[i] = v
+                d.copy_(h, non_blocking=True)
+                self._hyper[gi][2] = vals
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -76,5 +102,5 @@ class FusedSGD(torch.optim.Optimizer):
                 call('fsdet_sgd_step', ptr(tab['params']), ptr(tab['grads']), ptr(tab['moms']), ptr(tab['sizes']),
                      ptr(tab['chunk_tensor']), ptr(tab['chunk_offset']), tab['n_chunks'], _CHUNK, float(group['lr']),
                      float(group['momentum']), float(group['dampening']), float(group['weight_decay']),
-                     1 if first else 0, st)
+                     1 if first else 0, ptr(self._hyper[gi][0]) if self.capturable else None, st)
         return loss

@@ -144,8 +144,11 @@ class _RegionBase(nn.Module):
         else:
             tgt_rows = target2d[torch.as_tensor(inds, dtype=torch.long)]
         tgt = _to_device_f64(tgt_rows, dev)
-        anc32 = torch.tensor([float(a) for a in self.anchors], dtype=torch.float32).to(dev, non_blocking=True)
-        anc64 = torch.tensor([float(a) for a in self.anchors], dtype=torch.float64).to(dev, non_blocking=True)
+        key = (str(dev), tuple(float(a) for a in self.anchors))
+        if getattr(self, '_anchor_cache', (None,))[0] != key:   # small constants are uploaded once (CUDA-graph friendly)
+            self._anchor_cache = (key, torch.tensor(key[1], dtype=torch.float32).to(dev),
+                                  torch.tensor(key[1], dtype=torch.float64).to(dev))
+        anc32, anc64 = self._anchor_cache[1], self._anchor_cache[2]
         pred = torch.empty(max(nB, 1) * nA * nH * nW, 4, device=dev)
         call('fsdet_region_decode', ptr(out_c), ptr(inds_t), nB, nA, nC, nH, nW, ptr(anc32), ptr(pred), st)
         tg = torch.empty(9, max(nB, 1), nA, nH, nW, device=dev)
@@ -157,7 +160,10 @@ class _RegionBase(nn.Module):
         losses = torch.empty(8, dtype=torch.float64, device=dev)
         imgs_t = None
         if mode == 0:
-            imgs_t = torch.tensor(img_start, dtype=torch.int32).to(dev, non_blocking=True)
+            ikey = (str(dev), tuple(img_start))
+            if getattr(self, '_img_cache', (None,))[0] != ikey:
+                self._img_cache = (ikey, torch.tensor(img_start, dtype=torch.int32).to(dev))
+            imgs_t = self._img_cache[1]
         call('fsdet_region_loss_grad', ptr(out_c), ptr(grad), ptr(inds_t), None, ptr(imgs_t), rows_total, nB, bs, cs, nA,
              nC, nH, nW, *[ptr(tg[i]) for i in range(9)], float(self.coord_scale), float(self.class_scale), mode,
              1 if cfg.metayolo else 0, ptr(losses), st)

@@ -74,6 +74,11 @@ int fsdet_conv_stat_rows(int npix);
 int fsdet_conv_wgrad(const float* x, int ldx, const float* dz, int lddz, float* dw, float* workspace,
                      size_t workspace_floats, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
 size_t fsdet_conv_wgrad_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize);
+/* First-layer weight gradient (x = NHWC4 input images, Cout <= 32, 3x3): dw [Cout][9][4].
+ * HBM-bound row-streaming kernel; workspace float [fsdet_conv_first_wgrad_workspace_floats()]. */
+int fsdet_conv_first_wgrad(const float* x, const float* dz, int lddz, float* dw, float* workspace,
+                           size_t workspace_floats, int B, int H, int W, int Cout, void* stream);
+size_t fsdet_conv_first_wgrad_workspace_floats(int B, int H, int W, int Cout);
 /* wt[ci][kk-1-tap][co] = w[co][tap][ci]  (weights for the input-gradient conv) */
 int fsdet_weight_flip_transpose(const float* w, float* wt, int Cout, int kk, int Cin, void* stream);
 /* copy [rows][cin] -> [rows][cout] channel-padded / -cropped (zero fill) */
@@ -223,10 +228,14 @@ int fsdet_region_loss_grad(const float* output, float* grad_output, const int32_
 /* ---- optimiser (optim.SGD as configured in train_meta.py:143-147) ------ */
 /* One launch over a table of tensors: d = g + wd*p; m = first ? d : mom*m + (1-damp)*d;
  * p -= lr*m.  ptr tables live in device memory: params/grads/moms [n] pointers,
- * sizes [n] element counts, chunk table built by the caller (see optim.py). */
+ * sizes [n] element counts, chunk table built by the caller (see optim.py).
+ * hyper_dev (optional): device float[4] = {lr, momentum, dampening, weight_decay}
+ * overriding the scalar arguments, so that a CUDA-graph-captured step can follow
+ * the driver's learning-rate schedule (train_meta.py:150-163). */
 int fsdet_sgd_step(float* const* params, const float* const* grads, float* const* moms, const long long* sizes,
                    const int32_t* chunk_tensor, const long long* chunk_offset, int n_chunks, int chunk_elems,
-                   float lr, float momentum, float dampening, float weight_decay, int first_step, void* stream);
+                   float lr, float momentum, float dampening, float weight_decay, int first_step,
+                   const float* hyper_dev, void* stream);
 
 /* ---- misc --------------------------------------------------------------- */
 int fsdet_fill(float* p, float v, size_t n, void* stream);

@@ -239,3 +239,18 @@ def test_fused_sgd_matches_torch(L):
             g_['lr'] *= 0.5
     for pa, pb in zip(a, b):
         assert rel(pa, pb) < 1e-6
+
+
+@pytest.mark.parametrize('B,H,W,Cout', [(2, 13, 17, 32), (3, 64, 64, 16), (1, 5, 3, 8), (2, 416, 416, 32)])
+def test_conv_first_wgrad(L, B, H, W, Cout):
+    g = torch.Generator(device='cuda').manual_seed(H + W)
+    x = torch.rand(B, 4, H, W, device='cuda', generator=g)
+    w = torch.zeros(Cout, 4, 3, 3, device='cuda', requires_grad=True)
+    dz = torch.randn(B, Cout, H, W, device='cuda', generator=g)
+    F.conv2d(x.double(), w.double(), None, 1, 1).backward(dz.double())
+    xb, dzb = nhwc(x), nhwc(dz)
+    nws = L.lib.fsdet_conv_first_wgrad_workspace_floats(B, H, W, Cout)
+    ws = torch.empty(nws, device='cuda')
+    dw = torch.empty(Cout, 9, 4, device='cuda')
+    L.call('fsdet_conv_first_wgrad', xb.data_ptr(), dzb.data_ptr(), Cout, dw.data_ptr(), ws.data_ptr(), nws, B, H, W, Cout, st())
+    assert rel(dw.view(Cout, 3, 3, 4).permute(0, 3, 1, 2), w.grad) < 1e-5

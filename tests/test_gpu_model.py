@@ -307,3 +307,52 @@ def test_weight_file_roundtrip(tmp_path):
     assert np.array_equal(raw[:n], c0[1].bias.detach().cpu().numpy())
     w = c0[0].weight.detach().cpu().contiguous().numpy().reshape(-1)
     assert np.array_equal(raw[4 * n:4 * n + w.size], w)
+
+
+def test_cuda_graph_step_matches_eager():
+    """GraphedTrainStep (whole step replayed from a CUDA graph) follows the eager loop, incl. lr changes."""
+    from fewshot_detection_b200 import netcfg
+    from fewshot_detection_b200.optim import FusedSGD
+    from fewshot_detection_b200.distributed import GradAllReducer
+    from fewshot_detection_b200.graph import GraphedTrainStep
+    from seeding import synth_targets, synth_masks
+    det, ler = netcfg.mini_dynamic_blocks(128, 8), netcfg.mini_reweighting_blocks(64, 8, 256)
+    bs, cs = 4, 3
+
+    def batch(it):
+        g = torch.Generator().manual_seed(100 + it)
+        x = torch.rand(bs, 3, 128, 128, generator=g).cuda()
+        metax = torch.rand(cs, 3, 64, 64, generator=g).cuda()
+        return x, metax, torch.from_numpy(synth_masks(cs, 64, 200 + it)).cuda(), torch.from_numpy(synth_targets(bs, cs, 300 + it, max_gt=4))
+
+    runs = []
+    for graph in (False, True):
+        m = _meta(det, ler, 11)
+        opt = FusedSGD(m.parameters(), lr=1e-3, momentum=0.9, dampening=0, weight_decay=5e-4)
+        L = m.models[len(m.models) - 1]
+        L.verbose = False
+        L.seen = 20000
+        red = GradAllReducer(m)
+        gs = GraphedTrainStep(m, L, opt, red) if graph else None
+        losses = []
+        for it in range(5):
+            if it == 3:
+                for gr in opt.param_groups:
+                    gr['lr'] = 1e-4
+            x, metax, mask, tgt = batch(it)
+            L.seen += bs
+            if graph:
+                losses.append(gs(x, metax, mask, tgt).item())
+            else:
+                red.begin_step()
+                loss = L(m(x, metax, mask), tgt)
+                loss.backward()
+                red.finish()
+                opt.step()
+                losses.append(loss.item())
+        runs.append((losses, [p.detach().clone() for p in m.parameters()]))
+    (l0, p0), (l1, p1) = runs
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-5 * abs(a), (l0, l1)
+    for a, b in zip(p0, p1):
+        assert relt(b.cpu(), a.cpu()) < 1e-5
