@@ -314,11 +314,18 @@ def main():
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
     peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.4 PF (B200_PROFILING.md)'
     dom = max(kern, key=lambda k: kern[k]['ms_per_step']) if kern else None
+    traffic = None
+    try:
+        rj = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_r01.json')))
+        if rj.get('kernel') == dom:
+            traffic = rj['traffic_bytes_per_launch']
+    except Exception:
+        pass
     roofline = None
     if dom:
         a = kern[dom]['tflops_algorithmic']
         roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': a, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                    'frac': a / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                    'frac': a / peak_tf, 'traffic': traffic, 'peak_source': peak_src,
                     'share_of_step': kern[dom]['ms_per_step'] / (ms / args.steps), 'kernels': kern,
                     'note': 'tcgen05 implicit GEMM with fp16 hi/lo operand splitting: 3 tensor-core MMAs per fp32-equivalent '
                             'MAC, i.e. the tensor pipe does 3x the algorithmic FLOPs; measured against the bf16 peak. '
