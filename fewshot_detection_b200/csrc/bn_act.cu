@@ -10,28 +10,43 @@
 //   backward: bn_act_bwd_reduce -> sum(du), sum(du*xhat) partials (du = dy through pool+leaky)
 //             bn_bwd_finalize   -> dgamma, dbeta, c1 = dbeta/N, c2 = dgamma/N
 //             bn_act_bwd_apply  -> dz = scale*(du - c1 - xhat*c2)
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace fsdet {
 
+// power-of-two scale that maps a tensor with absolute maximum `a` into [512, 1024)  (same rule as conv_tc.cu)
+__device__ __forceinline__ float plane_scale(float a) {
+    if (!(a > 0.f) || !isfinite(a)) return 1.f;
+    int ex = (int)((__float_as_uint(a) >> 23) & 0xff) - 126;
+    int e = 10 - ex;
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+    return __uint_as_float((uint32_t)(e + 127) << 23);
+}
+
+__device__ __forceinline__ void store_planes4(__half* hi, __half* lo, long long off, float4 v, float sc) {
+    const float f[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
+    __half h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        h[k] = __float2half_rn(f[k]);
+        l[k] = __float2half_rn(f[k] - __half2float(h[k]));
+    }
+    *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<uint2*>(l);
+}
+
+
 // ------------------------------------------------------------ finalize (fwd)
-// grid: ceil(2C/32) blocks of 32x32 threads; column j<C: sum, j>=C: sum of squares
+// generic double-precision column sums of float partial rows (used by the backward finalize of the bias path)
 __global__ void __launch_bounds__(1024) colsum_double_kernel(const float* __restrict__ part, int nparts, int ncols,
                                                              double* __restrict__ out) {
     __shared__ double red[32][33];
     int col = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0;
-    if (col < ncols) {
-        int r = threadIdx.y;
-        for (; r + 96 < nparts; r += 128) {
-            float a = part[(long long)r * ncols + col];
-            float b = part[(long long)(r + 32) * ncols + col];
-            float c = part[(long long)(r + 64) * ncols + col];
-            float d = part[(long long)(r + 96) * ncols + col];
-            s += (double)a + (double)b + (double)c + (double)d;
-        }
-        for (; r < nparts; r += 32) s += (double)part[(long long)r * ncols + col];
-    }
+    if (col < ncols)
+        for (int r = threadIdx.y; r < nparts; r += 32) s += (double)part[(long long)r * ncols + col];
     red[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && col < ncols) {
@@ -58,55 +73,108 @@ __global__ void __launch_bounds__(1024) colsum_dd_kernel(const double* __restric
     }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float momentum, float eps, float* __restrict__ mean,
-                                   float* __restrict__ invstd, float* __restrict__ scale, float* __restrict__ shift,
-                                   int C, int training) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float m, is;
-    if (training) {
-        double mu = sums[c] / count;
-        double var = sums[C + c] / count - mu * mu;
-        if (var < 0.0) var = 0.0;
-        m = (float)mu;
-        is = (float)(1.0 / sqrt(var + (double)eps));
-        if (running_mean) {
-            double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
-            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+// Stage 1: grid (ceil(C/32), S): block (x, y) reduces rows [y*rps, (y+1)*rps) of the conv partial rows
+// [nparts][4C] = (sum | sum of squares | min | max) into red[y][4C] (doubles; sums accumulated in double).
+__global__ void __launch_bounds__(1024) bn_stats_reduce_kernel(const float* __restrict__ part, int nparts, int rps, int C,
+                                                               double* __restrict__ red) {
+    __shared__ double rs[32][33], rq[32][33];
+    __shared__ float rn[32][33], rx[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int r0 = blockIdx.y * rps;
+    const int r1 = min(r0 + rps, nparts);
+    double s = 0.0, q = 0.0;
+    float mn = INFINITY, mx = -INFINITY;
+    if (c < C) {
+        for (int r = r0 + threadIdx.y; r < r1; r += 32) {
+            const float* row = part + (long long)r * 4 * C;
+            s += (double)row[c];
+            q += (double)row[C + c];
+            mn = fminf(mn, row[2 * C + c]);
+            mx = fmaxf(mx, row[3 * C + c]);
         }
-    } else {
-        m = running_mean[c];
-        is = 1.f / sqrtf(running_var[c] + eps);
     }
-    float g = gamma ? gamma[c] : 1.f;
-    float b = beta ? beta[c] : 0.f;
-    float sc = g * is;
-    if (mean) mean[c] = m;
-    if (invstd) invstd[c] = is;
-    scale[c] = sc;
-    shift[c] = b - m * sc;
+    rs[threadIdx.y][threadIdx.x] = s; rq[threadIdx.y][threadIdx.x] = q;
+    rn[threadIdx.y][threadIdx.x] = mn; rx[threadIdx.y][threadIdx.x] = mx;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        s = 0.0; q = 0.0; mn = INFINITY; mx = -INFINITY;
+        for (int i = 0; i < 32; ++i) {
+            s += rs[i][threadIdx.x]; q += rq[i][threadIdx.x];
+            mn = fminf(mn, rn[i][threadIdx.x]); mx = fmaxf(mx, rx[i][threadIdx.x]);
+        }
+        double* dst = red + (long long)blockIdx.y * 4 * C;
+        dst[c] = s; dst[C + c] = q; dst[2 * C + c] = (double)mn; dst[3 * C + c] = (double)mx;
+    }
+}
+
+// Stage 2: fold the S reduced rows, derive mean / invstd / scale / shift, update the running statistics and - from
+// the per-channel range of z and the monotonicity of y = leaky(scale*z + shift) in z - the exact absolute maximum
+// of the activation.  One thread per channel.
+__global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restrict__ red, int S, double count,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                          float momentum, float eps, float* __restrict__ mean,
+                                                          float* __restrict__ invstd, float* __restrict__ scale,
+                                                          float* __restrict__ shift, float slope, float* __restrict__ amax_y,
+                                                          int C, int training) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    float ymax = 0.f;
+    if (c < C) {
+        float m, is;
+        float mn = INFINITY, mx = -INFINITY;
+        if (training) {
+            double s = 0.0, q = 0.0;
+            for (int i = 0; i < S; ++i) {
+                const double* row = red + (long long)i * 4 * C;
+                s += row[c]; q += row[C + c];
+                mn = fminf(mn, (float)row[2 * C + c]); mx = fmaxf(mx, (float)row[3 * C + c]);
+            }
+            double mu = s / count;
+            double var = q / count - mu * mu;
+            if (var < 0.0) var = 0.0;
+            m = (float)mu;
+            is = (float)(1.0 / sqrt(var + (double)eps));
+            if (running_mean) {
+                double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+            }
+        } else {
+            m = running_mean[c];
+            is = 1.f / sqrtf(running_var[c] + eps);
+        }
+        float g = gamma ? gamma[c] : 1.f;
+        float b = beta ? beta[c] : 0.f;
+        float sc = g * is;
+        float sh = b - m * sc;
+        if (mean) mean[c] = m;
+        if (invstd) invstd[c] = is;
+        scale[c] = sc;
+        shift[c] = sh;
+        if (training && mn <= mx)
+            ymax = fmaxf(fabsf(leaky(fmaf(mn, sc, sh), slope)), fabsf(leaky(fmaf(mx, sc, sh), slope)));
+    }
+    if (amax_y && training) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        if ((threadIdx.x & 31) == 0 && isfinite(ymax)) atomicMax(reinterpret_cast<int*>(amax_y), __float_as_int(ymax));
+    }
 }
 
 // ------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(256) bn_act_flat_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ scale,
-                                                          const float* __restrict__ shift, float slope,
-                                                          float* __restrict__ y, int ldy, long long npix, int C4) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long n = npix * C4;
-    if (i >= n) return;
-    long long p = i / C4;
-    int c = (int)(i - p * C4) * 4;
-    float4 v = ldg4(z + p * ldz + c);
-    float4 sc = ldg4(scale + c), sh = ldg4(shift + c);
-    v.x = leaky(fmaf(v.x, sc.x, sh.x), slope);
-    v.y = leaky(fmaf(v.y, sc.y, sh.y), slope);
-    v.z = leaky(fmaf(v.z, sc.z, sh.z), slope);
-    v.w = leaky(fmaf(v.w, sc.w, sh.w), slope);
-    *reinterpret_cast<float4*>(y + p * ldy + c) = v;
-}
+struct FwdArgs {
+    const float* z;
+    const float* scale;
+    const float* shift;
+    const float* amax;   // device scalar the fp16 planes are scaled by (plane_scale)
+    float* yf;           // fp32 full-resolution output (optional)
+    float* yp;           // fp32 pooled output (optional)
+    __half *fh, *fl;     // fp16 hi/lo planes of the full-resolution output [npix][Cpad] (optional)
+    __half *ph, *pl;     // fp16 hi/lo planes of the pooled output (optional)
+    int ldz, ldf, ldp, Cpad;
+    int B, H, W, C;
+    float slope;
+};
 
 __device__ __forceinline__ float4 act4(float4 v, float4 sc, float4 sh, float slope) {
     v.x = leaky(fmaf(v.x, sc.x, sh.x), slope);
@@ -116,22 +184,40 @@ __device__ __forceinline__ float4 act4(float4 v, float4 sc, float4 sh, float slo
     return v;
 }
 
-// one thread = one 2x2 window x 4 channels; windows cover ceil(H/2) x ceil(W/2)
-__global__ void __launch_bounds__(256) bn_act_pool_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ scale,
-                                                          const float* __restrict__ shift, float slope,
-                                                          float* __restrict__ yf, int ldf, float* __restrict__ yp, int ldp,
-                                                          int B, int H, int W, int C4) {
-    const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
+// no pooling: one thread = one pixel x 4 channels (channel index runs to Cpad: the zero padding of the planes)
+__global__ void __launch_bounds__(256) bn_act_flat_kernel(const FwdArgs a) {
+    const int CP4 = a.Cpad >> 2;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long n = (long long)B * H2 * W2 * C4;
+    const long long npix = (long long)a.B * a.H * a.W;
+    if (i >= npix * CP4) return;
+    long long p = i / CP4;
+    int c = (int)(i - p * CP4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < a.C) {
+        v = act4(ldg4(a.z + p * a.ldz + c), ldg4(a.scale + c), ldg4(a.shift + c), a.slope);
+        if (a.yf) *reinterpret_cast<float4*>(a.yf + p * a.ldf + c) = v;
+    }
+    if (a.fh) store_planes4(a.fh, a.fl, p * a.Cpad + c, v, plane_scale(__ldg(a.amax)));
+}
+
+// one thread = one 2x2 window x 4 channels; windows cover ceil(H/2) x ceil(W/2)
+__global__ void __launch_bounds__(256) bn_act_pool_kernel(const FwdArgs a) {
+    const int H = a.H, W = a.W;
+    const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
+    const int CP4 = a.Cpad >> 2;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long n = (long long)a.B * H2 * W2 * CP4;
     if (i >= n) return;
-    int c = (int)(i % C4) * 4;
-    long long wi = i / C4;
+    int c = (int)(i % CP4) * 4;
+    long long wi = i / CP4;
     int w2 = (int)(wi % W2);
     long long t = wi / W2;
     int h2 = (int)(t % H2);
     int b = (int)(t / H2);
-    float4 sc = ldg4(scale + c), sh = ldg4(shift + c);
+    const bool cok = c < a.C;
+    const float psc = (a.fh || a.ph) ? plane_scale(__ldg(a.amax)) : 1.f;
+    float4 sc = make_float4(0, 0, 0, 0), sh = sc;
+    if (cok) { sc = ldg4(a.scale + c); sh = ldg4(a.shift + c); }
     float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy)
@@ -140,14 +226,19 @@ __global__ void __launch_bounds__(256) bn_act_pool_kernel(const float* __restric
             int h = h2 * 2 + dy, w = w2 * 2 + dx;
             if (h < H && w < W) {
                 long long p = ((long long)b * H + h) * W + w;
-                float4 v = act4(ldg4(z + p * ldz + c), sc, sh, slope);
-                if (yf) *reinterpret_cast<float4*>(yf + p * ldf + c) = v;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (cok) {
+                    v = act4(ldg4(a.z + p * a.ldz + c), sc, sh, a.slope);
+                    if (a.yf) *reinterpret_cast<float4*>(a.yf + p * a.ldf + c) = v;
+                }
+                if (a.fh) store_planes4(a.fh, a.fl, p * a.Cpad + c, v, psc);
                 mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
             }
         }
-    if (yp && h2 < Hp && w2 < Wp) {
+    if (h2 < Hp && w2 < Wp) {
         long long pp = ((long long)b * Hp + h2) * Wp + w2;
-        *reinterpret_cast<float4*>(yp + pp * ldp + c) = mx;
+        if (a.yp && cok) *reinterpret_cast<float4*>(a.yp + pp * a.ldp + c) = mx;
+        if (a.ph) store_planes4(a.ph, a.pl, pp * a.Cpad + c, mx, psc);
     }
 }
 
@@ -162,6 +253,7 @@ struct BwdArgs {
     const float* invstd;
     const double* coef;
     float* dz;
+    float* amax_out;
     double* partial;
     int ldz, ld_dyf, ld_dyp, lddz;
     int B, H, W, C;
@@ -194,6 +286,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BwdArgs a) {
         }
     }
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    float amax = 0.f;
 
     for (long long wi = (long long)blockIdx.x * blockDim.y + threadIdx.y; cok && wi < nwin;
          wi += (long long)gridDim.x * blockDim.y) {
@@ -261,10 +354,19 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BwdArgs a) {
                     s2[k] += (double)d * xh;
                 }
             }
-            if (APPLY) *reinterpret_cast<float4*>(a.dz + pix[q] * a.lddz + c) = make_float4(o[0], o[1], o[2], o[3]);
+            if (APPLY) {
+                *reinterpret_cast<float4*>(a.dz + pix[q] * a.lddz + c) = make_float4(o[0], o[1], o[2], o[3]);
+                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
+            }
         }
     }
 
+    if (APPLY && a.amax_out) {  // absolute maximum of dz (scale of its fp16 planes), one atomic per warp
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && isfinite(amax) && amax > 0.f)
+            atomicMax(reinterpret_cast<int*>(a.amax_out), __float_as_int(amax));
+    }
     if (!APPLY) {
         // reduce over threadIdx.y -> one partial row per blockIdx.x
         extern __shared__ double red[];  // [blockDim.y][TC*8]
@@ -300,6 +402,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double c
     }
 }
 
+constexpr int kBnSplits = 64;
+
 static int bwd_rows(int B, int H, int W) {
     long long nwin = (long long)B * ((H + 1) / 2) * ((W + 1) / 2);
     long long r = (nwin + 63) / 64;
@@ -312,56 +416,68 @@ static int bwd_rows(int B, int H, int W) {
 
 using namespace fsdet;
 
-// The double-precision column sums (2*C doubles) are written behind the
-// partial rows: callers size the partial buffer with one extra "row pair"
-// (rows = fsdet_*_rows() + 2 gives 2*(2C) floats = 2C doubles).
-static inline double* sums_area(const float* partial, int nrows, int C) {
-    return reinterpret_cast<double*>(const_cast<float*>(partial) + (size_t)nrows * 2 * C);
-}
-
 extern "C" int fsdet_bn_bwd_rows(int B, int H, int W) { return bwd_rows(B, H, W); }
 
 extern "C" int fsdet_bn_finalize(const float* stat_partial, int nparts, double count, const float* gamma,
                                  const float* beta, float* running_mean, float* running_var, float momentum, float eps,
-                                 float* mean, float* invstd, float* scale, float* shift, int C, int training,
-                                 void* stream) {
+                                 float* mean, float* invstd, float* scale, float* shift, float slope, float* amax_y, int C,
+                                 int training, void* stream) {
     FSDET_CHECK_ARG(scale && shift && C > 0, "bn_finalize: bad args");
     cudaStream_t s = (cudaStream_t)stream;
-    double* sums = nullptr;
     if (training) {
         FSDET_CHECK_ARG(stat_partial && nparts > 0, "bn_finalize: training needs the conv partials");
-        FSDET_CHECK_ARG((((size_t)nparts * 2 * C) & 1) == 0, "bn_finalize: odd partial size");
-        sums = sums_area(stat_partial, nparts, C);
-        dim3 block(32, 32), grid(ceil_div(2 * C, 32));
-        colsum_double_kernel<<<grid, block, 0, s>>>(stat_partial, nparts, 2 * C, sums);
-        int st = launch_status("bn_finalize/colsum");
-        if (st) return st;
     } else {
         FSDET_CHECK_ARG(running_mean && running_var, "bn_finalize: eval needs running stats");
     }
-    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(sums, count, gamma, beta, running_mean, running_var, momentum,
-                                                        eps, mean, invstd, scale, shift, C, training);
+    if (amax_y) {
+        cudaError_t e = cudaMemsetAsync(amax_y, 0, sizeof(float), s);
+        if (e != cudaSuccess) { set_error("bn_finalize: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    const double* red = nullptr;
+    int S = 0;
+    if (training) {
+        // scratch for the stage-1 result lives behind the partial rows (fsdet_bn_stat_scratch_rows() extra rows)
+        S = ceil_div(nparts, 64);
+        if (S > kBnSplits) S = kBnSplits;
+        const int rps = ceil_div(nparts, S);
+        S = ceil_div(nparts, rps);
+        double* scratch = reinterpret_cast<double*>(const_cast<float*>(stat_partial) + (size_t)nparts * 4 * C);
+        dim3 block(32, 32), grid(ceil_div(C, 32), S);
+        bn_stats_reduce_kernel<<<grid, block, 0, s>>>(stat_partial, nparts, rps, C, scratch);
+        int st = launch_status("bn_finalize/reduce");
+        if (st) return st;
+        red = scratch;
+    }
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(red, S, count, gamma, beta, running_mean, running_var, momentum, eps, mean,
+                                                        invstd, scale, shift, slope, amax_y, C, training);
     return launch_status("bn_finalize");
 }
 
-extern "C" int fsdet_bn_act_fwd(const float* z, int ldz, const float* scale, const float* shift, float slope,
-                                float* y_full, int ld_full, float* y_pool, int ld_pool, int B, int H, int W, int C,
-                                void* stream) {
-    FSDET_CHECK_ARG(z && scale && shift && (y_full || y_pool), "bn_act_fwd: null pointer");
+extern "C" int fsdet_bn_stat_scratch_rows(void) { return 2 * kBnSplits; }  // kBnSplits rows of 4C doubles
+
+extern "C" int fsdet_bn_act_fwd(const float* z, int ldz, const float* scale, const float* shift, float slope, float* y_full,
+                                int ld_full, float* y_pool, int ld_pool, void* full_hi, void* full_lo, void* pool_hi,
+                                void* pool_lo, int Cpad, const float* amax, int B, int H, int W, int C, void* stream) {
+    const bool planes = full_hi || pool_hi;
+    FSDET_CHECK_ARG(z && scale && shift && (y_full || y_pool || planes), "bn_act_fwd: null pointer");
     FSDET_CHECK_ARG(C % 4 == 0 && ldz % 4 == 0 && (!y_full || ld_full % 4 == 0) && (!y_pool || ld_pool % 4 == 0),
                     "bn_act_fwd: C=%d and leading dims must be multiples of 4", C);
+    FSDET_CHECK_ARG(!planes || (amax && Cpad >= C && Cpad % 4 == 0 && (!full_hi || full_lo) && (!pool_hi || pool_lo)),
+                    "bn_act_fwd: plane outputs need amax, lo planes and Cpad >= C");
     cudaStream_t s = (cudaStream_t)stream;
-    int C4 = C / 4;
-    if (!y_pool) {
-        long long n = (long long)B * H * W * C4;
+    FwdArgs a;
+    a.z = z; a.scale = scale; a.shift = shift; a.amax = amax; a.yf = y_full; a.yp = y_pool;
+    a.fh = (__half*)full_hi; a.fl = (__half*)full_lo; a.ph = (__half*)pool_hi; a.pl = (__half*)pool_lo;
+    a.ldz = ldz; a.ldf = ld_full; a.ldp = ld_pool; a.Cpad = planes ? Cpad : C; a.B = B; a.H = H; a.W = W; a.C = C; a.slope = slope;
+    const int CP4 = a.Cpad / 4;
+    if (!y_pool && !pool_hi) {
+        long long n = (long long)B * H * W * CP4;
         if (n == 0) return 0;
-        bn_act_flat_kernel<<<ceil_div(n, 256), 256, 0, s>>>(z, ldz, scale, shift, slope, y_full, ld_full,
-                                                            (long long)B * H * W, C4);
+        bn_act_flat_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a);
     } else {
-        long long n = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * C4;
+        long long n = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * CP4;
         if (n == 0) return 0;
-        bn_act_pool_kernel<<<ceil_div(n, 256), 256, 0, s>>>(z, ldz, scale, shift, slope, y_full, ld_full, y_pool,
-                                                            ld_pool, B, H, W, C4);
+        bn_act_pool_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a);
     }
     return launch_status("bn_act_fwd");
 }
@@ -389,7 +505,7 @@ extern "C" int fsdet_bn_act_bwd_reduce(const float* z, int ldz, const float* dy_
     FSDET_CHECK_ARG(C % 4 == 0 && ldz % 4 == 0 && ld_dyf % 4 == 0 && ld_dyp % 4 == 0, "bn_act_bwd_reduce: alignment");
     BwdArgs a;
     a.z = z; a.dyf = dy_full; a.dyp = dy_pool; a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd;
-    a.coef = nullptr; a.dz = nullptr; a.partial = partial; a.ldz = ldz; a.ld_dyf = ld_dyf; a.ld_dyp = ld_dyp; a.lddz = 0;
+    a.coef = nullptr; a.dz = nullptr; a.amax_out = nullptr; a.partial = partial; a.ldz = ldz; a.ld_dyf = ld_dyf; a.ld_dyp = ld_dyp; a.lddz = 0;
     a.B = B; a.H = H; a.W = W; a.C = C; a.slope = slope; a.has_bn = has_bn;
     return launch_bwd(false, a, (cudaStream_t)stream);
 }
@@ -410,15 +526,19 @@ extern "C" int fsdet_bn_bwd_finalize(const double* partial, int nparts, double c
 
 extern "C" int fsdet_bn_act_bwd_apply(const float* z, int ldz, const float* dy_full, int ld_dyf, const float* dy_pool,
                                       int ld_dyp, const float* scale, const float* shift, const float* mean,
-                                      const float* invstd, const double* coef, float slope, float* dz, int lddz, int B,
-                                      int H, int W, int C, int has_bn, void* stream) {
+                                      const float* invstd, const double* coef, float slope, float* dz, int lddz,
+                                      float* amax_out, int B, int H, int W, int C, int has_bn, void* stream) {
     FSDET_CHECK_ARG(z && scale && shift && dz && (dy_full || dy_pool), "bn_act_bwd_apply: null pointer");
     FSDET_CHECK_ARG(!has_bn || (mean && invstd && coef), "bn_act_bwd_apply: BN needs mean/invstd/coef");
     FSDET_CHECK_ARG(C % 4 == 0 && ldz % 4 == 0 && ld_dyf % 4 == 0 && ld_dyp % 4 == 0 && lddz % 4 == 0,
                     "bn_act_bwd_apply: alignment");
     BwdArgs a;
     a.z = z; a.dyf = dy_full; a.dyp = dy_pool; a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd;
-    a.coef = coef; a.dz = dz; a.partial = nullptr; a.ldz = ldz; a.ld_dyf = ld_dyf; a.ld_dyp = ld_dyp; a.lddz = lddz;
+    a.coef = coef; a.dz = dz; a.amax_out = amax_out; a.partial = nullptr; a.ldz = ldz; a.ld_dyf = ld_dyf; a.ld_dyp = ld_dyp; a.lddz = lddz;
     a.B = B; a.H = H; a.W = W; a.C = C; a.slope = slope; a.has_bn = has_bn;
+    if (amax_out) {
+        cudaError_t e = cudaMemsetAsync(amax_out, 0, sizeof(float), (cudaStream_t)stream);
+        if (e != cudaSuccess) { set_error("bn_act_bwd_apply: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
     return launch_bwd(true, a, (cudaStream_t)stream);
 }

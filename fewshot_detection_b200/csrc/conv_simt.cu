@@ -200,29 +200,44 @@ __global__ void __launch_bounds__(256) conv_igemm_kernel(const ConvArgs p) {
     }
 
     if (p.stat) {
-        // per-CTA column sums (rows beyond M hold zeros). Reduce the 16 ty-threads
-        // through shared memory (re-using the operand buffers).
-        float* red_s = &As[0][0][0];  // [16][BN]
-        float* red_q = &Bs[0][0][0];  // needs 16*BN floats: 2*16*(BN+4) available
+        // per-CTA column statistics over the valid rows: sum, sum of squares, min, max (BatchNorm partials +
+        // the activation range).  Reduce the 16 ty-threads through shared memory (re-using the operand buffers).
+        float* red_s = &As[0][0][0];       // [16][BN]
+        float* red_mn = red_s + 16 * BN;   // [16][BN]   (As holds 2*16*(128+4) floats)
+        float* red_q = &Bs[0][0][0];       // [16][BN]
+        float* red_mx = red_q + 16 * BN;   // [16][BN]   (Bs holds 2*16*(BN+4) floats)
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            float s = 0.f, q = 0.f;
+            float s = 0.f, q = 0.f, mn = INFINITY, mx = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { s += acc[i][j]; q += acc[i][j] * acc[i][j]; }
+            for (int i = 0; i < 8; ++i) {
+                const long long m = m0 + ((i < 4) ? (ty * 4 + i) : (64 + ty * 4 + (i - 4)));
+                if (m < p.M) {
+                    const float v = acc[i][j];
+                    s += v; q += v * v; mn = fminf(mn, v); mx = fmaxf(mx, v);
+                }
+            }
             red_s[ty * BN + col_of(j)] = s;
             red_q[ty * BN + col_of(j)] = q;
+            red_mn[ty * BN + col_of(j)] = mn;
+            red_mx[ty * BN + col_of(j)] = mx;
         }
         __syncthreads();
         if (tid < BN) {
             int n = n0 + tid;
             if (n < p.Cout) {
-                float s = 0.f, q = 0.f;
+                float s = 0.f, q = 0.f, mn = INFINITY, mx = -INFINITY;
 #pragma unroll
-                for (int t = 0; t < 16; ++t) { s += red_s[t * BN + tid]; q += red_q[t * BN + tid]; }
-                float* dst = p.stat + (long long)blockIdx.x * 2 * p.Cout;
+                for (int t = 0; t < 16; ++t) {
+                    s += red_s[t * BN + tid]; q += red_q[t * BN + tid];
+                    mn = fminf(mn, red_mn[t * BN + tid]); mx = fmaxf(mx, red_mx[t * BN + tid]);
+                }
+                float* dst = p.stat + (long long)blockIdx.x * 4 * p.Cout;
                 dst[n] = s;
                 dst[p.Cout + n] = q;
+                dst[2 * p.Cout + n] = mn;
+                dst[3 * p.Cout + n] = mx;
             }
         }
     }

@@ -79,37 +79,46 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------ column statistics of z (BN partials)
-// one CTA per strip of `strip` pixels: partial[blockIdx.x][c] = sum z, [C + c] = sum z^2
+// one CTA per strip of `strip` pixels: partial[blockIdx.x] = [sum(C) | sum of squares(C) | min(C) | max(C)]
 __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ z, int ld, long long npix, int C, int strip,
                                                        float* __restrict__ part) {
     // threads: x = channel vector lane (float4), y = pixel lane
     const int C4 = C >> 2;
     const int TC = blockDim.x, TY = blockDim.y;
     long long p0 = (long long)blockIdx.x * strip, p1 = p0 + strip < npix ? p0 + strip : npix;
-    extern __shared__ float red[];  // [TY][TC*8]
+    extern __shared__ float red[];  // [TY][TC*16]
     for (int cv0 = 0; cv0 < C4; cv0 += TC) {
         int cv = cv0 + threadIdx.x;
         float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+        float mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (cv < C4)
             for (long long p = p0 + threadIdx.y; p < p1; p += TY) {
                 float4 v = ldg4(z + p * ld + cv * 4);
-                s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-                q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
-            }
-        float* mine = red + ((size_t)threadIdx.y * TC + threadIdx.x) * 8;
+                const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { mine[k] = s[k]; mine[4 + k] = q[k]; }
+                for (int k = 0; k < 4; ++k) {
+                    s[k] += f[k]; q[k] += f[k] * f[k]; mn[k] = fminf(mn[k], f[k]); mx[k] = fmaxf(mx[k], f[k]);
+                }
+            }
+        float* mine = red + ((size_t)threadIdx.y * TC + threadIdx.x) * 16;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { mine[k] = s[k]; mine[4 + k] = q[k]; mine[8 + k] = mn[k]; mine[12 + k] = mx[k]; }
         __syncthreads();
         if (threadIdx.y == 0 && cv < C4) {
             float ts[4] = {0, 0, 0, 0}, tq[4] = {0, 0, 0, 0};
+            float tn[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, tx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             for (int r = 0; r < TY; ++r) {
-                const float* o = red + ((size_t)r * TC + threadIdx.x) * 8;
+                const float* o = red + ((size_t)r * TC + threadIdx.x) * 16;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { ts[k] += o[k]; tq[k] += o[4 + k]; }
+                for (int k = 0; k < 4; ++k) {
+                    ts[k] += o[k]; tq[k] += o[4 + k]; tn[k] = fminf(tn[k], o[8 + k]); tx[k] = fmaxf(tx[k], o[12 + k]);
+                }
             }
-            float* dst = part + (long long)blockIdx.x * 2 * C;
+            float* dst = part + (long long)blockIdx.x * 4 * C;
             *reinterpret_cast<float4*>(dst + cv * 4) = make_float4(ts[0], ts[1], ts[2], ts[3]);
             *reinterpret_cast<float4*>(dst + C + cv * 4) = make_float4(tq[0], tq[1], tq[2], tq[3]);
+            *reinterpret_cast<float4*>(dst + 2 * C + cv * 4) = make_float4(tn[0], tn[1], tn[2], tn[3]);
+            *reinterpret_cast<float4*>(dst + 3 * C + cv * 4) = make_float4(tx[0], tx[1], tx[2], tx[3]);
         }
         __syncthreads();
     }
@@ -711,7 +720,7 @@ extern "C" int fsdet_colstats(const float* z, int ld, size_t npix, int C, float*
     int TCx = C4 >= 32 ? 32 : (C4 >= 16 ? 16 : (C4 >= 8 ? 8 : (C4 >= 4 ? 4 : (C4 >= 2 ? 2 : 1))));
     int TY = 256 / TCx;
     dim3 block(TCx, TY);
-    size_t smem = (size_t)TY * TCx * 8 * sizeof(float);
+    size_t smem = (size_t)TY * TCx * 16 * sizeof(float);
     colstats_kernel<<<fsdet_colstats_rows(npix), block, smem, (cudaStream_t)stream>>>(z, ld, (long long)npix, C, kStatStrip, partial);
     return launch_status("colstats");
 }

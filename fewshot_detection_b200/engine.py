@@ -46,15 +46,18 @@ def same_layout(a, b):
 
 
 class Act(object):
-    """A view [B*H*W pixels] x [C channels at column `off`] of a 2-D NHWC buffer."""
-    __slots__ = ('buf', 'off', 'C', 'B', 'H', 'W', 'g', 'needs_grad', 'parent', 'planes')
+    """A view [B*H*W pixels] x [C channels at column `off`] of a 2-D NHWC fp32 buffer, and/or the fp16 hi/lo
+    planes of the same activation for the tensor-core kernels (`buf` is None when only the planes exist)."""
+    __slots__ = ('buf', 'off', 'C', 'B', 'H', 'W', 'g', 'needs_grad', 'parent', 'planes', 'amax', 'dev')
 
-    def __init__(self, buf, off, C, B, H, W, needs_grad=True, parent=None):
+    def __init__(self, buf, off, C, B, H, W, needs_grad=True, parent=None, dev=None):
         self.buf, self.off, self.C, self.B, self.H, self.W = buf, off, C, B, H, W
         self.g = None            # gradient Act (same geometry) once some consumer wrote it
         self.needs_grad = needs_grad
         self.parent = parent     # concat buffer this view is a slice of
-        self.planes = None       # (hi, lo) bf16 planes of this activation for the tensor-core path
+        self.planes = None       # (hi, lo, amax) fp16 planes of this activation for the tensor-core path
+        self.amax = None         # device scalar |max| if already known (skips the amax pass before splitting)
+        self.dev = buf.device if buf is not None else dev
 
     @property
     def ld(self):
@@ -66,11 +69,19 @@ class Act(object):
 
     @property
     def ptr(self):
+        if self.buf is None:
+            raise RuntimeError('this activation only exists as fp16 planes (internal planning error)')
         return self.buf.data_ptr() + 4 * self.off
 
     @staticmethod
     def new(B, H, W, C, device, needs_grad=True):
         return Act(_empty(B * H * W, C, device=device), 0, C, B, H, W, needs_grad)
+
+    @staticmethod
+    def planes_only(B, H, W, C, device, planes):
+        a = Act(None, 0, C, B, H, W, True, dev=device)
+        a.planes = planes
+        return a
 
     def slice(self, off, C):
         return Act(self.buf, self.off + off, C, self.B, self.H, self.W, self.needs_grad, parent=(self, off))
@@ -86,7 +97,7 @@ class Act(object):
                 raise NotImplementedError('gradient of a concat slice written before the concat buffer')
             self.g = par.g.slice(off, self.C)
             return self.g, 1
-        self.g = Act.new(self.B, self.H, self.W, self.C, self.buf.device, needs_grad=False)
+        self.g = Act.new(self.B, self.H, self.W, self.C, self.dev, needs_grad=False)
         return self.g, 0
 
     def grad_for_read(self):
@@ -226,6 +237,7 @@ class NetRunner(object):
         self.blocks = blocks
         self.models = models  # nn.ModuleList aligned with spec.idx
         self.specs, self.out_ch, self.placement, self.in_ch = compile_blocks(blocks)
+        self.routed = set(l for sp in self.specs if sp.kind == 'route' for l in sp.layers)
         self.in_cpad = _round_up(self.in_ch, 4)
         self.grad_hook = None   # optional callable(param) invoked when a parameter gradient has been enqueued
         self.profile = None     # optional dict name -> [flops, [(start_event, end_event), ...]]
@@ -257,11 +269,13 @@ class NetRunner(object):
             _lib.lib.fsdet_conv_tc_supported(_round_up(cin, 64), cout, k))
 
     @staticmethod
-    def _split_tensor(t2d_ptr, ld, C, rows, dev, st, cpad=None):
-        """fp32 [rows][ld] -> (hi, lo, amax): scaled fp16 planes [rows][cpad] + the device scalar they were scaled by."""
+    def _split_tensor(t2d_ptr, ld, C, rows, dev, st, cpad=None, amax=None):
+        """fp32 [rows][ld] -> (hi, lo, amax): scaled fp16 planes [rows][cpad] + the device scalar they were scaled by
+        (computed here unless the producer already provided it)."""
         cpad = cpad or C
-        amax = torch.empty(1, dtype=torch.float32, device=dev)
-        call('fsdet_amax', t2d_ptr, ld, C, rows, ptr(amax), st)
+        if amax is None:
+            amax = torch.empty(1, dtype=torch.float32, device=dev)
+            call('fsdet_amax', t2d_ptr, ld, C, rows, ptr(amax), st)
         hi = torch.empty(rows, cpad, dtype=torch.float16, device=dev)
         lo = torch.empty(rows, cpad, dtype=torch.float16, device=dev)
         call('fsdet_split_f16', t2d_ptr, ld, C, cpad, rows, ptr(amax), ptr(hi), ptr(lo), st)
@@ -271,8 +285,21 @@ class NetRunner(object):
         """fp16 hi/lo planes [npix][round_up(C, 64)] (+ amax) of an activation (cached: the forward /
         input-gradient GEMM and the weight-gradient GEMM read the same planes)."""
         if act.planes is None:
-            act.planes = self._split_tensor(act.ptr, act.ld, act.C, act.npix, act.buf.device, st, _round_up(act.C, 64))
+            act.planes = self._split_tensor(act.ptr, act.ld, act.C, act.npix, act.dev, st, _round_up(act.C, 64), act.amax)
         return act.planes
+
+    def _consumer_takes_planes(self, spec_pos, cin):
+        """True if the block at position `spec_pos` is a convolution that will read its input only through the
+        tensor-core kernels (forward and weight gradient), so the producer may skip the fp32 activation."""
+        if not USE_TC or not {'fwd', 'dgrad', 'wgrad', 'head'} <= TC_PARTS or spec_pos >= len(self.specs):
+            return False
+        c = self.specs[spec_pos]
+        if c.kind == 'dyn':
+            return cin >= 32 and cin % 4 == 0
+        if c.kind != 'conv' or c.head or not c.bn:
+            return False
+        return self._tc_ok(cin, c.cout, c.k) and c.cout >= 32 and bool(
+            _lib.lib.fsdet_conv_tc_wgrad_supported(_round_up(cin, 64), _round_up(c.cout, 64), c.k))
 
     def _conv(self, name, x, w_ohwi, bias, z, stat_rows_out, cin, cout, k, acc, st):
         """z = conv(x, w) through the tensor-core kernel when the shape allows, else SIMT.
@@ -281,7 +308,7 @@ class NetRunner(object):
         if bias is None and name in TC_PARTS and self._tc_ok(cin, cout, k):
             cpad = _round_up(cin, 64)
             xh, xl, xa = self._planes(x, st)
-            wh, wl, wa = self._split_tensor(ptr(w_ohwi), cin, cin, cout * k * k, x.buf.device, st, cpad)
+            wh, wl, wa = self._split_tensor(ptr(w_ohwi), cin, cin, cout * k * k, x.dev, st, cpad)
             self._timed('conv_tc', flops, 'fsdet_conv_tc_fwd', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(xa), ptr(wa), z.ptr, z.ld,
                         x.B, x.H, x.W, cpad, cout, k, acc, st)
             if stat_rows_out is not None:
@@ -449,7 +476,7 @@ class NetRunner(object):
     def _conv_fwd(self, s, x, training, out_act, st):
         seq = self.models[s.idx]
         conv, bn = self._conv_modules(seq)
-        dev = x.buf.device
+        dev = x.dev
         B, H, W = x.B, x.H, x.W
         npix = x.npix
         w = self._ohwi(conv.weight)
@@ -466,27 +493,53 @@ class NetRunner(object):
             z = Act.new(B, H, W, s.cout, dev)
             use_batch_stats = training or not bn.track_running_stats
             rows_cap = max(_lib.lib.fsdet_conv_stat_rows(npix), _lib.lib.fsdet_colstats_rows(npix))
-            stat = _empty(rows_cap + 2, 2 * s.cout, device=dev) if use_batch_stats else None
+            stat = _empty(rows_cap + _lib.lib.fsdet_bn_stat_scratch_rows(), 4 * s.cout, device=dev) if use_batch_stats else None
             rows = self._conv('fwd', x, wuse, None, z, stat, cin_p, s.cout, s.k, 0, st)
             vec = _empty(4, s.cout, device=dev)  # mean, invstd, scale, shift
+            amax_y = _empty(1, device=dev) if use_batch_stats else None
             upd = training and bn.track_running_stats
             call('fsdet_bn_finalize', ptr(stat), rows, float(npix), ptr(bn.weight), ptr(bn.bias),
                  ptr(bn.running_mean) if (upd or not use_batch_stats) else None,
                  ptr(bn.running_var) if (upd or not use_batch_stats) else None,
                  BN_MOMENTUM if bn.momentum is None else float(bn.momentum), float(bn.eps),
-                 ptr(vec[0]), ptr(vec[1]), ptr(vec[2]), ptr(vec[3]), s.cout, 1 if use_batch_stats else 0, st)
+                 ptr(vec[0]), ptr(vec[1]), ptr(vec[2]), ptr(vec[3]), s.slope, ptr(amax_y), s.cout,
+                 1 if use_batch_stats else 0, st)
             if upd and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked += 1
+            # which outputs exist, and in which representation (fp32 and / or fp16 planes)
+            pos = self.specs.index(s)
+            cp64 = _round_up(s.cout, 64)
+            want_full = (not s.fuse_pool) or s.keep_full
+            want_pool = s.fuse_pool
             full = pooled = None
-            if s.fuse_pool:
-                pooled = out_act(s.idx + 1, B, H // 2, W // 2, s.cout)
-                if s.keep_full:
+            fpl = ppl = None
+            if want_full:
+                planes_ok = (amax_y is not None and not s.fuse_pool and s.idx not in self.placement
+                             and s.idx not in self.routed and self._consumer_takes_planes(pos + 1, s.cout))
+                if planes_ok:
+                    fpl = (torch.empty(npix, cp64, dtype=torch.float16, device=dev),
+                           torch.empty(npix, cp64, dtype=torch.float16, device=dev), amax_y)
+                    full = Act.planes_only(B, H, W, s.cout, dev, fpl)
+                else:
                     full = out_act(s.idx, B, H, W, s.cout)
-            else:
-                full = out_act(s.idx, B, H, W, s.cout)
+                    full.amax = amax_y
+            if want_pool:
+                Hp, Wp = H // 2, W // 2
+                planes_ok = (amax_y is not None and (s.idx + 1) not in self.placement and (s.idx + 1) not in self.routed
+                             and self._consumer_takes_planes(pos + 2, s.cout))
+                if planes_ok:
+                    ppl = (torch.empty(B * Hp * Wp, cp64, dtype=torch.float16, device=dev),
+                           torch.empty(B * Hp * Wp, cp64, dtype=torch.float16, device=dev), amax_y)
+                    pooled = Act.planes_only(B, Hp, Wp, s.cout, dev, ppl)
+                else:
+                    pooled = out_act(s.idx + 1, B, Hp, Wp, s.cout)
+                    pooled.amax = amax_y   # upper bound (max-pool of y): still a valid plane scale
+            f32 = full if (full is not None and full.buf is not None) else None
+            p32 = pooled if (pooled is not None and pooled.buf is not None) else None
             call('fsdet_bn_act_fwd', z.ptr, z.ld, ptr(vec[2]), ptr(vec[3]), s.slope,
-                 full.ptr if full else None, full.ld if full else 0, pooled.ptr if pooled else None,
-                 pooled.ld if pooled else 0, B, H, W, s.cout, st)
+                 f32.ptr if f32 else None, f32.ld if f32 else 0, p32.ptr if p32 else None, p32.ld if p32 else 0,
+                 ptr(fpl[0]) if fpl else None, ptr(fpl[1]) if fpl else None, ptr(ppl[0]) if ppl else None,
+                 ptr(ppl[1]) if ppl else None, cp64, ptr(amax_y) if (fpl or ppl) else None, B, H, W, s.cout, st)
             rec = ('convbn', s, x, wuse, z, vec, full, pooled, conv, bn)
             return ((full, pooled) if s.fuse_pool else full), rec
         # conv + bias (+ leaky), no BN
@@ -519,7 +572,8 @@ class NetRunner(object):
             else:
                 full = out_act(s.idx, B, H, W, cout_p)
             call('fsdet_bn_act_fwd', z.ptr, z.ld, ptr(ones), ptr(zeros), s.slope, full.ptr if full else None,
-                 full.ld if full else 0, pooled.ptr if pooled else None, pooled.ld if pooled else 0, B, H, W, cout_p, st)
+                 full.ld if full else 0, pooled.ptr if pooled else None, pooled.ld if pooled else 0, None, None, None, None,
+                 cout_p, None, B, H, W, cout_p, st)
         else:
             full = z  # linear: the conv output is the block output
         rec = ('convbias', s, x, wp, z, (ones, zeros), full, pooled, conv, cout_p)
@@ -530,7 +584,7 @@ class NetRunner(object):
         following nn.Conv2d(K, O, 1): out[b*n_cls+c] = (W (.) rw[c]) x[b] + bias."""
         if rw is None:
             raise ValueError('this network has a dynamic convolution: dynamic weights are required')
-        dev = x.buf.device
+        dev = x.dev
         conv, _ = self._conv_modules(self.models[head.idx])
         K = x.C
         n_cls = rw.shape[0]
@@ -620,7 +674,7 @@ class NetRunner(object):
         """dX = conv(dZ, flip-transposed W) accumulated into x's gradient."""
         if not x.needs_grad:
             return
-        dev = x.buf.device
+        dev = x.dev
         kk = k * k
         wt = _empty(cin_p, kk, cout, device=dev)
         call('fsdet_weight_flip_transpose', ptr(w_ohwi), ptr(wt), cout, kk, cin_p, st)
@@ -628,7 +682,7 @@ class NetRunner(object):
         self._conv('dgrad', dz, wt, None, g, None, cout, cin_p, k, acc, st)
 
     def _wgrad(self, x, dz, out_tensor, cin_p, cout, k, st):
-        dev = x.buf.device
+        dev = x.dev
         flops = 2.0 * x.npix * cout * k * k * cin_p
         ci64, co64 = _round_up(cin_p, 64), _round_up(cout, 64)
         if USE_TC and 'wgrad' in TC_PARTS and cin_p >= 32 and cout >= 32 and _lib.lib.fsdet_conv_tc_wgrad_supported(ci64, co64, k):
@@ -656,7 +710,7 @@ class NetRunner(object):
 
     def _convbn_bwd(self, rec, st):
         _, s, x, wuse, z, vec, full, pooled, conv, bn = rec
-        dev = x.buf.device
+        dev = x.dev
         B, H, W = x.B, x.H, x.W
         gf = full.grad_for_read() if full is not None else None
         gp = pooled.grad_for_read() if pooled is not None else None
@@ -681,8 +735,9 @@ class NetRunner(object):
         call('fsdet_bn_bwd_finalize', ptr(part), rows, float(x.npix), ptr(bn.weight), ptr(vec[1]), ptr(gg), ptr(gb),
              ptr(coef), s.cout, 1, st)
         dz = Act.new(B, H, W, s.cout, dev, False)
+        dz.amax = _empty(1, device=dev) if USE_TC else None
         call('fsdet_bn_act_bwd_apply', z.ptr, z.ld, a_gf[0], a_gf[1], a_gp[0], a_gp[1], ptr(vec[2]), ptr(vec[3]),
-             ptr(vec[0]), ptr(vec[1]), ptr(coef), s.slope, dz.ptr, dz.ld, B, H, W, s.cout, 1, st)
+             ptr(vec[0]), ptr(vec[1]), ptr(coef), s.slope, dz.ptr, dz.ld, ptr(dz.amax), B, H, W, s.cout, 1, st)
         cin_p = x.C
         if cin_p != s.cin:
             gwp = _empty(s.cout, s.k * s.k, cin_p, device=dev)
@@ -698,7 +753,7 @@ class NetRunner(object):
 
     def _convbias_bwd(self, rec, st):
         _, s, x, wp, z, onez, full, pooled, conv, cout_p = rec
-        dev = x.buf.device
+        dev = x.dev
         B, H, W = x.B, x.H, x.W
         gf = full.grad_for_read() if full is not None else None
         gp = pooled.grad_for_read() if pooled is not None else None
@@ -730,7 +785,7 @@ class NetRunner(object):
         else:
             dz = Act.new(B, H, W, cout_p, dev, False)
             call('fsdet_bn_act_bwd_apply', z.ptr, z.ld, a_gf[0], a_gf[1], a_gp[0], a_gp[1], ptr(ones), ptr(zeros), None,
-                 None, None, s.slope, dz.ptr, dz.ld, B, H, W, cout_p, 0, st)
+                 None, None, s.slope, dz.ptr, dz.ld, None, B, H, W, cout_p, 0, st)
         cin_p = x.C
         kk = s.k * s.k
         gwp = _empty(cout_p, kk, cin_p, device=dev)
@@ -750,7 +805,7 @@ class NetRunner(object):
 
     def _head_bwd(self, rec, gout, st):
         _, s, head, x, rw2, weff, conv, n_cls, O, Npad = rec
-        dev = x.buf.device
+        dev = x.dev
         K = x.C
         N = n_cls * O
         HW = x.H * x.W

@@ -59,10 +59,8 @@ int fsdet_nhwc_to_nchw(const float* in, int ld, const float* bias, float* out, i
 /* Implicit GEMM  z[p][n] = sum_{tap,ci} x[p+tap][ci] * w[n][tap][ci] (+bias[n])
  * (+ previous z when accumulate != 0).  Used for forward (w = OHWI weights) and
  * for the input gradient (x = dz, w = fsdet_weight_flip_transpose(weights)).
- * stat_partial (optional): per-CTA partial column sums for train-mode
- * BatchNorm, float [fsdet_conv_stat_rows(B*H*W) + 2][2*Cout] (sum, sum of
- * squares; the two extra rows are scratch for fsdet_bn_finalize's
- * double-precision totals).
+ * stat_partial (optional): per-CTA column statistics for train-mode BatchNorm,
+ * float [fsdet_conv_stat_rows(B*H*W)][4*Cout] = (sum | sum of squares | min | max).
  * Requires Cin % 4 == 0, ldx % 4 == 0, 16-byte aligned pointers. */
 int fsdet_conv_fwd(const float* x, int ldx, const float* w, const float* bias, float* z, int ldz,
                    float* stat_partial, int B, int H, int W, int Cin, int Cout, int ksize, int accumulate,
@@ -118,7 +116,7 @@ int fsdet_amax(const float* src, int ld, int C, size_t rows, float* amax_out, vo
  * are zero (lets 32-channel layers use the 64-channel K tiles) */
 int fsdet_split_f16(const float* src, int ld, int C, int Cpad, size_t rows, const float* amax, void* hi, void* lo,
                     void* stream);
-/* per-strip column sums / sums of squares of z: float [fsdet_colstats_rows(npix) + 2][2*C] */
+/* per-strip column statistics of z: float [fsdet_colstats_rows(npix)][4*C] = (sum | sum of squares | min | max) */
 int fsdet_colstats(const float* z, int ld, size_t npix, int C, float* partial, void* stream);
 int fsdet_colstats_rows(size_t npix);
 /* test hook: one im2col TMA tile (128 pixels x 64 channels of filter tap `tap`,
@@ -129,17 +127,27 @@ int fsdet_debug_im2col_tile(const void* x_plane, int B, int H, int W, int C, int
 /* ---- BatchNorm2d(train/eval) + LeakyReLU(0.1) + MaxPool2d(2,2) -------- */
 /* nn.BatchNorm2d defaults (darknet_meta.py:247): eps 1e-5, momentum 0.1, biased
  * batch variance for normalisation, unbiased for running_var.
- * Reduces the conv kernel's partials; writes mean/invstd (saved for backward)
- * and the fused per-channel scale/shift; updates running stats when
- * training != 0.  In eval mode (training == 0) scale/shift come from the running
- * statistics and stat_partial is ignored. */
+ * Reduces the conv partial rows float [nparts][4*C] = (sum | sum of squares | min
+ * | max per channel; written by fsdet_conv_fwd or fsdet_colstats; the buffer
+ * must have fsdet_bn_stat_scratch_rows() further rows of scratch); writes
+ * mean/invstd (saved for backward) and the fused per-channel scale/shift; updates
+ * running stats when training != 0.  amax_y (optional device float): exact
+ * absolute maximum of y = leaky(z*scale+shift, slope) over the tensor, derived
+ * from the per-channel range of z (scale of the fp16 planes of y).  In eval mode
+ * (training == 0) scale/shift come from the running statistics, stat_partial is
+ * ignored and amax_y is not written. */
 int fsdet_bn_finalize(const float* stat_partial, int nparts, double count, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, float momentum, float eps, float* mean,
-                      float* invstd, float* scale, float* shift, int C, int training, void* stream);
-/* y = leaky(z*scale+shift, slope); optional full-resolution output y_full and
- * optional MaxPool2d(2,2) (floor) output y_pool written in the same pass. */
+                      float* invstd, float* scale, float* shift, float slope, float* amax_y, int C, int training,
+                      void* stream);
+int fsdet_bn_stat_scratch_rows(void);
+/* y = leaky(z*scale+shift, slope), written in one pass as any subset of: fp32
+ * full resolution (y_full), fp32 MaxPool2d(2,2) (floor) output (y_pool), and the
+ * fp16 hi/lo planes [pixels][Cpad] of either (for the tensor-core convolutions;
+ * scaled by the power of two derived from *amax, channels C..Cpad-1 zero). */
 int fsdet_bn_act_fwd(const float* z, int ldz, const float* scale, const float* shift, float slope, float* y_full,
-                     int ld_full, float* y_pool, int ld_pool, int B, int H, int W, int C, void* stream);
+                     int ld_full, float* y_pool, int ld_pool, void* full_hi, void* full_lo, void* pool_hi,
+                     void* pool_lo, int Cpad, const float* amax, int B, int H, int W, int C, void* stream);
 /* Backward of the block above.  dy_full / dy_pool: gradients w.r.t. the two
  * outputs (either may be NULL).  Pass 1 reduces  sum(du), sum(du*xhat) into
  * partials double [fsdet_bn_bwd_rows(B,H,W) + 1][2*C] (the extra row receives
@@ -159,8 +167,9 @@ int fsdet_bn_bwd_finalize(const double* partial, int nparts, double count, const
                           float* dgamma, float* dbeta, double* coef /* [2*C] */, int C, int has_bn, void* stream);
 int fsdet_bn_act_bwd_apply(const float* z, int ldz, const float* dy_full, int ld_dyf, const float* dy_pool,
                            int ld_dyp, const float* scale, const float* shift, const float* mean,
-                           const float* invstd, const double* coef, float slope, float* dz, int lddz, int B, int H,
-                           int W, int C, int has_bn, void* stream);
+                           const float* invstd, const double* coef, float slope, float* dz, int lddz,
+                           float* amax_out /* optional: absolute maximum of dz */, int B, int H, int W, int C,
+                           int has_bn, void* stream);
 
 /* ---- stand-alone pooling / reorg / route (darknet_meta.py:47-74,157-171) */
 /* size 2; stride 2 (floor) or stride 1 with replicate pad right/bottom

@@ -60,15 +60,17 @@ def test_conv_fwd_stats_bias_accumulate(L, B, H, W, Cin, Cout, k):
     ld = Cout + 4  # exercise ld > C
     z = torch.zeros(B * H * W, ld, device='cuda')
     rows = L.lib.fsdet_conv_stat_rows(B * H * W)
-    stat = torch.zeros(rows + 2, 2 * Cout, device='cuda')
+    stat = torch.zeros(rows, 4 * Cout, device='cuda')
     L.call('fsdet_conv_fwd', xb.data_ptr(), Cin, wb.data_ptr(), None, z.data_ptr(), ld, stat.data_ptr(), B, H, W, Cin, Cout,
            k, 0, st())
     got = nchw(z[:, :Cout].contiguous(), B, H, W)
     assert rel(got, ref) < TOL
     assert (z[:, Cout:] == 0).all()
-    s = stat[:rows].double().sum(0)
+    s = stat.double().sum(0)
     assert rel(s[:Cout], ref.double().sum((0, 2, 3))) < 1e-4
-    assert rel(s[Cout:], (ref.double() ** 2).sum((0, 2, 3))) < 1e-4
+    assert rel(s[Cout:2 * Cout], (ref.double() ** 2).sum((0, 2, 3))) < 1e-4
+    assert torch.equal(stat[:, 2 * Cout:3 * Cout].min(0)[0], z[:, :Cout].min(0)[0])
+    assert torch.equal(stat[:, 3 * Cout:].max(0)[0], z[:, :Cout].max(0)[0])
     # bias + accumulate
     z2 = z.clone()
     L.call('fsdet_conv_fwd', xb.data_ptr(), Cin, wb.data_ptr(), bias.data_ptr(), z2.data_ptr(), ld, None, B, H, W, Cin, Cout,
@@ -119,25 +121,39 @@ def test_bn_act_pool_fwd_bwd(L, B, H, W, C, pool, full):
         outs.append(yp)
         gouts.append(torch.randn(yp.shape, device='cuda', generator=g))
     torch.autograd.backward(outs, gouts)
-    # ours: emulate the conv epilogue partials with one "partial row" holding the totals
+    # ours: column statistics of z (the same partial layout the conv epilogues write), finalize, activation
     zb = nhwc(z.detach())
     npix = B * H * W
-    stat = torch.zeros(1 + 2, 2 * C, device='cuda')
-    stat[0, :C] = zb.sum(0)
-    stat[0, C:] = (zb.double() ** 2).sum(0).float()
+    srows = L.lib.fsdet_colstats_rows(npix)
+    stat = torch.zeros(srows + L.lib.fsdet_bn_stat_scratch_rows(), 4 * C, device='cuda')
+    L.call('fsdet_colstats', zb.data_ptr(), C, npix, C, stat.data_ptr(), st())
     rm2, rv2 = torch.zeros(C, device='cuda'), torch.ones(C, device='cuda')
     vec = torch.empty(4, C, device='cuda')
-    L.call('fsdet_bn_finalize', stat.data_ptr(), 1, float(npix), gamma.data_ptr(), beta.data_ptr(), rm2.data_ptr(),
-           rv2.data_ptr(), 0.1, 1e-5, vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(), C, 1, st())
+    amax = torch.zeros(1, device='cuda')
+    L.call('fsdet_bn_finalize', stat.data_ptr(), srows, float(npix), gamma.data_ptr(), beta.data_ptr(), rm2.data_ptr(),
+           rv2.data_ptr(), 0.1, 1e-5, vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(), 0.1,
+           amax.data_ptr(), C, 1, st())
     assert rel(rm2, rm) < 1e-5 and rel(rv2, rv) < 1e-5
+    assert abs(amax.item() - y.abs().max().item()) <= 1e-5 * y.abs().max().item()
     yf = torch.empty(npix, C, device='cuda') if full else None
     ypb = torch.empty(B * (H // 2) * (W // 2), C, device='cuda') if pool else None
+    cp = (C + 63) // 64 * 64
+    fh = torch.full((npix, cp), 7.0, dtype=torch.float16, device='cuda')
+    fl = torch.full((npix, cp), 7.0, dtype=torch.float16, device='cuda')
+    ph = torch.full((B * (H // 2) * (W // 2), cp), 7.0, dtype=torch.float16, device='cuda')
+    pl = torch.full((B * (H // 2) * (W // 2), cp), 7.0, dtype=torch.float16, device='cuda')
     L.call('fsdet_bn_act_fwd', zb.data_ptr(), C, vec[2].data_ptr(), vec[3].data_ptr(), 0.1,
-           yf.data_ptr() if full else None, C, ypb.data_ptr() if pool else None, C, B, H, W, C, st())
+           yf.data_ptr() if full else None, C, ypb.data_ptr() if pool else None, C, fh.data_ptr(), fl.data_ptr(),
+           ph.data_ptr() if pool else None, pl.data_ptr() if pool else None, cp, amax.data_ptr(), B, H, W, C, st())
+    import math
+    sc = 2.0 ** (10 - math.frexp(amax.item())[1])
+    assert rel((fh.float() + fl.float())[:, :C] / sc, nhwc(y)) < 1e-5
+    assert (fh[:, C:] == 0).all() and (fl[:, C:] == 0).all()
     if full:
         assert rel(nchw(yf, B, H, W), y) < 1e-5
     if pool:
         assert rel(nchw(ypb, B, H // 2, W // 2), yp) < 1e-5
+        assert rel((ph.float() + pl.float())[:, :C] / sc, nhwc(yp)) < 1e-5
     gi = 0
     gf = gp = None
     if full:
@@ -154,7 +170,9 @@ def test_bn_act_pool_fwd_bwd(L, B, H, W, C, pool, full):
     L.call('fsdet_bn_bwd_finalize', part.data_ptr(), rows, float(npix), gamma.data_ptr(), vec[1].data_ptr(), dgam.data_ptr(),
            dbet.data_ptr(), coef.data_ptr(), C, 1, st())
     dz = torch.empty(npix, C, device='cuda')
-    L.call('fsdet_bn_act_bwd_apply', *a, coef.data_ptr(), 0.1, dz.data_ptr(), C, B, H, W, C, 1, st())
+    dzmax = torch.zeros(1, device='cuda')
+    L.call('fsdet_bn_act_bwd_apply', *a, coef.data_ptr(), 0.1, dz.data_ptr(), C, dzmax.data_ptr(), B, H, W, C, 1, st())
+    assert dzmax.item() == dz.abs().max().item()
     assert rel(dgam, gamma.grad) < 1e-4
     assert rel(dbet, beta.grad) < 1e-4
     assert rel(nchw(dz, B, H, W), z.grad) < 1e-4

@@ -122,11 +122,13 @@ def test_colstats(L):
     buf = torch.zeros(5000, 100, device='cuda')
     buf[:, :96] = z
     rows = L.lib.fsdet_colstats_rows(5000)
-    part = torch.zeros(rows + 2, 192, device='cuda')
+    part = torch.zeros(rows, 4 * 96, device='cuda')
     L.call('fsdet_colstats', buf.data_ptr(), 100, 5000, 96, part.data_ptr(), st())
-    s = part[:rows].double().sum(0)
+    s = part.double().sum(0)
     assert rel(s[:96], z.double().sum(0)) < 1e-5
-    assert rel(s[96:], (z.double() ** 2).sum(0)) < 1e-5
+    assert rel(s[96:192], (z.double() ** 2).sum(0)) < 1e-5
+    assert torch.equal(part[:, 192:288].min(0)[0], z.min(0)[0])
+    assert torch.equal(part[:, 288:].max(0)[0], z.max(0)[0])
 
 
 WG_CASES = [
