@@ -105,6 +105,13 @@ class ClockSampler(object):
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def cpu_threads():
+    """Host threads for the CPU arm: all cores up to 32.  torch/oneDNN throughput on this workload peaks at 16-32
+    threads and collapses beyond (measured on the 128-core GPU box with tools/cpu_threads.py: 2.5 s/step at 16, 2.9 s at
+    32, 4.4 s at 64, 50 s at 128 threads), so using more threads would only handicap the reference arm."""
+    return min(os.cpu_count() or 1, 32)
+
+
 def cpu_step_factory(ncls, side, B, threads):
     """The reference's algorithm on the host CPU: oracle port (torch-CPU ops +
     Python build_targets), one full training step."""
@@ -153,7 +160,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     B = args.ref_batch
     step, state = cpu_step_factory(args.ncls, args.side, B, threads)
     for _ in range(args.warmup):
@@ -369,14 +376,17 @@ def main():
     cpu_baseline = None
     bt_cpu_ms = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = cpu_threads()
         cstep, cstate = cpu_step_factory(ncls, side, args.ref_batch, threads)
+        cstep()                                   # warm-up (oneDNN primitive creation)
         t0 = time.perf_counter()
         cstep()
-        dt = time.perf_counter() - t0
+        cstep()
+        dt = (time.perf_counter() - t0) / 2
         cpu_baseline = {'value': args.ref_batch / dt, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
-                        'sample': '1 full training step of %d query + %d support images at %dx%d (oracle port: torch-CPU '
-                                  'ops + Python build_targets), no warm-up' % (args.ref_batch, ncls, side, side)}
+                        'sample': '2 full training steps (after 1 warm-up) of %d query + %d support images at %dx%d (oracle '
+                                  'port: torch-CPU ops + Python build_targets); %d of %d host cores used, see cpu_threads()'
+                                  % (args.ref_batch, ncls, side, side, threads, os.cpu_count() or 1)}
         bt_cpu_ms = cpu_build_targets_ms(B, ncls, G)
 
     line = {
