@@ -26,7 +26,8 @@ SIGNATURES = {
     'fsdet_conv_stat_rows': ('i', 'i'),
     'fsdet_conv_wgrad': ('pipippz iiiiii p'.replace(' ', ''), 'i'),
     'fsdet_conv_wgrad_workspace_floats': ('iiiiii', 'z'),
-    'fsdet_conv_first_wgrad': ('ppippziiiip', 'i'),
+    'fsdet_conv_first_fwd': ('pipippiiiiip', 'i'),
+    'fsdet_conv_first_wgrad': ('pipipippziiiip', 'i'),
     'fsdet_conv_first_wgrad_workspace_floats': ('iiii', 'z'),
     'fsdet_weight_flip_transpose': ('ppiiip', 'i'),
     'fsdet_pad_channels': ('pipizp', 'i'),

@@ -421,11 +421,68 @@ __global__ void pad_channels_kernel(const float* __restrict__ in, int cin, float
 }
 
 // ---------------------------------------------------------------------------
-// First-layer weight gradient (Cin padded to 4, Cout <= 32, 3x3): dw[co][tap][ci] = sum_p dz[p][co] * x[p+tap][ci]
-// HBM-bound (reads dz once, 128 B per pixel).  One CTA walks image rows: the dz row and the three x rows
-// it needs are staged in shared memory; thread (tap, co) keeps its 4 input-channel sums in registers for all
-// rows of the CTA, partials are reduced in a fixed order afterwards.
-__global__ void __launch_bounds__(288) conv_first_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, int lddz,
+// First layer (3 or 3+1 input channels read straight from the reference-facing NCHW tensors, Cout <= 32, 3x3).
+// HBM-bound: forward writes 128 B per pixel, the weight gradient reads them once.
+
+// channel c of the (virtually concatenated) NCHW input pair, zero outside the image / beyond C0+C1
+__device__ __forceinline__ float in_px(const float* __restrict__ in0, int C0, const float* __restrict__ in1, int C1, int b, int c,
+                                       int h, int w, int H, int W) {
+    if (h < 0 || h >= H || w < 0 || w >= W) return 0.f;
+    if (c < C0) return __ldg(in0 + (((long long)b * C0 + c) * H + h) * W + w);
+    if (c < C0 + C1) return __ldg(in1 + (((long long)b * C1 + (c - C0)) * H + h) * W + w);
+    return 0.f;
+}
+
+// forward: one thread = one pixel, all Cout channels; tile 8 rows x 32 cols per CTA
+constexpr int FT_H = 8, FT_W = 32;
+__global__ void __launch_bounds__(256) conv_first_fwd_kernel(const float* __restrict__ in0, int C0, const float* __restrict__ in1,
+                                                             int C1, const float* __restrict__ w /* [Cout][9][4] */,
+                                                             float* __restrict__ z, int ldz, int B, int H, int W, int Cout) {
+    __shared__ float4 xs[FT_H + 2][FT_W + 2];
+    __shared__ float4 ws[32 * 9];
+    const int tid = threadIdx.x;
+    const int tiles_w = (W + FT_W - 1) / FT_W, tiles_h = (H + FT_H - 1) / FT_H;
+    int t = blockIdx.x;
+    const int tw = t % tiles_w; t /= tiles_w;
+    const int th = t % tiles_h;
+    const int b = t / tiles_h;
+    const int h0 = th * FT_H, w0 = tw * FT_W;
+    for (int i = tid; i < Cout * 9; i += 256) ws[i] = ldg4(w + i * 4);
+    for (int i = tid; i < (FT_H + 2) * (FT_W + 2); i += 256) {
+        int r = i / (FT_W + 2), c = i - r * (FT_W + 2);
+        int h = h0 + r - 1, ww = w0 + c - 1;
+        xs[r][c] = make_float4(in_px(in0, C0, in1, C1, b, 0, h, ww, H, W), in_px(in0, C0, in1, C1, b, 1, h, ww, H, W),
+                               in_px(in0, C0, in1, C1, b, 2, h, ww, H, W), in_px(in0, C0, in1, C1, b, 3, h, ww, H, W));
+    }
+    __syncthreads();
+    const int lr = tid / FT_W, lc = tid % FT_W;
+    const int h = h0 + lr, ww = w0 + lc;
+    if (h >= H || ww >= W) return;
+    float4 x[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) x[k] = xs[lr + k / 3][lc + k % 3];
+    float* zr = z + (((long long)b * H + h) * W + ww) * ldz;
+    for (int co = 0; co < Cout; co += 4) {
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const float4 wv = ws[(co + j) * 9 + k];
+                acc = fmaf(x[k].x, wv.x, acc); acc = fmaf(x[k].y, wv.y, acc); acc = fmaf(x[k].z, wv.z, acc); acc = fmaf(x[k].w, wv.w, acc);
+            }
+            o[j] = acc;
+        }
+        *reinterpret_cast<float4*>(zr + co) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// weight gradient: dw[co][tap][ci] = sum_p dz[p][co] * x[p+tap][ci].  One CTA walks image rows: the dz row and the
+// three x rows it needs are staged in shared memory; thread (tap, co) keeps its 4 input-channel sums in registers
+// for all rows of the CTA, partials are reduced in a fixed order afterwards.
+__global__ void __launch_bounds__(288) conv_first_wgrad_kernel(const float* __restrict__ in0, int C0, const float* __restrict__ in1,
+                                                               int C1, const float* __restrict__ dz, int lddz,
                                                                float* __restrict__ part, int B, int H, int W, int Cout) {
     extern __shared__ __align__(16) float sm[];
     float4* xs = reinterpret_cast<float4*>(sm);              // [3][W + 2] pixels of 4 channels (zero halo)
@@ -441,9 +498,8 @@ __global__ void __launch_bounds__(288) conv_first_wgrad_kernel(const float* __re
         for (int i = tid; i < 3 * (W + 2); i += blockDim.x) {
             int r = i / (W + 2), c = i - r * (W + 2);
             int hh = h + r - 1, ww = c - 1;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = ldg4(x + (((long long)b * H + hh) * W + ww) * 4);
-            xs[i] = v;
+            xs[i] = make_float4(in_px(in0, C0, in1, C1, b, 0, hh, ww, H, W), in_px(in0, C0, in1, C1, b, 1, hh, ww, H, W),
+                                in_px(in0, C0, in1, C1, b, 2, hh, ww, H, W), in_px(in0, C0, in1, C1, b, 3, hh, ww, H, W));
         }
         const float* drow = dz + (row * W) * lddz;
         for (int i = tid; i < W * 8; i += blockDim.x) {      // 8 float4 per pixel (32 channels, zero beyond Cout)
@@ -578,11 +634,23 @@ extern "C" size_t fsdet_conv_first_wgrad_workspace_floats(int B, int H, int W, i
     return (size_t)first_wgrad_ctas(B, H) * Cout * 36;
 }
 
-extern "C" int fsdet_conv_first_wgrad(const float* x, const float* dz, int lddz, float* dw, float* workspace,
-                                      size_t workspace_floats, int B, int H, int W, int Cout, void* stream) {
-    FSDET_CHECK_ARG(x && dz && dw && workspace, "conv_first_wgrad: null pointer");
+extern "C" int fsdet_conv_first_fwd(const float* in0, int C0, const float* in1, int C1, const float* w_pad4, float* z, int ldz,
+                                    int B, int H, int W, int Cout, void* stream) {
+    FSDET_CHECK_ARG(in0 && w_pad4 && z && C0 > 0 && C1 >= 0 && (C1 == 0 || in1) && C0 + C1 <= 4, "conv_first_fwd: bad inputs");
+    FSDET_CHECK_ARG(Cout > 0 && Cout <= 32 && Cout % 4 == 0 && ldz % 4 == 0 && aligned16(z) && aligned16(w_pad4),
+                    "conv_first_fwd: Cout=%d ldz=%d", Cout, ldz);
+    long long tiles = (long long)B * ceil_div(H, FT_H) * ceil_div(W, FT_W);
+    if (tiles == 0) return 0;
+    conv_first_fwd_kernel<<<(unsigned)tiles, 256, 0, (cudaStream_t)stream>>>(in0, C0, in1, C1, w_pad4, z, ldz, B, H, W, Cout);
+    return launch_status("conv_first_fwd");
+}
+
+extern "C" int fsdet_conv_first_wgrad(const float* in0, int C0, const float* in1, int C1, const float* dz, int lddz, float* dw,
+                                      float* workspace, size_t workspace_floats, int B, int H, int W, int Cout, void* stream) {
+    FSDET_CHECK_ARG(in0 && dz && dw && workspace && C0 > 0 && C1 >= 0 && (C1 == 0 || in1) && C0 + C1 <= 4,
+                    "conv_first_wgrad: bad inputs");
     FSDET_CHECK_ARG(Cout > 0 && Cout <= 32 && Cout % 4 == 0 && lddz % 4 == 0, "conv_first_wgrad: Cout=%d lddz=%d", Cout, lddz);
-    FSDET_CHECK_ARG(aligned16(x) && aligned16(dz) && aligned16(dw) && aligned16(workspace), "conv_first_wgrad: alignment");
+    FSDET_CHECK_ARG(aligned16(dz) && aligned16(dw) && aligned16(workspace), "conv_first_wgrad: alignment");
     const int ctas = first_wgrad_ctas(B, H);
     FSDET_CHECK_ARG(workspace_floats >= (size_t)ctas * Cout * 36, "conv_first_wgrad: workspace too small");
     if (ctas == 0) return 0;
@@ -595,7 +663,7 @@ extern "C" int fsdet_conv_first_wgrad(const float* x, const float* dz, int lddz,
         if (e != cudaSuccess) { set_error("conv_first_wgrad: %s", cudaGetErrorString(e)); return (int)e; }
         smem_set = smem;
     }
-    conv_first_wgrad_kernel<<<ctas, 288, smem, s>>>(x, dz, lddz, workspace, B, H, W, Cout);
+    conv_first_wgrad_kernel<<<ctas, 288, smem, s>>>(in0, C0, in1, C1, dz, lddz, workspace, B, H, W, Cout);
     int st = launch_status("conv_first_wgrad");
     if (st) return st;
     long long n4 = (long long)Cout * 36 / 4;

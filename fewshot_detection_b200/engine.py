@@ -48,7 +48,7 @@ def same_layout(a, b):
 class Act(object):
     """A view [B*H*W pixels] x [C channels at column `off`] of a 2-D NHWC fp32 buffer, and/or the fp16 hi/lo
     planes of the same activation for the tensor-core kernels (`buf` is None when only the planes exist)."""
-    __slots__ = ('buf', 'off', 'C', 'B', 'H', 'W', 'g', 'needs_grad', 'parent', 'planes', 'amax', 'dev')
+    __slots__ = ('buf', 'off', 'C', 'B', 'H', 'W', 'g', 'needs_grad', 'parent', 'planes', 'amax', 'dev', 'nchw')
 
     def __init__(self, buf, off, C, B, H, W, needs_grad=True, parent=None, dev=None):
         self.buf, self.off, self.C, self.B, self.H, self.W = buf, off, C, B, H, W
@@ -58,6 +58,7 @@ class Act(object):
         self.planes = None       # (hi, lo, amax) fp16 planes of this activation for the tensor-core path
         self.amax = None         # device scalar |max| if already known (skips the amax pass before splitting)
         self.dev = buf.device if buf is not None else dev
+        self.nchw = None         # (in0, C0, in1, C1): the network input, still in the reference's NCHW tensors
 
     @property
     def ld(self):
@@ -305,6 +306,15 @@ class NetRunner(object):
         """z = conv(x, w) through the tensor-core kernel when the shape allows, else SIMT.
         Returns the number of BN partial rows written to `stat_rows_out` (a float tensor or None)."""
         flops = 2.0 * x.npix * cout * k * k * cin
+        if x.nchw is not None:
+            in0, c0, in1, c1 = x.nchw
+            assert bias is None and not acc and cin == 4 and k == 3
+            self._timed('first_fwd', flops, 'fsdet_conv_first_fwd', ptr(in0), c0, ptr(in1), c1, ptr(w_ohwi), z.ptr, z.ld, x.B, x.H,
+                        x.W, cout, st)
+            if stat_rows_out is not None:
+                call('fsdet_colstats', z.ptr, z.ld, x.npix, cout, ptr(stat_rows_out), st)
+                return _lib.lib.fsdet_colstats_rows(x.npix)
+            return 0
         if bias is None and name in TC_PARTS and self._tc_ok(cin, cout, k):
             cpad = _round_up(cin, 64)
             xh, xl, xa = self._planes(x, st)
@@ -368,9 +378,17 @@ class NetRunner(object):
         for t in inputs:
             if t.dtype != torch.float32 or not t.is_cuda:
                 raise TypeError('inputs must be float32 CUDA tensors (no CPU fallback)')
-        xin = Act.new(B, H, W, self.in_cpad, dev, needs_grad=False)
-        call('fsdet_nchw_to_nhwc', ptr(inputs[0].contiguous()), c0,
-             ptr(inputs[1].contiguous()) if c1 else None, c1, xin.ptr, xin.ld, self.in_cpad, B, H * W, st)
+        first = self.specs[0] if self.specs else None
+        in0 = inputs[0].contiguous()
+        in1 = inputs[1].contiguous() if c1 else None
+        if (first is not None and first.kind == 'conv' and not first.dynamic and first.k == 3 and first.cout <= 32
+                and first.cout % 4 == 0 and self.in_ch <= 4):
+            # the first convolution reads the NCHW input directly (no NHWC copy of the images)
+            xin = Act(None, 0, 4, B, H, W, needs_grad=False, dev=dev)
+            xin.nchw = (in0, c0, in1, c1)
+        else:
+            xin = Act.new(B, H, W, self.in_cpad, dev, needs_grad=False)
+            call('fsdet_nchw_to_nhwc', ptr(in0), c0, ptr(in1), c1, xin.ptr, xin.ld, self.in_cpad, B, H * W, st)
         outputs = {}
         cat_bufs = {}
         cur = xin
@@ -697,11 +715,12 @@ class NetRunner(object):
             if padded:  # crop the zero channels / rows: rows [0, cout) are contiguous, channels via pad_channels
                 call('fsdet_pad_channels', ptr(tgt), ci64, ptr(out_tensor), cin_p, cout * k * k, st)
             return
-        if cin_p == 4 and x.ld == 4 and k == 3 and cout <= 32 and cout % 4 == 0:
+        if x.nchw is not None:
+            in0, c0, in1, c1 = x.nchw
             nws = _lib.lib.fsdet_conv_first_wgrad_workspace_floats(x.B, x.H, x.W, cout)
             ws = _empty(max(nws, 4), device=dev)
-            self._timed('first_wgrad', flops, 'fsdet_conv_first_wgrad', x.ptr, dz.ptr, dz.ld, ptr(out_tensor), ptr(ws), nws,
-                        x.B, x.H, x.W, cout, st)
+            self._timed('first_wgrad', flops, 'fsdet_conv_first_wgrad', ptr(in0), c0, ptr(in1), c1, dz.ptr, dz.ld, ptr(out_tensor),
+                        ptr(ws), nws, x.B, x.H, x.W, cout, st)
             return
         nws = _lib.lib.fsdet_conv_wgrad_workspace_floats(x.B, x.H, x.W, cin_p, cout, k)
         ws = _empty(max(nws, 4), device=dev)

@@ -72,10 +72,14 @@ int fsdet_conv_stat_rows(int npix);
 int fsdet_conv_wgrad(const float* x, int ldx, const float* dz, int lddz, float* dw, float* workspace,
                      size_t workspace_floats, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
 size_t fsdet_conv_wgrad_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize);
-/* First-layer weight gradient (x = NHWC4 input images, Cout <= 32, 3x3): dw [Cout][9][4].
- * HBM-bound row-streaming kernel; workspace float [fsdet_conv_first_wgrad_workspace_floats()]. */
-int fsdet_conv_first_wgrad(const float* x, const float* dz, int lddz, float* dw, float* workspace,
-                           size_t workspace_floats, int B, int H, int W, int Cout, void* stream);
+/* First layer, read straight from the reference-facing NCHW tensors (in0 [B,C0,H,W] and optionally in1
+ * [B,C1,H,W] = the support branch's torch.cat([metax, mask], 1); C0+C1 <= 4; Cout <= 32; 3x3, pad 1):
+ * forward z NHWC fp32 with weights zero-padded to [Cout][9][4]; weight gradient dw [Cout][9][4].
+ * HBM-bound kernels; workspace float [fsdet_conv_first_wgrad_workspace_floats()]. */
+int fsdet_conv_first_fwd(const float* in0, int C0, const float* in1, int C1, const float* w_pad4, float* z, int ldz,
+                         int B, int H, int W, int Cout, void* stream);
+int fsdet_conv_first_wgrad(const float* in0, int C0, const float* in1, int C1, const float* dz, int lddz, float* dw,
+                           float* workspace, size_t workspace_floats, int B, int H, int W, int Cout, void* stream);
 size_t fsdet_conv_first_wgrad_workspace_floats(int B, int H, int W, int Cout);
 /* wt[ci][kk-1-tap][co] = w[co][tap][ci]  (weights for the input-gradient conv) */
 int fsdet_weight_flip_transpose(const float* w, float* wt, int Cout, int kk, int Cin, void* stream);

@@ -259,16 +259,28 @@ def test_fused_sgd_matches_torch(L):
         assert rel(pa, pb) < 1e-6
 
 
-@pytest.mark.parametrize('B,H,W,Cout', [(2, 13, 17, 32), (3, 64, 64, 16), (1, 5, 3, 8), (2, 416, 416, 32)])
-def test_conv_first_wgrad(L, B, H, W, Cout):
+@pytest.mark.parametrize('B,H,W,Cout,C0,C1', [(2, 13, 17, 32, 3, 0), (3, 64, 64, 16, 3, 1), (1, 5, 3, 8, 2, 1), (2, 416, 416, 32, 3, 1)])
+def test_conv_first_layer_fwd_wgrad(L, B, H, W, Cout, C0, C1):
     g = torch.Generator(device='cuda').manual_seed(H + W)
-    x = torch.rand(B, 4, H, W, device='cuda', generator=g)
-    w = torch.zeros(Cout, 4, 3, 3, device='cuda', requires_grad=True)
+    a = torch.rand(B, C0, H, W, device='cuda', generator=g)
+    m = torch.rand(B, C1, H, W, device='cuda', generator=g) if C1 else None
+    C = C0 + C1
+    x = torch.cat([a, m], 1) if C1 else a
+    w = (torch.randn(Cout, C, 3, 3, device='cuda', generator=g) * 0.2).double().requires_grad_(True)
     dz = torch.randn(B, Cout, H, W, device='cuda', generator=g)
-    F.conv2d(x.double(), w.double(), None, 1, 1).backward(dz.double())
-    xb, dzb = nhwc(x), nhwc(dz)
+    ref = F.conv2d(x.double(), w, None, 1, 1)
+    ref.backward(dz.double())
+    wp = torch.zeros(Cout, 9, 4, device='cuda')
+    wp[:, :, :C] = w.detach().float().permute(0, 2, 3, 1).reshape(Cout, 9, C)
+    z = torch.empty(B * H * W, Cout, device='cuda')
+    L.call('fsdet_conv_first_fwd', a.data_ptr(), C0, m.data_ptr() if C1 else None, C1, wp.data_ptr(), z.data_ptr(), Cout, B, H, W,
+           Cout, st())
+    assert rel(nchw(z, B, H, W), ref) < 1e-5
+    dzb = nhwc(dz)
     nws = L.lib.fsdet_conv_first_wgrad_workspace_floats(B, H, W, Cout)
     ws = torch.empty(nws, device='cuda')
     dw = torch.empty(Cout, 9, 4, device='cuda')
-    L.call('fsdet_conv_first_wgrad', xb.data_ptr(), dzb.data_ptr(), Cout, dw.data_ptr(), ws.data_ptr(), nws, B, H, W, Cout, st())
-    assert rel(dw.view(Cout, 3, 3, 4).permute(0, 3, 1, 2), w.grad) < 1e-5
+    L.call('fsdet_conv_first_wgrad', a.data_ptr(), C0, m.data_ptr() if C1 else None, C1, dzb.data_ptr(), Cout, dw.data_ptr(),
+           ws.data_ptr(), nws, B, H, W, Cout, st())
+    assert rel(dw.view(Cout, 3, 3, 4)[:, :, :, :C].permute(0, 3, 1, 2), w.grad) < 1e-5
+    assert (dw.view(Cout, 9, 4)[:, :, C:] == 0).all()
