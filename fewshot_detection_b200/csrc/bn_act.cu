@@ -186,12 +186,13 @@ __device__ __forceinline__ float4 act4(float4 v, float4 sc, float4 sh, float slo
 
 // no pooling: one thread = one pixel x 4 channels (channel index runs to Cpad: the zero padding of the planes)
 __global__ void __launch_bounds__(256) bn_act_flat_kernel(const FwdArgs a) {
-    const int CP4 = a.Cpad >> 2;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long npix = (long long)a.B * a.H * a.W;
+    const unsigned CP4 = a.Cpad >> 2;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;   // host guarantees npix * CP4 < 2^31
+    const unsigned npix = (unsigned)a.B * a.H * a.W;
     if (i >= npix * CP4) return;
-    long long p = i / CP4;
-    int c = (int)(i - p * CP4) * 4;
+    const unsigned pu = i / CP4;
+    const long long p = pu;
+    const int c = (int)(i - pu * CP4) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < a.C) {
         v = act4(ldg4(a.z + p * a.ldz + c), ldg4(a.scale + c), ldg4(a.shift + c), a.slope);
@@ -204,16 +205,16 @@ __global__ void __launch_bounds__(256) bn_act_flat_kernel(const FwdArgs a) {
 __global__ void __launch_bounds__(256) bn_act_pool_kernel(const FwdArgs a) {
     const int H = a.H, W = a.W;
     const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
-    const int CP4 = a.Cpad >> 2;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long n = (long long)a.B * H2 * W2 * CP4;
+    const unsigned CP4 = a.Cpad >> 2;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;   // host guarantees n < 2^31: 32-bit index math
+    const unsigned n = (unsigned)a.B * H2 * W2 * CP4;
     if (i >= n) return;
-    int c = (int)(i % CP4) * 4;
-    long long wi = i / CP4;
-    int w2 = (int)(wi % W2);
-    long long t = wi / W2;
-    int h2 = (int)(t % H2);
-    int b = (int)(t / H2);
+    const unsigned wi = i / CP4;
+    const int c = (int)(i - wi * CP4) * 4;
+    const unsigned t = wi / W2;
+    const int w2 = (int)(wi - t * W2);
+    const int b = (int)(t / H2);
+    const int h2 = (int)(t - (unsigned)b * H2);
     const bool cok = c < a.C;
     const float psc = (a.fh || a.ph) ? plane_scale(__ldg(a.amax)) : 1.f;
     float4 sc = make_float4(0, 0, 0, 0), sh = sc;
@@ -262,7 +263,7 @@ struct BwdArgs {
 };
 
 template <bool APPLY>
-__global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_kernel(const BwdArgs a) {
     const int H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1, Hp = a.H >> 1, Wp = a.W >> 1;
     const int C4 = a.C >> 2;
     const int TC = blockDim.x;          // channel-vector lanes
@@ -288,12 +289,11 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BwdArgs a) {
     double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     float amax = 0.f;
 
-    for (long long wi = (long long)blockIdx.x * blockDim.y + threadIdx.y; cok && wi < nwin;
-         wi += (long long)gridDim.x * blockDim.y) {
-        int w2 = (int)(wi % W2);
-        long long t = wi / W2;
-        int h2 = (int)(t % H2);
-        int b = (int)(t / H2);
+    for (unsigned wi = blockIdx.x * blockDim.y + threadIdx.y; cok && wi < (unsigned)nwin; wi += gridDim.x * blockDim.y) {
+        const unsigned t = wi / W2;
+        const int w2 = (int)(wi - t * W2);
+        const int b = (int)(t / H2);
+        const int h2 = (int)(t - (unsigned)b * H2);
         float zv[4][4], yv[4][4];
         long long pix[4];
         bool ok[4];
@@ -470,6 +470,7 @@ extern "C" int fsdet_bn_act_fwd(const float* z, int ldz, const float* scale, con
     a.fh = (__half*)full_hi; a.fl = (__half*)full_lo; a.ph = (__half*)pool_hi; a.pl = (__half*)pool_lo;
     a.ldz = ldz; a.ldf = ld_full; a.ldp = ld_pool; a.Cpad = planes ? Cpad : C; a.B = B; a.H = H; a.W = W; a.C = C; a.slope = slope;
     const int CP4 = a.Cpad / 4;
+    FSDET_CHECK_ARG((long long)B * H * W * CP4 < (1ll << 31), "bn_act_fwd: tensor too large for 32-bit indexing");
     if (!y_pool && !pool_hi) {
         long long n = (long long)B * H * W * CP4;
         if (n == 0) return 0;
@@ -483,6 +484,7 @@ extern "C" int fsdet_bn_act_fwd(const float* z, int ldz, const float* scale, con
 }
 
 static int launch_bwd(bool apply, const BwdArgs& a, cudaStream_t s) {
+    FSDET_CHECK_ARG((long long)a.B * a.H * a.W < (1ll << 31), "bn_act_bwd: tensor too large for 32-bit indexing");
     int C4 = a.C / 4;
     int TC = C4 >= 32 ? 32 : (C4 >= 16 ? 16 : (C4 >= 8 ? 8 : (C4 >= 4 ? 4 : (C4 >= 2 ? 2 : 1))));
     int TY = 256 / TC;

@@ -433,8 +433,9 @@ __device__ __forceinline__ float in_px(const float* __restrict__ in0, int C0, co
     return 0.f;
 }
 
-// forward: one thread = one pixel, all Cout channels; tile 8 rows x 32 cols per CTA
-constexpr int FT_H = 8, FT_W = 32;
+// forward: one thread = two vertically adjacent pixels, all Cout channels (each weight float4 read from shared
+// memory feeds 8 FMAs); tile 16 rows x 32 cols per CTA of 256 threads
+constexpr int FT_H = 16, FT_W = 32;
 __global__ void __launch_bounds__(256) conv_first_fwd_kernel(const float* __restrict__ in0, int C0, const float* __restrict__ in1,
                                                              int C1, const float* __restrict__ w /* [Cout][9][4] */,
                                                              float* __restrict__ z, int ldz, int B, int H, int W, int Cout) {
@@ -455,26 +456,31 @@ __global__ void __launch_bounds__(256) conv_first_fwd_kernel(const float* __rest
                                in_px(in0, C0, in1, C1, b, 2, h, ww, H, W), in_px(in0, C0, in1, C1, b, 3, h, ww, H, W));
     }
     __syncthreads();
-    const int lr = tid / FT_W, lc = tid % FT_W;
+    const int lr = (tid / FT_W) * 2, lc = tid % FT_W;   // rows lr, lr+1
     const int h = h0 + lr, ww = w0 + lc;
     if (h >= H || ww >= W) return;
-    float4 x[9];
+    float4 x[12];                                       // 4 input rows x 3 columns
 #pragma unroll
-    for (int k = 0; k < 9; ++k) x[k] = xs[lr + k / 3][lc + k % 3];
-    float* zr = z + (((long long)b * H + h) * W + ww) * ldz;
+    for (int k = 0; k < 12; ++k) x[k] = xs[lr + k / 3][lc + k % 3];
+    const bool two = h + 1 < H;
+    float* z0 = z + (((long long)b * H + h) * W + ww) * ldz;
+    float* z1 = z0 + (long long)W * ldz;
     for (int co = 0; co < Cout; co += 4) {
-        float o[4];
+        float o0[4], o1[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float acc = 0.f;
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
                 const float4 wv = ws[(co + j) * 9 + k];
-                acc = fmaf(x[k].x, wv.x, acc); acc = fmaf(x[k].y, wv.y, acc); acc = fmaf(x[k].z, wv.z, acc); acc = fmaf(x[k].w, wv.w, acc);
+                const float4 p0 = x[k], p1 = x[k + 3];
+                a0 = fmaf(p0.x, wv.x, a0); a0 = fmaf(p0.y, wv.y, a0); a0 = fmaf(p0.z, wv.z, a0); a0 = fmaf(p0.w, wv.w, a0);
+                a1 = fmaf(p1.x, wv.x, a1); a1 = fmaf(p1.y, wv.y, a1); a1 = fmaf(p1.z, wv.z, a1); a1 = fmaf(p1.w, wv.w, a1);
             }
-            o[j] = acc;
+            o0[j] = a0; o1[j] = a1;
         }
-        *reinterpret_cast<float4*>(zr + co) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(z0 + co) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+        if (two) *reinterpret_cast<float4*>(z1 + co) = make_float4(o1[0], o1[1], o1[2], o1[3]);
     }
 }
 

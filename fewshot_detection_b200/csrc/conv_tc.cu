@@ -38,10 +38,11 @@ __device__ __forceinline__ float scale_from_amax(float a) {
 
 __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ src, int ld, int C4, long long rows, float* __restrict__ out) {
     float m = 0.f;
-    const long long n = rows * C4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        long long r = i / C4;
-        int c = (int)(i - r * C4) * 4;
+    const unsigned n = (unsigned)rows * (unsigned)C4;   // host guarantees < 2^31
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned ru = i / (unsigned)C4;
+        const long long r = ru;
+        const int c = (int)(i - ru * (unsigned)C4) * 4;
         float4 v = ldg4(src + r * ld + c);
         m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
@@ -59,11 +60,12 @@ __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ src
 __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ src, int ld, int C, int Cpad4, long long rows,
                                                         const float* __restrict__ amax, __half* __restrict__ hi,
                                                         __half* __restrict__ lo) {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * Cpad4) return;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;   // host guarantees rows * Cpad4 < 2^31
+    if (i >= (unsigned)rows * (unsigned)Cpad4) return;
     const float sc = amax ? scale_from_amax(__ldg(amax)) : 1.f;
-    long long r = i / Cpad4;
-    int c = (int)(i - r * Cpad4) * 4;
+    const unsigned ru = i / (unsigned)Cpad4;
+    const long long r = ru;
+    const int c = (int)(i - ru * (unsigned)Cpad4) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < C) v = ldg4(src + r * ld + c);  // C % 4 == 0; channels C..Cpad-1 are zero filled
     float f[4] = {v.x * sc, v.y * sc, v.z * sc, v.w * sc};
@@ -692,6 +694,7 @@ extern "C" int fsdet_amax(const float* src, int ld, int C, size_t rows, float* a
     if (e != cudaSuccess) { set_error("amax: memset: %s", cudaGetErrorString(e)); return (int)e; }
     long long n = (long long)rows * (C / 4);
     if (n == 0) return 0;
+    FSDET_CHECK_ARG(n < (1ll << 31), "amax: tensor too large for 32-bit indexing");
     int blocks = ceil_div(n, 256 * 8);
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
     amax_kernel<<<blocks, 256, 0, s>>>(src, ld, C / 4, (long long)rows, amax_out);
@@ -705,6 +708,7 @@ extern "C" int fsdet_split_f16(const float* src, int ld, int C, int Cpad, size_t
     FSDET_CHECK_ARG(aligned16(src) && ((uintptr_t)hi % 8 == 0) && ((uintptr_t)lo % 8 == 0), "split_f16: alignment");
     long long n = (long long)rows * (Cpad / 4);
     if (n == 0) return 0;
+    FSDET_CHECK_ARG(n < (1ll << 31), "split_f16: tensor too large for 32-bit indexing");
     split_f16_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, ld, C, Cpad / 4, (long long)rows, amax, (__half*)hi,
                                                                          (__half*)lo);
     return launch_status("split_f16");
