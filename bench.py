@@ -308,6 +308,11 @@ def main():
     launches = sum((calls1.get(k, 0) - calls0.get(k, 0)) * LAUNCHES.get(k, 1) for k in calls1) * args.steps // prof_steps
 
     # per-kernel roofline of the dominant kernel (CUDA events recorded on the launching stream)
+    launches_tbl = prof.pop('_launches', [])
+    if os.environ.get('FSDET_DUMP_LAUNCHES') and rank == 0:
+        rows = [(a.elapsed_time(b2) * 1e3, n, f, d) for (n, f, a, b2, d) in launches_tbl[len(launches_tbl) // 2:]]
+        for us, n, f, d in sorted(rows, key=lambda r: -r[0]):
+            sys.stderr.write('%9.1f us %-12s %7.1f TF/s  %s\n' % (us, n, f / us / 1e6, d[-9:]))
     kern = {}
     for name, (flops, evs) in prof.items():
         t = sum(a.elapsed_time(b) for a, b in evs)

@@ -32,7 +32,7 @@ SIGNATURES = {
     'fsdet_weight_flip_transpose': ('ppiiip', 'i'),
     'fsdet_pad_channels': ('pipizp', 'i'),
     'fsdet_conv_tc_supported': ('iii', 'i'),
-    'fsdet_conv_tc_fwd': ('pppppppiiiiiiiip', 'i'),
+    'fsdet_conv_tc_fwd': ('pppppppiiiiiiiiip', 'i'),
     'fsdet_conv_tc_wgrad_supported': ('iii', 'i'),
     'fsdet_conv_tc_wgrad_workspace_floats': ('iiiiii', 'z'),
     'fsdet_conv_tc_wgrad': ('ppppppppziiiiiip', 'i'),

@@ -183,6 +183,17 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
     return d;
 }
 
+// K-major, 64-byte swizzle (tile rows of 64 B = 32 halves, 8-row groups 512 B apart)
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                        // SWIZZLE_64B
+    return d;
+}
+
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -220,28 +231,39 @@ struct TcArgs {
     const float* amax_b;
     int ldz;
     int H, W, Cin, Cout, ks, pad;
+    int cpitch;   // channel pitch of the weight planes' K axis: k = tap * cpitch + c
     long long M;  // B*H*W
     int accumulate;
 };
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;                       // bf16 elements per stage row = 128 B
+constexpr int TC_BK = 64;                       // halves per 128-byte row (im2col debug tile, weight-gradient tiles)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB per plane
 
-template <int BN>
+constexpr int tmem_cols(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : (n <= 256 ? 256 : 512))); }
+
+// Two flavours of the same kernel:
+//   BK = 64 (128-byte rows), 3 hi accumulators, 1 CTA / SM : large-K layers (long accumulation chains)
+//   BK = 32 ( 64-byte rows), 1 hi accumulator,  2 CTAs / SM: small-K layers (K = k*k*Cin <= 2304) and 32-channel
+//        inputs; the two co-resident CTAs overlap one's epilogue / prologue with the other's MMAs.
+template <int BN, int BK, int STAGES_, int NH>
 struct TcCfg {
-    static constexpr int B_BYTES = BN * TC_BK * 2;
-    static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+    static constexpr int ROW_BYTES = BK * 2;
+    static constexpr int A_BYTES = TC_BM * ROW_BYTES;
+    static constexpr int B_BYTES = BN * ROW_BYTES;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = STAGES_;
+    static constexpr int TMEM_COLS = tmem_cols((NH + 1) * BN);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int BK, int STAGES_, int NH, int MINB>
+__global__ void __launch_bounds__(192, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcArgs p) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, BK, STAGES_, NH>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int A_BYTES = Cfg::A_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -253,7 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int n_tile = blockIdx.x;
     const long long m0 = (long long)blockIdx.y * TC_BM;
-    const int kchunks = p.Cin / TC_BK;
+    const int kchunks = p.Cin / BK;
     const int nk = p.ks * p.ks * kchunks;
 
     if (warp == 0 && lane == 0) {
@@ -268,8 +290,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) {  // whole warp: allocate NACC x BN fp32 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(NACC * BN)));
+    if (warp == 1) {  // whole warp: allocate the fp32 accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
@@ -289,12 +311,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 uint8_t* st = smem + s * Cfg::STAGE_BYTES;
                 mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
                 const int tap = kb / kchunks;
-                const int c0 = (kb - tap * kchunks) * TC_BK;
+                const int c0 = (kb - tap * kchunks) * BK;
                 const int r = tap / p.ks, sx = tap - r * p.ks;
                 tma_load_im2col_4d(st, &tmAhi, &full_bar[s], c0, pw - p.pad, ph - p.pad, img, (uint16_t)sx, (uint16_t)r);
-                tma_load_im2col_4d(st + TC_A_BYTES, &tmAlo, &full_bar[s], c0, pw - p.pad, ph - p.pad, img, (uint16_t)sx, (uint16_t)r);
-                tma_load_2d(st + 2 * TC_A_BYTES, &tmBhi, &full_bar[s], tap * p.Cin + c0, n_tile * BN);
-                tma_load_2d(st + 2 * TC_A_BYTES + Cfg::B_BYTES, &tmBlo, &full_bar[s], tap * p.Cin + c0, n_tile * BN);
+                tma_load_im2col_4d(st + A_BYTES, &tmAlo, &full_bar[s], c0, pw - p.pad, ph - p.pad, img, (uint16_t)sx, (uint16_t)r);
+                tma_load_2d(st + 2 * A_BYTES, &tmBhi, &full_bar[s], tap * p.cpitch + c0, n_tile * BN);
+                tma_load_2d(st + 2 * A_BYTES + Cfg::B_BYTES, &tmBlo, &full_bar[s], tap * p.cpitch + c0, n_tile * BN);
             }
         }
     } else if (warp == 1) {
@@ -306,14 +328,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 mbar_wait(&full_bar[s], (kb / STAGES) & 1);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint64_t ahi = umma_desc_k_sw128(sa), alo = umma_desc_k_sw128(sa + TC_A_BYTES);
-                const uint64_t bhi = umma_desc_k_sw128(sa + 2 * TC_A_BYTES), blo = umma_desc_k_sw128(sa + 2 * TC_A_BYTES + Cfg::B_BYTES);
+                uint64_t ahi, alo, bhi, blo;
+                if constexpr (BK == 64) {
+                    ahi = umma_desc_k_sw128(sa); alo = umma_desc_k_sw128(sa + A_BYTES);
+                    bhi = umma_desc_k_sw128(sa + 2 * A_BYTES); blo = umma_desc_k_sw128(sa + 2 * A_BYTES + Cfg::B_BYTES);
+                } else {
+                    ahi = umma_desc_k_sw64(sa); alo = umma_desc_k_sw64(sa + A_BYTES);
+                    bhi = umma_desc_k_sw64(sa + 2 * A_BYTES); blo = umma_desc_k_sw64(sa + 2 * A_BYTES + Cfg::B_BYTES);
+                }
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
+                for (int k = 0; k < BK / 16; ++k) {
                     const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 halves = 32 B along K inside the swizzle atom
-                    const uint32_t dhi = tmem_base + (uint32_t)((kb % NHI) * BN);
-                    const uint32_t dlo = tmem_base + (uint32_t)(NHI * BN);
-                    umma_f16(dhi, ahi + adv, bhi + adv, idesc, (kb >= NHI || k > 0) ? 1u : 0u);
+                    const uint32_t dhi = tmem_base + (uint32_t)((kb % NH) * BN);
+                    const uint32_t dlo = tmem_base + (uint32_t)(NH * BN);
+                    umma_f16(dhi, ahi + adv, bhi + adv, idesc, (kb >= NH || k > 0) ? 1u : 0u);
                     umma_f16(dlo, alo + adv, bhi + adv, idesc, (kb | k) ? 1u : 0u);
                     umma_f16(dlo, ahi + adv, blo + adv, idesc, 1u);
                 }
@@ -330,13 +358,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         const bool row_ok = m < p.M;
         float* zr = p.z + (row_ok ? m : 0) * p.ldz;
         const float inv = 1.f / (scale_from_amax(p.amax_a ? __ldg(p.amax_a) : 0.f) * scale_from_amax(p.amax_b ? __ldg(p.amax_b) : 0.f));
-        const int nhi = nk < NHI ? nk : NHI;
+        const int nhi = nk < NH ? nk : NH;
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
             uint32_t r[32];
             float acc[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32;
-            tmem_ld32(taddr + NHI * BN, r);  // lo terms first (small), then the hi*hi partial sums
+            tmem_ld32(taddr + NH * BN, r);  // lo terms first (small), then the hi*hi partial sums
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
             for (int a = nhi - 1; a >= 0; --a) {
@@ -368,7 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NACC * BN)));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS));
     }
 }
 
@@ -621,17 +649,20 @@ static int load_driver_fns() {
     return 0;
 }
 
-// activation plane [B][H][W][C] bf16 -> im2col map: 128 pixels x 64 channels per load
-static int make_im2col_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int ks, int pixels) {
+// activation plane [B][H][W][cpitch] fp16 (first C channels used) -> im2col map: `pixels` x `bk` channels per load
+static int make_im2col_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int ks, int pixels, int cpitch = 0,
+                           int bk = TC_BK) {
+    if (cpitch == 0) cpitch = C;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)W * cpitch * 2, (cuuint64_t)H * W * cpitch * 2};
     const int pad = (ks - 1) / 2;
     int lower[2] = {-pad, -pad};
     int upper[2] = {pad - (ks - 1), pad - (ks - 1)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = g_encodeIm2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
-                                (cuuint32_t)TC_BK, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                (cuuint32_t)bk, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeIm2col failed (%d) for B=%d H=%d W=%d C=%d ks=%d", (int)r, B, H, W, C, ks);
         return -3;
@@ -640,19 +671,19 @@ static int make_im2col_map(CUtensorMap* map, const void* base, int B, int H, int
     // 128 KiB, drivers <= 13.1 set a bit that must be cleared.
     int drv = 0;
     cudaDriverGetVersion(&drv);
-    if (drv <= 13010 && (size_t)B * H * W * C * 2 < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+    if (drv <= 13010 && (size_t)B * H * W * cpitch * 2 < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
     return 0;
 }
 
-// weight plane [rows][K] bf16 -> 2-D tiled map with box 64 x box_rows
-static int make_tiled_map(CUtensorMap* map, const void* base, long long rows, long long K, int box_rows) {
+// weight plane [rows][K] fp16 -> 2-D tiled map with box bk x box_rows
+static int make_tiled_map(CUtensorMap* map, const void* base, long long rows, long long K, int box_rows, int bk = TC_BK) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%lld", (int)r, rows, K);
         return -3;
@@ -660,18 +691,23 @@ static int make_tiled_map(CUtensorMap* map, const void* base, long long rows, lo
     return 0;
 }
 
-template <int BN>
-static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const void* w_hi, const void* w_lo, const TcArgs& a,
-                     cudaStream_t s) {
-    CUtensorMap b_hi, b_lo;
-    const long long K = (long long)a.ks * a.ks * a.Cin;
-    int rc = make_tiled_map(&b_hi, w_hi, a.Cout, K, BN);
+template <int BN, int BK, int STAGES_, int NH, int MINB>
+static int launch_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int B, const TcArgs& a, cudaStream_t s) {
+    using Cfg = TcCfg<BN, BK, STAGES_, NH>;
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    int rc = make_im2col_map(&a_hi, x_hi, B, a.H, a.W, a.Cin, a.ks, TC_BM, a.cpitch, BK);
     if (rc) return rc;
-    rc = make_tiled_map(&b_lo, w_lo, a.Cout, K, BN);
+    rc = make_im2col_map(&a_lo, x_lo, B, a.H, a.W, a.Cin, a.ks, TC_BM, a.cpitch, BK);
+    if (rc) return rc;
+    const long long K = (long long)a.ks * a.ks * a.cpitch;
+    rc = make_tiled_map(&b_hi, w_hi, a.Cout, K, BN, BK);
+    if (rc) return rc;
+    rc = make_tiled_map(&b_lo, w_lo, a.Cout, K, BN, BK);
     if (rc) return rc;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, STAGES_, NH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES);
         if (e != cudaSuccess) {
             set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return (int)e;
@@ -679,7 +715,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const voi
         attr_done = true;
     }
     dim3 grid(ceil_div(a.Cout, BN), ceil_div(a.M, TC_BM));
-    conv_tc_kernel<BN><<<grid, 192, TcCfg<BN>::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, a);
+    conv_tc_kernel<BN, BK, STAGES_, NH, MINB><<<grid, 192, Cfg::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, a);
     return launch_status("conv_tc");
 }
 
@@ -730,30 +766,31 @@ extern "C" int fsdet_colstats(const float* z, int ld, size_t npix, int C, float*
 }
 
 extern "C" int fsdet_conv_tc_supported(int Cin, int Cout, int ksize) {
-    return (Cin % TC_BK == 0) && (Cout >= 8) && (Cout % 4 == 0) && (ksize == 1 || ksize == 3);
+    return (Cin % 32 == 0) && (Cout >= 8) && (Cout % 4 == 0) && (ksize == 1 || ksize == 3);
 }
 
 extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* amax_x,
-                                 const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin, int Cout, int ksize,
-                                 int accumulate, void* stream) {
+                                 const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin, int cpitch, int Cout,
+                                 int ksize, int accumulate, void* stream) {
     FSDET_CHECK_ARG(x_hi && x_lo && w_hi && w_lo && z, "conv_tc_fwd: null pointer");
-    FSDET_CHECK_ARG(fsdet_conv_tc_supported(Cin, Cout, ksize), "conv_tc_fwd: unsupported Cin=%d Cout=%d k=%d", Cin, Cout, ksize);
+    FSDET_CHECK_ARG(fsdet_conv_tc_supported(Cin, Cout, ksize) && cpitch >= Cin && cpitch % 8 == 0,
+                    "conv_tc_fwd: unsupported Cin=%d (pitch %d) Cout=%d k=%d", Cin, cpitch, Cout, ksize);
     FSDET_CHECK_ARG(ldz % 4 == 0 && aligned16(z) && aligned16(x_hi) && aligned16(x_lo) && aligned16(w_hi) && aligned16(w_lo),
                     "conv_tc_fwd: alignment");
     int rc = load_driver_fns();
     if (rc) return rc;
     TcArgs a;
     a.z = z; a.amax_a = amax_x; a.amax_b = amax_w; a.ldz = ldz; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ks = ksize;
-    a.pad = (ksize - 1) / 2; a.M = (long long)B * H * W; a.accumulate = accumulate;
+    a.pad = (ksize - 1) / 2; a.cpitch = cpitch; a.M = (long long)B * H * W; a.accumulate = accumulate;
     if (a.M == 0) return 0;
-    CUtensorMap a_hi, a_lo;
-    rc = make_im2col_map(&a_hi, x_hi, B, H, W, Cin, ksize, TC_BM);
-    if (rc) return rc;
-    rc = make_im2col_map(&a_lo, x_lo, B, H, W, Cin, ksize, TC_BM);
-    if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    if (Cout >= 128) return launch_tc<128>(a_hi, a_lo, w_hi, w_lo, a, s);
-    return launch_tc<64>(a_hi, a_lo, w_hi, w_lo, a, s);
+    const bool small_k = (Cin % 64 != 0) || (ksize * ksize * Cin <= 2304);
+    if (small_k) {   // 64-byte rows, one hi accumulator, two CTAs per SM
+        if (Cout >= 128) return launch_tc<128, 32, 3, 1, 2>(x_hi, x_lo, w_hi, w_lo, B, a, s);
+        return launch_tc<64, 32, 4, 1, 2>(x_hi, x_lo, w_hi, w_lo, B, a, s);
+    }
+    if (Cout >= 128) return launch_tc<128, 64, 3, NHI, 1>(x_hi, x_lo, w_hi, w_lo, B, a, s);
+    return launch_tc<64, 64, 4, NHI, 1>(x_hi, x_lo, w_hi, w_lo, B, a, s);
 }
 
 static int wg_splits(long long M, int Cin, int Cout, int ks, int bn) {

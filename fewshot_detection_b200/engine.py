@@ -267,7 +267,7 @@ class NetRunner(object):
     def _tc_ok(cin, cout, k):
         """Tensor-core path: >= 32 input channels (planes are zero-padded to a multiple of 64)."""
         return USE_TC and cin >= 32 and cin % 4 == 0 and cout % 4 == 0 and bool(
-            _lib.lib.fsdet_conv_tc_supported(_round_up(cin, 64), cout, k))
+            _lib.lib.fsdet_conv_tc_supported(_round_up(cin, 32), cout, k))
 
     @staticmethod
     def _split_tensor(t2d_ptr, ld, C, rows, dev, st, cpad=None, amax=None):
@@ -320,7 +320,7 @@ class NetRunner(object):
             xh, xl, xa = self._planes(x, st)
             wh, wl, wa = self._split_tensor(ptr(w_ohwi), cin, cin, cout * k * k, x.dev, st, cpad)
             self._timed('conv_tc', flops, 'fsdet_conv_tc_fwd', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(xa), ptr(wa), z.ptr, z.ld,
-                        x.B, x.H, x.W, cpad, cout, k, acc, st)
+                        x.B, x.H, x.W, _round_up(cin, 32), cpad, cout, k, acc, st)
             if stat_rows_out is not None:
                 call('fsdet_colstats', z.ptr, z.ld, x.npix, cout, ptr(stat_rows_out), st)
                 return _lib.lib.fsdet_colstats_rows(x.npix)
@@ -347,6 +347,7 @@ class NetRunner(object):
         ent = self.profile.setdefault(name, [0.0, []])
         ent[0] += flops
         ent[1].append((e0, e1))
+        self.profile.setdefault('_launches', []).append((name, flops, e0, e1, tuple(a for a in args if isinstance(a, int) and a < 100000)))
 
     @staticmethod
     def _param_grad(p):

@@ -87,8 +87,10 @@ int fsdet_weight_flip_transpose(const float* w, float* wt, int Cout, int kk, int
 int fsdet_pad_channels(const float* in, int cin, float* out, int cout, size_t rows, void* stream);
 
 /* ---- tensor-core convolution (tcgen05 + TMA im2col), csrc/conv_tc.cu ---- */
-/* Same contraction as fsdet_conv_fwd for layers with Cin % 64 == 0 (pad the
- * planes with zero channels otherwise), Cout % 4 == 0 (fsdet_conv_tc_supported).
+/* Same contraction as fsdet_conv_fwd for layers with Cin % 32 == 0, Cout % 4 == 0
+ * (fsdet_conv_tc_supported); `cpitch` >= Cin is the channel pitch of the planes
+ * (activation rows and the weights' [tap][channel] axis), so 32-channel tensors
+ * stored in 64-channel-padded planes are read without touching the padding.
  * Operands are fp16 hi/lo planes produced by fsdet_amax + fsdet_split_f16:
  * the tensor is scaled by the power of two that maps its absolute maximum
  * into [512, 1024), hi = fp16(s*x), lo = fp16(s*x - hi); three MMAs per K step
@@ -101,8 +103,8 @@ int fsdet_pad_channels(const float* in, int cin, float* out, int cout, size_t ro
  * fsdet_bn_finalize reads. */
 int fsdet_conv_tc_supported(int Cin, int Cout, int ksize);
 int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* amax_x,
-                      const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin, int Cout, int ksize,
-                      int accumulate, void* stream);
+                      const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin, int cpitch, int Cout,
+                      int ksize, int accumulate, void* stream);
 /* Weight gradient on the tensor cores (pixels are the GEMM K dimension; both
  * operands are consumed MN-major straight from the NHWC planes).  Needs
  * Cin % 64 == 0 and Cout % 64 == 0.  dw [Cout][k*k][Cin] fp32 (OHWI);

@@ -91,6 +91,7 @@ TC_CASES = [
     (2, 13, 13, 64, 128, 3), (4, 26, 26, 128, 64, 1), (1, 52, 52, 64, 128, 3), (2, 13, 13, 1024, 480, 1),
     (2, 13, 13, 1280, 1024, 3), (3, 6, 6, 1024, 1024, 3), (2, 19, 19, 256, 512, 3), (1, 104, 104, 128, 256, 3),
     (3, 4, 4, 128, 256, 3), (3, 8, 8, 64, 128, 3), (3, 4, 4, 256, 256, 3), (1, 2, 2, 64, 64, 3), (3, 16, 16, 64, 64, 1),
+    (2, 26, 26, 32, 64, 3), (2, 26, 26, 96, 128, 3), (2, 13, 13, 512, 1024, 3), (4, 26, 26, 512, 64, 1), (2, 52, 52, 256, 128, 1),
 ]
 
 
@@ -106,13 +107,13 @@ def test_conv_tc_fwd(L, B, H, W, Cin, Cout, k):
     ld = Cout + 4
     z = torch.zeros(B * H * W, ld, device='cuda')
     L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), X.lo.data_ptr(), Wp.hi.data_ptr(), Wp.lo.data_ptr(), X.a, Wp.a, z.data_ptr(), ld,
-           B, H, W, Cin, Cout, k, 0, st())
+           B, H, W, Cin, Cin, Cout, k, 0, st())
     torch.cuda.synchronize()
     got = z[:, :Cout].contiguous().view(B, H, W, Cout).permute(0, 3, 1, 2)
     assert rel(got, ref) < TOL_TC
     assert (z[:, Cout:] == 0).all()
     L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), X.lo.data_ptr(), Wp.hi.data_ptr(), Wp.lo.data_ptr(), X.a, Wp.a, z.data_ptr(), ld,
-           B, H, W, Cin, Cout, k, 1, st())
+           B, H, W, Cin, Cin, Cout, k, 1, st())
     got2 = z[:, :Cout].contiguous().view(B, H, W, Cout).permute(0, 3, 1, 2)
     assert rel(got2, 2 * ref) < TOL_TC
 
@@ -172,7 +173,7 @@ def test_conv_tc_padded_channels_and_small_cout(L):
     Wp = split(L, w.detach().permute(0, 2, 3, 1).contiguous().view(Cout * k * k, Cin), 64)
     z = torch.zeros(B * H * W, Cout, device='cuda')
     L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), X.lo.data_ptr(), Wp.hi.data_ptr(), Wp.lo.data_ptr(), X.a, Wp.a, z.data_ptr(), Cout,
-           B, H, W, 64, Cout, k, 0, st())
+           B, H, W, 32, 64, Cout, k, 0, st())
     assert rel(z.view(B, H, W, Cout).permute(0, 3, 1, 2), ref) < TOL_TC
     # dgrad: GEMM Cin = 64 (dz channels), Cout = 32
     wt = torch.empty(Cin, k * k, Cout, device='cuda')
@@ -181,7 +182,7 @@ def test_conv_tc_padded_channels_and_small_cout(L):
     D = split(L, nhwc(dz))
     dx = torch.zeros(B * H * W, Cin, device='cuda')
     L.call('fsdet_conv_tc_fwd', D.hi.data_ptr(), D.lo.data_ptr(), T.hi.data_ptr(), T.lo.data_ptr(), D.a, T.a, dx.data_ptr(), Cin,
-           B, H, W, Cout, Cin, k, 0, st())
+           B, H, W, Cout, Cout, Cin, k, 0, st())
     assert rel(dx.view(B, H, W, Cin).permute(0, 3, 1, 2), x.grad) < TOL_TC
     # wgrad with padded input channels: result [Cout][9][64], first 32 channels valid, rest zero
     nws = L.lib.fsdet_conv_tc_wgrad_workspace_floats(B, H, W, 64, Cout, k)
