@@ -485,8 +485,10 @@ __global__ void __launch_bounds__(256) conv_first_fwd_kernel(const float* __rest
 }
 
 // weight gradient: dw[co][tap][ci] = sum_p dz[p][co] * x[p+tap][ci].  One CTA walks image rows: the dz row and the
-// three x rows it needs are staged in shared memory; thread (tap, co) keeps its 4 input-channel sums in registers
-// for all rows of the CTA, partials are reduced in a fixed order afterwards.
+// three x rows it needs are staged in shared memory.  Thread (co, filter row ty, column segment) keeps the 3 taps of
+// its filter row x 4 input channels in registers and slides a 3-pixel window along its third of the image row
+// (one new x pixel + one dz value per step feed 12 FMAs); partials are reduced in a fixed order afterwards.
+constexpr int FW_SEG = 3;   // column segments per row (thread groups)
 __global__ void __launch_bounds__(288) conv_first_wgrad_kernel(const float* __restrict__ in0, int C0, const float* __restrict__ in1,
                                                                int C1, const float* __restrict__ dz, int lddz,
                                                                float* __restrict__ part, int B, int H, int W, int Cout) {
@@ -494,9 +496,12 @@ __global__ void __launch_bounds__(288) conv_first_wgrad_kernel(const float* __re
     float4* xs = reinterpret_cast<float4*>(sm);              // [3][W + 2] pixels of 4 channels (zero halo)
     float* ds = sm + 3 * (W + 2) * 4;                        // [W][32]
     const int tid = threadIdx.x;
-    const int co = tid & 31, tap = tid >> 5;                 // 9 warps = 9 taps
-    const int ty = tap / 3, tx = tap - ty * 3;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int co = tid & 31;
+    const int ty = (tid >> 5) % 3;                           // filter row
+    const int seg = (tid >> 5) / 3;                          // column segment 0..FW_SEG-1
+    const int wseg = (W + FW_SEG - 1) / FW_SEG;
+    const int wbeg = seg * wseg, wend = min(W, wbeg + wseg);
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;   // taps (ty, 0), (ty, 1), (ty, 2)
     const long long rows = (long long)B * H;
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const int b = (int)(row / H), h = (int)(row - (long long)b * H);
@@ -515,15 +520,26 @@ __global__ void __launch_bounds__(288) conv_first_wgrad_kernel(const float* __re
             *reinterpret_cast<float4*>(ds + pw * 32 + c4) = v;
         }
         __syncthreads();
-        const float4* xr = xs + ty * (W + 2) + tx;           // x[h + ty - 1][w + tx - 1] for w = 0
+        const float4* xr = xs + ty * (W + 2);                // xr[w + tx] = x[h + ty - 1][w + tx - 1]
+        if (wbeg < wend) {
+            float4 x0 = xr[wbeg], x1 = xr[wbeg + 1];
 #pragma unroll 4
-        for (int w = 0; w < W; ++w) {
-            const float d = ds[w * 32 + co];
-            const float4 v = xr[w];
-            acc.x = fmaf(d, v.x, acc.x); acc.y = fmaf(d, v.y, acc.y); acc.z = fmaf(d, v.z, acc.z); acc.w = fmaf(d, v.w, acc.w);
+            for (int w = wbeg; w < wend; ++w) {
+                const float4 x2 = xr[w + 2];
+                const float d = ds[w * 32 + co];
+                a0.x = fmaf(d, x0.x, a0.x); a0.y = fmaf(d, x0.y, a0.y); a0.z = fmaf(d, x0.z, a0.z); a0.w = fmaf(d, x0.w, a0.w);
+                a1.x = fmaf(d, x1.x, a1.x); a1.y = fmaf(d, x1.y, a1.y); a1.z = fmaf(d, x1.z, a1.z); a1.w = fmaf(d, x1.w, a1.w);
+                a2.x = fmaf(d, x2.x, a2.x); a2.y = fmaf(d, x2.y, a2.y); a2.z = fmaf(d, x2.z, a2.z); a2.w = fmaf(d, x2.w, a2.w);
+                x0 = x1; x1 = x2;
+            }
         }
     }
-    if (co < Cout) *reinterpret_cast<float4*>(part + ((long long)blockIdx.x * Cout + co) * 36 + tap * 4) = acc;
+    if (co < Cout) {
+        float* dst = part + (((long long)blockIdx.x * FW_SEG + seg) * Cout + co) * 36 + ty * 12;
+        *reinterpret_cast<float4*>(dst) = a0;
+        *reinterpret_cast<float4*>(dst + 4) = a1;
+        *reinterpret_cast<float4*>(dst + 8) = a2;
+    }
 }
 
 static int wgrad_splits(long long M, int Cin, int Cout, int ks, int bmc) {
@@ -637,7 +653,7 @@ static int first_wgrad_ctas(int B, int H) {
 
 extern "C" size_t fsdet_conv_first_wgrad_workspace_floats(int B, int H, int W, int Cout) {
     (void)W;
-    return (size_t)first_wgrad_ctas(B, H) * Cout * 36;
+    return (size_t)first_wgrad_ctas(B, H) * FW_SEG * Cout * 36;
 }
 
 extern "C" int fsdet_conv_first_fwd(const float* in0, int C0, const float* in1, int C1, const float* w_pad4, float* z, int ldz,
@@ -658,7 +674,7 @@ extern "C" int fsdet_conv_first_wgrad(const float* in0, int C0, const float* in1
     FSDET_CHECK_ARG(Cout > 0 && Cout <= 32 && Cout % 4 == 0 && lddz % 4 == 0, "conv_first_wgrad: Cout=%d lddz=%d", Cout, lddz);
     FSDET_CHECK_ARG(aligned16(dz) && aligned16(dw) && aligned16(workspace), "conv_first_wgrad: alignment");
     const int ctas = first_wgrad_ctas(B, H);
-    FSDET_CHECK_ARG(workspace_floats >= (size_t)ctas * Cout * 36, "conv_first_wgrad: workspace too small");
+    FSDET_CHECK_ARG(workspace_floats >= (size_t)ctas * FW_SEG * Cout * 36, "conv_first_wgrad: workspace too small");
     if (ctas == 0) return 0;
     const size_t smem = ((size_t)3 * (W + 2) * 4 + (size_t)W * 32) * sizeof(float);
     FSDET_CHECK_ARG(smem <= 200 * 1024, "conv_first_wgrad: image width %d too large", W);
@@ -674,6 +690,6 @@ extern "C" int fsdet_conv_first_wgrad(const float* in0, int C0, const float* in1
     if (st) return st;
     long long n4 = (long long)Cout * 36 / 4;
     splitk_reduce_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(workspace), reinterpret_cast<float4*>(dw),
-                                                          n4, ctas);
+                                                          n4, ctas * FW_SEG);
     return launch_status("conv_first_wgrad_reduce");
 }
