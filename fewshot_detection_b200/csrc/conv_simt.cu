@@ -433,54 +433,66 @@ __device__ __forceinline__ float in_px(const float* __restrict__ in0, int C0, co
     return 0.f;
 }
 
-// forward: one thread = two vertically adjacent pixels, all Cout channels (each weight float4 read from shared
-// memory feeds 8 FMAs); tile 16 rows x 32 cols per CTA of 256 threads
-constexpr int FT_H = 16, FT_W = 32;
+// forward: lane = output channel (its 9x4 filter lives in registers), one warp walks along an image row keeping the
+// 3x3 input window in registers (3 broadcast shared-memory loads + 36 FMAs per pixel, one coalesced 128-byte store).
+// CTA tile = FT_H rows (one per warp) x FT_W columns.
+constexpr int FT_H = 8, FT_W = 104;
 __global__ void __launch_bounds__(256) conv_first_fwd_kernel(const float* __restrict__ in0, int C0, const float* __restrict__ in1,
                                                              int C1, const float* __restrict__ w /* [Cout][9][4] */,
                                                              float* __restrict__ z, int ldz, int B, int H, int W, int Cout) {
     __shared__ float4 xs[FT_H + 2][FT_W + 2];
-    __shared__ float4 ws[32 * 9];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_w = (W + FT_W - 1) / FT_W, tiles_h = (H + FT_H - 1) / FT_H;
     int t = blockIdx.x;
     const int tw = t % tiles_w; t /= tiles_w;
     const int th = t % tiles_h;
     const int b = t / tiles_h;
     const int h0 = th * FT_H, w0 = tw * FT_W;
-    for (int i = tid; i < Cout * 9; i += 256) ws[i] = ldg4(w + i * 4);
-    for (int i = tid; i < (FT_H + 2) * (FT_W + 2); i += 256) {
-        int r = i / (FT_W + 2), c = i - r * (FT_W + 2);
-        int h = h0 + r - 1, ww = w0 + c - 1;
-        xs[r][c] = make_float4(in_px(in0, C0, in1, C1, b, 0, h, ww, H, W), in_px(in0, C0, in1, C1, b, 1, h, ww, H, W),
-                               in_px(in0, C0, in1, C1, b, 2, h, ww, H, W), in_px(in0, C0, in1, C1, b, 3, h, ww, H, W));
-    }
-    __syncthreads();
-    const int lr = (tid / FT_W) * 2, lc = tid % FT_W;   // rows lr, lr+1
-    const int h = h0 + lr, ww = w0 + lc;
-    if (h >= H || ww >= W) return;
-    float4 x[12];                                       // 4 input rows x 3 columns
+    // stage the input tile (+halo) channel plane by channel plane: one 32-bit-indexed load per element, batches of
+    // 4 independent loads per thread for memory-level parallelism
+    constexpr int NPX = (FT_H + 2) * (FT_W + 2);
+    const int HW = H * W;
+    float* xsf = reinterpret_cast<float*>(&xs[0][0]);
 #pragma unroll
-    for (int k = 0; k < 12; ++k) x[k] = xs[lr + k / 3][lc + k % 3];
-    const bool two = h + 1 < H;
-    float* z0 = z + (((long long)b * H + h) * W + ww) * ldz;
-    float* z1 = z0 + (long long)W * ldz;
-    for (int co = 0; co < Cout; co += 4) {
-        float o0[4], o1[4];
+    for (int ch = 0; ch < 4; ++ch) {
+        const float* plane = ch < C0 ? in0 + ((long long)b * C0 + ch) * HW
+                                     : (ch < C0 + C1 ? in1 + ((long long)b * C1 + (ch - C0)) * HW : nullptr);
+        for (int base = 0; base < NPX; base += 4 * 256) {
+            float v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const float4 wv = ws[(co + j) * 9 + k];
-                const float4 p0 = x[k], p1 = x[k + 3];
-                a0 = fmaf(p0.x, wv.x, a0); a0 = fmaf(p0.y, wv.y, a0); a0 = fmaf(p0.z, wv.z, a0); a0 = fmaf(p0.w, wv.w, a0);
-                a1 = fmaf(p1.x, wv.x, a1); a1 = fmaf(p1.y, wv.y, a1); a1 = fmaf(p1.z, wv.z, a1); a1 = fmaf(p1.w, wv.w, a1);
+            for (int u = 0; u < 4; ++u) {
+                const int i = base + u * 256 + tid;
+                const int r = i / (FT_W + 2), c = i - r * (FT_W + 2);
+                const int h = h0 + r - 1, ww = w0 + c - 1;
+                v[u] = (plane && i < NPX && h >= 0 && h < H && ww >= 0 && ww < W) ? __ldg(plane + h * W + ww) : 0.f;
             }
-            o0[j] = a0; o1[j] = a1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = base + u * 256 + tid;
+                if (i < NPX) xsf[i * 4 + ch] = v[u];
+            }
         }
-        *reinterpret_cast<float4*>(z0 + co) = make_float4(o0[0], o0[1], o0[2], o0[3]);
-        if (two) *reinterpret_cast<float4*>(z1 + co) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+    }
+    float4 wr[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wr[k] = lane < Cout ? ldg4(w + (lane * 9 + k) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const int h = h0 + warp;
+    if (h >= H) return;
+    const int wn = min(FT_W, W - w0);
+    float4 x00 = xs[warp][0], x01 = xs[warp][1], x10 = xs[warp + 1][0], x11 = xs[warp + 1][1], x20 = xs[warp + 2][0], x21 = xs[warp + 2][1];
+    float* zr = z + (((long long)b * H + h) * W + w0) * ldz + lane;
+#pragma unroll 2
+    for (int c = 0; c < wn; ++c) {
+        const float4 x02 = xs[warp][c + 2], x12 = xs[warp + 1][c + 2], x22 = xs[warp + 2][c + 2];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent FMA chains (one per input channel)
+#define FSDET_TAP(X, Wv) a0 = fmaf(X.x, Wv.x, a0); a1 = fmaf(X.y, Wv.y, a1); a2 = fmaf(X.z, Wv.z, a2); a3 = fmaf(X.w, Wv.w, a3);
+        FSDET_TAP(x00, wr[0]) FSDET_TAP(x01, wr[1]) FSDET_TAP(x02, wr[2])
+        FSDET_TAP(x10, wr[3]) FSDET_TAP(x11, wr[4]) FSDET_TAP(x12, wr[5])
+        FSDET_TAP(x20, wr[6]) FSDET_TAP(x21, wr[7]) FSDET_TAP(x22, wr[8])
+#undef FSDET_TAP
+        if (lane < Cout) zr[(long long)c * ldz] = (a0 + a1) + (a2 + a3);
+        x00 = x01; x01 = x02; x10 = x11; x11 = x12; x20 = x21; x21 = x22;
     }
 }
 
@@ -506,18 +518,46 @@ __global__ void __launch_bounds__(288) conv_first_wgrad_kernel(const float* __re
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const int b = (int)(row / H), h = (int)(row - (long long)b * H);
         __syncthreads();
-        for (int i = tid; i < 3 * (W + 2); i += blockDim.x) {
-            int r = i / (W + 2), c = i - r * (W + 2);
-            int hh = h + r - 1, ww = c - 1;
-            xs[i] = make_float4(in_px(in0, C0, in1, C1, b, 0, hh, ww, H, W), in_px(in0, C0, in1, C1, b, 1, hh, ww, H, W),
-                                in_px(in0, C0, in1, C1, b, 2, hh, ww, H, W), in_px(in0, C0, in1, C1, b, 3, hh, ww, H, W));
+        // staging, channel plane by channel plane, in batches of 4 independent loads per thread
+        {
+            const int HW = H * W, NX = 3 * (W + 2);
+            float* xsf = reinterpret_cast<float*>(xs);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                const float* plane = ch < C0 ? in0 + ((long long)b * C0 + ch) * HW
+                                             : (ch < C0 + C1 ? in1 + ((long long)b * C1 + (ch - C0)) * HW : nullptr);
+                for (int base = 0; base < NX; base += 4 * 288) {
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = base + u * 288 + tid;
+                        const int r = i / (W + 2), c = i - r * (W + 2);
+                        const int hh = h + r - 1, ww = c - 1;
+                        v[u] = (plane && i < NX && hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(plane + hh * W + ww) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = base + u * 288 + tid;
+                        if (i < NX) xsf[i * 4 + ch] = v[u];
+                    }
+                }
+            }
         }
         const float* drow = dz + (row * W) * lddz;
-        for (int i = tid; i < W * 8; i += blockDim.x) {      // 8 float4 per pixel (32 channels, zero beyond Cout)
-            int pw = i >> 3, c4 = (i & 7) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c4 < Cout) v = ldg4(drow + (long long)pw * lddz + c4);
-            *reinterpret_cast<float4*>(ds + pw * 32 + c4) = v;
+        for (int base = 0; base < W * 8; base += 6 * 288) {  // 8 float4 per pixel (32 channels, zero beyond Cout)
+            float4 v[6];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int i = base + u * 288 + tid;
+                const int pw = i >> 3, c4 = (i & 7) * 4;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < W * 8 && c4 < Cout) v[u] = ldg4(drow + (long long)pw * lddz + c4);
+            }
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int i = base + u * 288 + tid;
+                if (i < W * 8) *reinterpret_cast<float4*>(ds + (i >> 3) * 32 + (i & 7) * 4) = v[u];
+            }
         }
         __syncthreads();
         const float4* xr = xs + ty * (W + 2);                // xr[w + tx] = x[h + ty - 1][w + tx - 1]
@@ -663,6 +703,7 @@ extern "C" int fsdet_conv_first_fwd(const float* in0, int C0, const float* in1, 
                     "conv_first_fwd: Cout=%d ldz=%d", Cout, ldz);
     long long tiles = (long long)B * ceil_div(H, FT_H) * ceil_div(W, FT_W);
     if (tiles == 0) return 0;
+    FSDET_CHECK_ARG(tiles < (1ll << 31), "conv_first_fwd: too many tiles");
     conv_first_fwd_kernel<<<(unsigned)tiles, 256, 0, (cudaStream_t)stream>>>(in0, C0, in1, C1, w_pad4, z, ldz, B, H, W, Cout);
     return launch_status("conv_first_fwd");
 }

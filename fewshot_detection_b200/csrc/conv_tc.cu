@@ -168,6 +168,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -260,7 +275,8 @@ struct TcCfg {
 template <int BN, int BK, int STAGES_, int NH, int MINB>
 __global__ void __launch_bounds__(192, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
-               const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcArgs p) {
+               const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+               const __grid_constant__ CUtensorMap tmZ, const TcArgs p) {
     using Cfg = TcCfg<BN, BK, STAGES_, NH>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int A_BYTES = Cfg::A_BYTES;
@@ -283,6 +299,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         tma_prefetch_desc(&tmAlo);
         tma_prefetch_desc(&tmBhi);
         tma_prefetch_desc(&tmBlo);
+        tma_prefetch_desc(&tmZ);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -350,15 +367,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
             umma_commit(tmem_full_bar);      // accumulator complete
         }
     } else {
-        // epilogue warps 2..5 -> TMEM lane quarters (warp % 4)
+        // epilogue warps 2..5 -> TMEM lane quarters (warp % 4).  Each warp owns 32 output pixels.  In the short-K
+        // flavour it stages each 32x32 fp32 chunk in (128-byte-swizzled) shared memory - the operand stages are free
+        // once the accumulator is complete - and one lane issues a TMA tensor store (reduce-add when accumulating), so
+        // the global writes are full 128-byte rows, asynchronous, and clipped at the tensor edges by the hardware.
         const int quarter = warp & 3;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        const long long m = m0 + quarter * 32 + lane;
-        const bool row_ok = m < p.M;
-        float* zr = p.z + (row_ok ? m : 0) * p.ldz;
         const float inv = 1.f / (scale_from_amax(p.amax_a ? __ldg(p.amax_a) : 0.f) * scale_from_amax(p.amax_b ? __ldg(p.amax_b) : 0.f));
         const int nhi = nk < NH ? nk : NH;
+        uint8_t* stage_buf = smem + quarter * 8192;          // two 4 KB buffers per warp
+        const long long mrow = m0 + quarter * 32;
+        const long long m = mrow + lane;
+        float* zr = p.z + (m < p.M ? m : 0) * p.ldz;
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
             uint32_t r[32];
@@ -373,7 +394,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
             }
             const int n0 = n_tile * BN + ch * 32;
-            if (row_ok) {
+            if constexpr (MINB == 2) {
+                // short-K flavour (output bytes per MMA are high): TMA tensor store of a swizzled shared-memory tile
+                if (n0 < p.Cout && mrow < p.M) {             // warp-uniform
+                    uint8_t* buf = stage_buf + (ch & 1) * 4096;
+                    if (ch >= 2) {                           // the store that last read this buffer must have drained
+                        if (lane == 0) tma_store_wait_read<1>();
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 v = make_float4(acc[4 * j] * inv, acc[4 * j + 1] * inv, acc[4 * j + 2] * inv, acc[4 * j + 3] * inv);
+                        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (p.accumulate) tma_reduce_add_2d(&tmZ, buf, n0, (int)mrow);
+                        else tma_store_2d(&tmZ, buf, n0, (int)mrow);
+                        tma_store_commit();
+                    }
+                }
+            } else if (m < p.M) {
+                // long-K flavour: the epilogue is a small fraction of the tile, plain vector stores
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int n = n0 + j;
@@ -390,6 +433,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                     }
                 }
             }
+        }
+        if constexpr (MINB == 2) {
+            if (lane == 0) tma_store_wait_read<0>();         // shared memory must outlive the bulk reads
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -436,7 +483,7 @@ struct WgCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, int TAPS>   // N tile = TAPS filter taps x (BN / TAPS) input channels
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant__ CUtensorMap tmDlo,
                 const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__ CUtensorMap tmXlo, const TcWgArgs p) {
@@ -451,9 +498,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int ci_tiles = (p.Cin + BN - 1) / BN;
-    const int tap = blockIdx.x / ci_tiles;
-    const int ci0 = (blockIdx.x - tap * ci_tiles) * BN;
+    constexpr int CIB = BN / TAPS;                      // input channels per tap in this tile (64 or 128)
+    const int kk = p.ks * p.ks;
+    const int ci_tiles = (p.Cin + CIB - 1) / CIB;
+    const int tap0 = (blockIdx.x / ci_tiles) * TAPS;
+    const int ci0 = (blockIdx.x - (blockIdx.x / ci_tiles) * ci_tiles) * CIB;
     const int co0 = blockIdx.y * 128;
     const long long pbeg = (long long)blockIdx.z * p.pix_per_split;
     long long pend = pbeg + p.pix_per_split;
@@ -484,7 +533,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
     if (warp == 0) {
         if (lane == 0) {
             const int HW = p.H * p.W;
-            const int r = tap / p.ks, sx = tap - r * p.ks;
             for (int kb = 0; kb < nk; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
@@ -501,10 +549,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
                 }
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j) {
-                    tma_load_im2col_4d(st + 2 * Cfg::A_BYTES + j * WG_BLK, &tmXhi, &full_bar[s], ci0 + 64 * j, pw - p.pad,
+                    int tap = tap0 + (j * 64) / CIB;
+                    if (tap >= kk) tap = kk - 1;      // tail group: duplicate load, its columns are not stored
+                    const int r = tap / p.ks, sx = tap - r * p.ks;
+                    const int ci = ci0 + (j * 64) % CIB;
+                    tma_load_im2col_4d(st + 2 * Cfg::A_BYTES + j * WG_BLK, &tmXhi, &full_bar[s], ci, pw - p.pad, ph - p.pad, img,
+                                       (uint16_t)sx, (uint16_t)r);
+                    tma_load_im2col_4d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + j * WG_BLK, &tmXlo, &full_bar[s], ci, pw - p.pad,
                                        ph - p.pad, img, (uint16_t)sx, (uint16_t)r);
-                    tma_load_im2col_4d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + j * WG_BLK, &tmXlo, &full_bar[s], ci0 + 64 * j,
-                                       pw - p.pad, ph - p.pad, img, (uint16_t)sx, (uint16_t)r);
                 }
             }
         }
@@ -537,7 +589,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
         const int quarter = warp & 3;
         const int co = co0 + quarter * 32 + lane;
         const long long K = (long long)p.ks * p.ks * p.Cin;
-        float* orow = p.out + ((long long)blockIdx.z * p.Cout + (co < p.Cout ? co : 0)) * K + (long long)tap * p.Cin;
+        float* orow = p.out + ((long long)blockIdx.z * p.Cout + (co < p.Cout ? co : 0)) * K;
         if (nk > 0) {
             mbar_wait(tmem_full_bar, 0);
             tc_fence_after();
@@ -561,12 +613,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
             }
-            const int c = ci0 + ch * 32;
-            if (co < p.Cout) {
+            const int tap = tap0 + (ch * 32) / CIB;
+            const int c = ci0 + (ch * 32) % CIB;
+            if (co < p.Cout && tap < kk) {
+                float* o = orow + (long long)tap * p.Cin + c;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     if (c + j < p.Cin)  // Cin % 4 == 0
-                        *reinterpret_cast<float4*>(orow + c + j) = make_float4(acc[j] * inv, acc[j + 1] * inv, acc[j + 2] * inv, acc[j + 3] * inv);
+                        *reinterpret_cast<float4*>(o + j) = make_float4(acc[j] * inv, acc[j + 1] * inv, acc[j + 2] * inv, acc[j + 3] * inv);
             }
         }
     }
@@ -704,6 +758,19 @@ static int launch_tc(const void* x_hi, const void* x_lo, const void* w_hi, const
     if (rc) return rc;
     rc = make_tiled_map(&b_lo, w_lo, a.Cout, K, BN, BK);
     if (rc) return rc;
+    CUtensorMap zmap;   // fp32 output [M][ldz] (first Cout columns): 32 x 32 boxes, 128-byte swizzle
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)a.Cout, (cuuint64_t)a.M};
+        cuuint64_t strides[1] = {(cuuint64_t)a.ldz * 4};
+        cuuint32_t box[2] = {32, 32};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_encodeTiled(&zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.z, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("conv_tc: output tensor map failed (%d) M=%lld Cout=%d ldz=%d", (int)r, a.M, a.Cout, a.ldz);
+            return -3;
+        }
+    }
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, STAGES_, NH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -715,7 +782,7 @@ static int launch_tc(const void* x_hi, const void* x_lo, const void* w_hi, const
         attr_done = true;
     }
     dim3 grid(ceil_div(a.Cout, BN), ceil_div(a.M, TC_BM));
-    conv_tc_kernel<BN, BK, STAGES_, NH, MINB><<<grid, 192, Cfg::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, a);
+    conv_tc_kernel<BN, BK, STAGES_, NH, MINB><<<grid, 192, Cfg::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, zmap, a);
     return launch_status("conv_tc");
 }
 
@@ -783,6 +850,7 @@ extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void*
     a.z = z; a.amax_a = amax_x; a.amax_b = amax_w; a.ldz = ldz; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ks = ksize;
     a.pad = (ksize - 1) / 2; a.cpitch = cpitch; a.M = (long long)B * H * W; a.accumulate = accumulate;
     if (a.M == 0) return 0;
+    FSDET_CHECK_ARG(a.M < (1ll << 31), "conv_tc_fwd: too many pixels");
     cudaStream_t s = (cudaStream_t)stream;
     const bool small_k = (Cin % 64 != 0) || (ksize * ksize * Cin <= 2304);
     if (small_k) {   // 64-byte rows, one hi accumulator, two CTAs per SM
@@ -793,8 +861,13 @@ extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void*
     return launch_tc<64, 64, 4, NHI, 1>(x_hi, x_lo, w_hi, w_lo, B, a, s);
 }
 
-static int wg_splits(long long M, int Cin, int Cout, int ks, int bn) {
-    long long tiles = (long long)((Cin + bn - 1) / bn) * ks * ks * ((Cout + 127) / 128);
+// tile shape of the weight-gradient kernel: Cin <= 64 packs two filter taps into one 128-wide N tile
+static inline int wg_cib(int Cin) { return Cin >= 128 ? 128 : 64; }
+static inline int wg_taps(int Cin) { return Cin >= 128 ? 1 : 2; }
+
+static int wg_splits(long long M, int Cin, int Cout, int ks, int /*bn*/) {
+    long long tiles = (long long)((Cin + wg_cib(Cin) - 1) / wg_cib(Cin)) * ((ks * ks + wg_taps(Cin) - 1) / wg_taps(Cin)) *
+                      ((Cout + 127) / 128);
     long long want = (2LL * kNumSMs + tiles - 1) / tiles;
     long long maxs = (M + 511) / 512;  // at least 512 pixels (8 stages) per split
     if (want > maxs) want = maxs;
@@ -813,20 +886,21 @@ extern "C" size_t fsdet_conv_tc_wgrad_workspace_floats(int B, int H, int W, int 
     return splits > 1 ? (size_t)splits * Cout * ksize * ksize * Cin : 0;
 }
 
-template <int BN>
+template <int BN, int TAPS>
 static int launch_wg(const CUtensorMap& dhi, const CUtensorMap& dlo, const CUtensorMap& xhi, const CUtensorMap& xlo,
                      const TcWgArgs& a, int splits, cudaStream_t s) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<BN>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<BN>::SMEM_BYTES);
         if (e != cudaSuccess) {
             set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return (int)e;
         }
         attr_done = true;
     }
-    dim3 grid(((a.Cin + BN - 1) / BN) * a.ks * a.ks, (a.Cout + 127) / 128, splits);
-    wgrad_tc_kernel<BN><<<grid, 192, WgCfg<BN>::SMEM_BYTES, s>>>(dhi, dlo, xhi, xlo, a);
+    constexpr int CIB = BN / TAPS;
+    dim3 grid(((a.Cin + CIB - 1) / CIB) * ((a.ks * a.ks + TAPS - 1) / TAPS), (a.Cout + 127) / 128, splits);
+    wgrad_tc_kernel<BN, TAPS><<<grid, 192, WgCfg<BN>::SMEM_BYTES, s>>>(dhi, dlo, xhi, xlo, a);
     return launch_status("conv_tc_wgrad");
 }
 
@@ -873,7 +947,7 @@ extern "C" int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const voi
     rc = make_im2col_map(&xlo, x_lo, B, H, W, Cin, ksize, WG_BP);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    rc = (bn == 128) ? launch_wg<128>(dhi, dlo, xhi, xlo, a, splits, s) : launch_wg<64>(dhi, dlo, xhi, xlo, a, splits, s);
+    rc = (bn == 128) ? launch_wg<128, 1>(dhi, dlo, xhi, xlo, a, splits, s) : launch_wg<128, 2>(dhi, dlo, xhi, xlo, a, splits, s);
     if (rc) return rc;
     if (splits > 1) {
         long long n4 = (long long)Cout * ksize * ksize * Cin / 4;
