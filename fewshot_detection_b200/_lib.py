@@ -46,8 +46,8 @@ SIGNATURES = {
     'fsdet_bn_act_fwd': ('pippfpipippppipiiiip', 'i'),
     'fsdet_bn_act_bwd_reduce': ('pipipippppfpiiiiip', 'i'),
     'fsdet_bn_bwd_rows': ('iii', 'i'),
-    'fsdet_bn_bwd_finalize': ('pidpppppiip', 'i'),
-    'fsdet_bn_act_bwd_apply': ('pipipipppppfpipiiiiip', 'i'),
+    'fsdet_bn_bwd_finalize': ('pidppppppiip', 'i'),
+    'fsdet_bn_act_bwd_apply': ('pipipipppppfpippipiiiiip', 'i'),
     'fsdet_maxpool_fwd': ('pipiiiiiip', 'i'),
     'fsdet_maxpool_bwd': ('pipipiiiiiip', 'i'),
     'fsdet_reorg_fwd': ('pipiiiiip', 'i'),

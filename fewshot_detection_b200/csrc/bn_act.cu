@@ -56,19 +56,24 @@ __global__ void __launch_bounds__(1024) colsum_double_kernel(const float* __rest
     }
 }
 
-// same reduction over double-precision partial rows (backward pass)
-__global__ void __launch_bounds__(1024) colsum_dd_kernel(const double* __restrict__ part, int nparts, int ncols,
+// reduction over the double-precision partial rows of the backward pass: columns [0, nsum) are summed (fixed
+// order), columns [nsum, ncols) hold maxima
+__global__ void __launch_bounds__(1024) colsum_dd_kernel(const double* __restrict__ part, int nparts, int ncols, int nsum,
                                                          double* __restrict__ out) {
     __shared__ double red[32][33];
     int col = blockIdx.x * 32 + threadIdx.x;
+    const bool is_max = col >= nsum;
     double s = 0.0;
     if (col < ncols)
-        for (int r = threadIdx.y; r < nparts; r += 32) s += part[(long long)r * ncols + col];
+        for (int r = threadIdx.y; r < nparts; r += 32) {
+            const double v = part[(long long)r * ncols + col];
+            s = is_max ? fmax(s, v) : s + v;
+        }
     red[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
     if (threadIdx.y == 0 && col < ncols) {
         double t = 0.0;
-        for (int i = 0; i < 32; ++i) t += red[i][threadIdx.x];
+        for (int i = 0; i < 32; ++i) t = is_max ? fmax(t, red[i][threadIdx.x]) : t + red[i][threadIdx.x];
         out[col] = t;
     }
 }
@@ -201,45 +206,65 @@ __global__ void __launch_bounds__(256) bn_act_flat_kernel(const FwdArgs a) {
     if (a.fh) store_planes4(a.fh, a.fl, p * a.Cpad + c, v, plane_scale(__ldg(a.amax)));
 }
 
-// one thread = one 2x2 window x 4 channels; windows cover ceil(H/2) x ceil(W/2)
+// block (TC channel-vector lanes, TY windows): one thread = one 2x2 window x 4 channels per pass over the channel
+// lanes; windows cover ceil(H/2) x ceil(W/2).  FULL = some full-resolution output is wanted; otherwise only the
+// pooled activation is produced, from max(leaky(y)) == leaky(max(y)) (leaky is monotone).
+template <bool FULL>
 __global__ void __launch_bounds__(256) bn_act_pool_kernel(const FwdArgs a) {
     const int H = a.H, W = a.W;
     const int H2 = (H + 1) >> 1, W2 = (W + 1) >> 1, Hp = H >> 1, Wp = W >> 1;
-    const unsigned CP4 = a.Cpad >> 2;
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;   // host guarantees n < 2^31: 32-bit index math
-    const unsigned n = (unsigned)a.B * H2 * W2 * CP4;
-    if (i >= n) return;
-    const unsigned wi = i / CP4;
-    const int c = (int)(i - wi * CP4) * 4;
+    const int CP4 = a.Cpad >> 2;
+    const unsigned wi = blockIdx.x * blockDim.y + threadIdx.y;   // host guarantees B*H*W < 2^31
+    if (wi >= (unsigned)a.B * H2 * W2) return;
     const unsigned t = wi / W2;
     const int w2 = (int)(wi - t * W2);
     const int b = (int)(t / H2);
     const int h2 = (int)(t - (unsigned)b * H2);
-    const bool cok = c < a.C;
+    const bool whole = h2 < Hp && w2 < Wp;
+    if (!FULL && !whole) return;                                 // no pooled output for windows cut by an odd edge
     const float psc = (a.fh || a.ph) ? plane_scale(__ldg(a.amax)) : 1.f;
-    float4 sc = make_float4(0, 0, 0, 0), sh = sc;
-    if (cok) { sc = ldg4(a.scale + c); sh = ldg4(a.shift + c); }
-    float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    const float slope = a.slope;
+    const unsigned p00 = ((unsigned)b * H + 2 * h2) * W + 2 * w2;
+    const unsigned pp = ((unsigned)b * Hp + h2) * Wp + w2;
+    for (int cv = threadIdx.x; cv < CP4; cv += blockDim.x) {
+        const int c = cv * 4;
+        const bool cok = c < a.C;
+        float4 sc = make_float4(0, 0, 0, 0), sh = sc;
+        if (cok) { sc = ldg4(a.scale + c); sh = ldg4(a.shift + c); }
+        float4 mx;
+        if (FULL) {
+            mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-            int h = h2 * 2 + dy, w = w2 * 2 + dx;
-            if (h < H && w < W) {
-                long long p = ((long long)b * H + h) * W + w;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (cok) {
-                    v = act4(ldg4(a.z + p * a.ldz + c), sc, sh, a.slope);
-                    if (a.yf) *reinterpret_cast<float4*>(a.yf + p * a.ldf + c) = v;
+            for (int q = 0; q < 4; ++q) {
+                if (2 * h2 + (q >> 1) < H && 2 * w2 + (q & 1) < W) {
+                    const unsigned p = p00 + (q >> 1) * W + (q & 1);
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cok) {
+                        v = act4(ldg4(a.z + (size_t)p * a.ldz + c), sc, sh, slope);
+                        if (a.yf) *reinterpret_cast<float4*>(a.yf + (size_t)p * a.ldf + c) = v;
+                    }
+                    if (a.fh) store_planes4(a.fh, a.fl, (long long)p * a.Cpad + c, v, psc);
+                    mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
                 }
-                if (a.fh) store_planes4(a.fh, a.fl, p * a.Cpad + c, v, psc);
-                mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+            }
+        } else {
+            mx = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cok) {
+                float4 v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = ldg4(a.z + (size_t)(p00 + (q >> 1) * W + (q & 1)) * a.ldz + c);
+                float4 y;
+                y.x = fmaxf(fmaxf(fmaf(v[0].x, sc.x, sh.x), fmaf(v[1].x, sc.x, sh.x)), fmaxf(fmaf(v[2].x, sc.x, sh.x), fmaf(v[3].x, sc.x, sh.x)));
+                y.y = fmaxf(fmaxf(fmaf(v[0].y, sc.y, sh.y), fmaf(v[1].y, sc.y, sh.y)), fmaxf(fmaf(v[2].y, sc.y, sh.y), fmaf(v[3].y, sc.y, sh.y)));
+                y.z = fmaxf(fmaxf(fmaf(v[0].z, sc.z, sh.z), fmaf(v[1].z, sc.z, sh.z)), fmaxf(fmaf(v[2].z, sc.z, sh.z), fmaf(v[3].z, sc.z, sh.z)));
+                y.w = fmaxf(fmaxf(fmaf(v[0].w, sc.w, sh.w), fmaf(v[1].w, sc.w, sh.w)), fmaxf(fmaf(v[2].w, sc.w, sh.w), fmaf(v[3].w, sc.w, sh.w)));
+                mx = make_float4(leaky(y.x, slope), leaky(y.y, slope), leaky(y.z, slope), leaky(y.w, slope));
             }
         }
-    if (h2 < Hp && w2 < Wp) {
-        long long pp = ((long long)b * Hp + h2) * Wp + w2;
-        if (a.yp && cok) *reinterpret_cast<float4*>(a.yp + pp * a.ldp + c) = mx;
-        if (a.ph) store_planes4(a.ph, a.pl, pp * a.Cpad + c, mx, psc);
+        if (whole) {
+            if (a.yp && cok) *reinterpret_cast<float4*>(a.yp + (size_t)pp * a.ldp + c) = mx;
+            if (a.ph) store_planes4(a.ph, a.pl, (long long)pp * a.Cpad + c, mx, psc);
+        }
     }
 }
 
@@ -254,14 +279,47 @@ struct BwdArgs {
     const float* invstd;
     const double* coef;
     float* dz;
-    float* amax_out;
+    __half* dh;
+    __half* dl;
+    const float* amax;
     double* partial;
-    int ldz, ld_dyf, ld_dyp, lddz;
+    int ldz, ld_dyf, ld_dyp, lddz, cpad;
     int B, H, W, C;
     float slope;
     int has_bn;
 };
 
+// compensated (Kahan) fp32 accumulation: (s, e) carries ~48 bits, read back as (double)s - (double)e
+__device__ __forceinline__ void kahan_add(float& s, float& e, float x) {
+    const float y = x - e;
+    const float t = s + y;
+    e = (t - s) - y;
+    s = t;
+}
+
+// reduce-pass epilogue: red[blockDim.y][TC*16] doubles (per thread: 4 x sum(du), 4 x sum(du*xhat), 4 x max|du|,
+// 4 x max|xhat|) -> one partial row; column j is reduced over the blockDim.y lanes in a fixed order, all threads busy
+__device__ __forceinline__ void bwd_block_reduce(const double* red, double* dst, int C, int cv0) {
+    const int TC = blockDim.x, TY = blockDim.y;
+    for (int j = threadIdx.y * TC + threadIdx.x; j < TC * 16; j += TC * TY) {
+        const int lane = j >> 4, stat = (j >> 2) & 3, comp = j & 3;
+        const int ch = (cv0 + lane) * 4 + comp;
+        if (ch >= C) continue;
+        double t = red[j];
+        for (int r = 1; r < TY; ++r) {
+            const double o = red[(size_t)r * TC * 16 + j];
+            t = stat < 2 ? t + o : fmax(t, o);
+        }
+        dst[stat * C + ch] = t;
+    }
+}
+
+// The BN-backward projection dz = scale*(du - mean(du) - xhat*mean(du*xhat)) cancels heavily when du is dominated
+// by its per-channel mean.  The sums are therefore accumulated to double-precision accuracy (compensated fp32 per
+// thread, double across threads), the coefficients are computed in double, and the apply pass subtracts mean(du)
+// as a (hi, lo) float pair: a difference of close floats is exact, so nothing is lost to the cancellation.
+// REDUCE writes per CTA row [sum(du) | sum(du*xhat) | max|du| | max|xhat|] (4C doubles).
+// APPLY writes dz as fp32 and/or directly as the scaled fp16 (hi, lo) planes the tensor-core GEMMs read.
 template <bool APPLY>
 __global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_kernel(const BwdArgs a) {
     const int H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1, Hp = a.H >> 1, Wp = a.W >> 1;
@@ -272,22 +330,30 @@ __global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_kernel(const Bw
     const int c = cv * 4;
     const long long nwin = (long long)a.B * H2 * W2;
 
-    // The BN-backward projection dz = scale*(du - mean(du) - xhat*mean(du*xhat)) cancels heavily when du is
-    // dominated by its per-channel mean; sums, coefficients and the combination are therefore carried in
-    // float64 (as torch's CPU batch_norm_backward does through acc_type<float> = double).
-    float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0), mu = sh, is = sc;
-    double c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};
+    float scv[4] = {1, 1, 1, 1}, shv[4] = {0, 0, 0, 0}, muv[4] = {0, 0, 0, 0}, isv[4] = {1, 1, 1, 1};
+    float c1h[4] = {0, 0, 0, 0}, c1l[4] = {0, 0, 0, 0}, c2f[4] = {0, 0, 0, 0};
     if (cok) {
-        sc = ldg4(a.scale + c);
-        sh = ldg4(a.shift + c);
-        if (a.has_bn) { mu = ldg4(a.mean + c); is = ldg4(a.invstd + c); }
+        const float4 sc = ldg4(a.scale + c), sh = ldg4(a.shift + c);
+        scv[0] = sc.x; scv[1] = sc.y; scv[2] = sc.z; scv[3] = sc.w;
+        shv[0] = sh.x; shv[1] = sh.y; shv[2] = sh.z; shv[3] = sh.w;
+        if (a.has_bn) {
+            const float4 mu = ldg4(a.mean + c), is = ldg4(a.invstd + c);
+            muv[0] = mu.x; muv[1] = mu.y; muv[2] = mu.z; muv[3] = mu.w;
+            isv[0] = is.x; isv[1] = is.y; isv[2] = is.z; isv[3] = is.w;
+        }
         if (APPLY && a.has_bn) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { c1[k] = a.coef[c + k]; c2[k] = a.coef[a.C + c + k]; }
+            for (int k = 0; k < 4; ++k) {
+                const double c1 = a.coef[c + k];
+                c1h[k] = (float)c1;
+                c1l[k] = (float)(c1 - (double)c1h[k]);
+                c2f[k] = (float)a.coef[a.C + c + k];
+            }
         }
     }
-    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-    float amax = 0.f;
+    const float psc = (APPLY && a.dh) ? plane_scale(__ldg(a.amax)) : 1.f;
+    float s1[4] = {0, 0, 0, 0}, e1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, e2[4] = {0, 0, 0, 0};
+    float md[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};
 
     for (unsigned wi = blockIdx.x * blockDim.y + threadIdx.y; cok && wi < (unsigned)nwin; wi += gridDim.x * blockDim.y) {
         const unsigned t = wi / W2;
@@ -305,8 +371,6 @@ __global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_kernel(const Bw
             float4 v = ok[q] ? ldg4(a.z + pix[q] * a.ldz + c) : make_float4(0, 0, 0, 0);
             zv[q][0] = v.x; zv[q][1] = v.y; zv[q][2] = v.z; zv[q][3] = v.w;
         }
-        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-        const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
         float du[4][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -345,60 +409,183 @@ __global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_kernel(const Bw
             float o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float d = du[q][k] * (yv[q][k] > 0.f ? 1.f : a.slope);
-                double xh = ((double)zv[q][k] - (double)muv[k]) * (double)isv[k];
+                const float d = du[q][k] * (yv[q][k] > 0.f ? 1.f : a.slope);
+                const float xh = (zv[q][k] - muv[k]) * isv[k];
                 if (APPLY) {
-                    o[k] = a.has_bn ? (float)((double)scv[k] * ((double)d - c1[k] - xh * c2[k])) : d;
+                    o[k] = a.has_bn ? scv[k] * fmaf(-xh, c2f[k], (d - c1h[k]) - c1l[k]) : d;
                 } else {
-                    s1[k] += (double)d;
-                    s2[k] += (double)d * xh;
+                    kahan_add(s1[k], e1[k], d);
+                    kahan_add(s2[k], e2[k], d * xh);
+                    md[k] = fmaxf(md[k], fabsf(d));
+                    mx[k] = fmaxf(mx[k], fabsf(xh));
                 }
             }
             if (APPLY) {
-                *reinterpret_cast<float4*>(a.dz + pix[q] * a.lddz + c) = make_float4(o[0], o[1], o[2], o[3]);
-                amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
+                const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+                if (a.dz) *reinterpret_cast<float4*>(a.dz + pix[q] * a.lddz + c) = ov;
+                if (a.dh) store_planes4(a.dh, a.dl, pix[q] * a.cpad + c, ov, psc);
             }
         }
     }
 
-    if (APPLY && a.amax_out) {  // absolute maximum of dz (scale of its fp16 planes), one atomic per warp
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-        if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && isfinite(amax) && amax > 0.f)
-            atomicMax(reinterpret_cast<int*>(a.amax_out), __float_as_int(amax));
-    }
     if (!APPLY) {
         // reduce over threadIdx.y -> one partial row per blockIdx.x
-        extern __shared__ double red[];  // [blockDim.y][TC*8]
-        double* mine = red + ((size_t)threadIdx.y * TC + threadIdx.x) * 8;
+        extern __shared__ double red[];  // [blockDim.y][TC*16]
+        double* mine = red + ((size_t)threadIdx.y * TC + threadIdx.x) * 16;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { mine[k] = s1[k]; mine[4 + k] = s2[k]; }
-        __syncthreads();
-        if (threadIdx.y == 0 && cok) {
-            double t1[4] = {0, 0, 0, 0}, t2[4] = {0, 0, 0, 0};
-            for (int r = 0; r < blockDim.y; ++r) {
-                const double* o = red + ((size_t)r * TC + threadIdx.x) * 8;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { t1[k] += o[k]; t2[k] += o[4 + k]; }
-            }
-            double* dst = a.partial + (long long)blockIdx.x * 2 * a.C;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { dst[c + k] = t1[k]; dst[a.C + c + k] = t2[k]; }
+        for (int k = 0; k < 4; ++k) {
+            mine[k] = (double)s1[k] - (double)e1[k];
+            mine[4 + k] = (double)s2[k] - (double)e2[k];
+            mine[8 + k] = (double)md[k];
+            mine[12 + k] = (double)mx[k];
         }
+        __syncthreads();
+        bwd_block_reduce(red, a.partial + (long long)blockIdx.x * 4 * a.C, a.C, blockIdx.y * TC);
     }
 }
 
+// Specialisation for the common block conv + BN + leaky + maxpool whose full-resolution output has no other
+// consumer (only dy_pool exists): du is non-zero only at the arg-max pixel of each 2x2 window, so the reduce pass
+// touches one element per window and channel, and the apply pass needs the activation derivative only there.
+// Same arithmetic as the general kernel (the zero terms are dropped), a fraction of the instructions.
+template <bool APPLY>
+__global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_pool_kernel(const BwdArgs a) {
+    const int H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1, Hp = a.H >> 1, Wp = a.W >> 1;
+    const int C4 = a.C >> 2;
+    const int TC = blockDim.x;          // channel-vector lanes
+    const int cv = blockIdx.y * TC + threadIdx.x;
+    const bool cok = cv < C4;
+    const int c = cv * 4;
+    const unsigned nwin = (unsigned)a.B * H2 * W2;
+
+    float scv[4] = {1, 1, 1, 1}, shv[4] = {0, 0, 0, 0}, muv[4] = {0, 0, 0, 0}, isv[4] = {1, 1, 1, 1};
+    float c1h[4] = {0, 0, 0, 0}, c1l[4] = {0, 0, 0, 0}, c2f[4] = {0, 0, 0, 0}, t0[4] = {0, 0, 0, 0};
+    if (cok) {
+        const float4 sc = ldg4(a.scale + c), sh = ldg4(a.shift + c), mu = ldg4(a.mean + c), is = ldg4(a.invstd + c);
+        scv[0] = sc.x; scv[1] = sc.y; scv[2] = sc.z; scv[3] = sc.w;
+        shv[0] = sh.x; shv[1] = sh.y; shv[2] = sh.z; shv[3] = sh.w;
+        muv[0] = mu.x; muv[1] = mu.y; muv[2] = mu.z; muv[3] = mu.w;
+        isv[0] = is.x; isv[1] = is.y; isv[2] = is.z; isv[3] = is.w;
+        if (APPLY) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double c1 = a.coef[c + k];
+                c1h[k] = (float)c1;
+                c1l[k] = (float)(c1 - (double)c1h[k]);
+                c2f[k] = (float)a.coef[a.C + c + k];
+                t0[k] = (0.f - c1h[k]) - c1l[k];     // du == 0
+            }
+        }
+    }
+    const float psc = (APPLY && a.dh) ? plane_scale(__ldg(a.amax)) : 1.f;
+    const float slope = a.slope;
+    float s1[4] = {0, 0, 0, 0}, e1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, e2[4] = {0, 0, 0, 0};
+    float md[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};
+
+    for (unsigned wi = blockIdx.x * blockDim.y + threadIdx.y; cok && wi < nwin; wi += gridDim.x * blockDim.y) {
+        const unsigned t = wi / W2;
+        const int w2 = (int)(wi - t * W2);
+        const int b = (int)(t / H2);
+        const int h2 = (int)(t - (unsigned)b * H2);
+        const bool whole = h2 < Hp && w2 < Wp;       // windows cut by an odd edge have no pooled output
+        const unsigned p00 = ((unsigned)b * a.H + 2 * h2) * a.W + 2 * w2;
+        float zv[4][4];
+        bool ok[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            ok[q] = whole || ((2 * h2 + (q >> 1) < a.H) && (2 * w2 + (q & 1) < a.W));
+            const unsigned pq = p00 + (q >> 1) * a.W + (q & 1);
+            const float4 v = ok[q] ? ldg4(a.z + (size_t)pq * a.ldz + c) : make_float4(0, 0, 0, 0);
+            zv[q][0] = v.x; zv[q][1] = v.y; zv[q][2] = v.z; zv[q][3] = v.w;
+        }
+        float gv[4] = {0, 0, 0, 0};
+        if (whole) {
+            const unsigned pp = ((unsigned)b * Hp + h2) * Wp + w2;
+            const float4 g = ldg4(a.dyp + (size_t)pp * a.ld_dyp + c);
+            gv[0] = g.x; gv[1] = g.y; gv[2] = g.z; gv[3] = g.w;
+        }
+        float o[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // first maximum of the activated values in scan order (torch max_pool2d: strict >)
+            int best = 0;
+            float yb = fmaf(zv[0][k], scv[k], shv[k]);
+            float vb = fmaxf(yb, yb * slope);        // leaky for 0 <= slope <= 1 (checked by the host)
+            float zb = zv[0][k];
+#pragma unroll
+            for (int q = 1; q < 4; ++q) {
+                const float y = fmaf(zv[q][k], scv[k], shv[k]);
+                const float v = fmaxf(y, y * slope);
+                if (v > vb) { vb = v; yb = y; zb = zv[q][k]; best = q; }
+            }
+            const float d = gv[k] * (yb > 0.f ? 1.f : slope);
+            if (APPLY) {
+                const float tb = (d - c1h[k]) - c1l[k];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float xh = (zv[q][k] - muv[k]) * isv[k];
+                    o[q][k] = scv[k] * fmaf(-xh, c2f[k], (whole && q == best) ? tb : t0[k]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (ok[q]) mx[k] = fmaxf(mx[k], fabsf((zv[q][k] - muv[k]) * isv[k]));
+                if (whole) {
+                    const float xh = (zb - muv[k]) * isv[k];
+                    kahan_add(s1[k], e1[k], d);
+                    kahan_add(s2[k], e2[k], d * xh);
+                    md[k] = fmaxf(md[k], fabsf(d));
+                }
+            }
+        }
+        if (APPLY) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (!ok[q]) continue;
+                const unsigned pq = p00 + (q >> 1) * a.W + (q & 1);
+                const float4 ov = make_float4(o[q][0], o[q][1], o[q][2], o[q][3]);
+                if (a.dz) *reinterpret_cast<float4*>(a.dz + (size_t)pq * a.lddz + c) = ov;
+                if (a.dh) store_planes4(a.dh, a.dl, (long long)pq * a.cpad + c, ov, psc);
+            }
+        }
+    }
+
+    if (!APPLY) {
+        extern __shared__ double red[];  // [blockDim.y][TC*16]
+        double* mine = red + ((size_t)threadIdx.y * TC + threadIdx.x) * 16;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            mine[k] = (double)s1[k] - (double)e1[k];
+            mine[4 + k] = (double)s2[k] - (double)e2[k];
+            mine[8 + k] = (double)md[k];
+            mine[12 + k] = (double)mx[k];
+        }
+        __syncthreads();
+        bwd_block_reduce(red, a.partial + (long long)blockIdx.x * 4 * a.C, a.C, blockIdx.y * TC);
+    }
+}
+
+// sums row [4C] -> dgamma, dbeta, the projection coefficients, and an upper bound of max|dz| (the scale of dz's fp16
+// planes): |dz| <= |scale| * (max|du| + |c1| + max|xhat| * |c2|)
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
                                        const float* __restrict__ invstd, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, double* __restrict__ coef, int C, int has_bn) {
+                                       float* __restrict__ dbeta, double* __restrict__ coef, float* __restrict__ amax_bound,
+                                       int C, int has_bn) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double sdu = sums[c], sdux = sums[C + c];
+    double bound = sums[2 * C + c];
     if (dbeta) dbeta[c] = (float)sdu;
     if (has_bn) {
         if (dgamma) dgamma[c] = (float)sdux;
-        coef[c] = sdu / count;
-        coef[C + c] = sdux / count;
+        const double c1 = sdu / count, c2 = sdux / count;
+        coef[c] = c1;
+        coef[C + c] = c2;
+        bound = fabs((double)gamma[c] * (double)invstd[c]) * (bound + fabs(c1) + sums[3 * C + c] * fabs(c2));
+    }
+    if (amax_bound) {
+        const float bf = (float)(bound * 1.0001);
+        if (isfinite(bf) && bf > 0.f) atomicMax(reinterpret_cast<int*>(amax_bound), __float_as_int(bf));
     }
 }
 
@@ -476,24 +663,31 @@ extern "C" int fsdet_bn_act_fwd(const float* z, int ldz, const float* scale, con
         if (n == 0) return 0;
         bn_act_flat_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a);
     } else {
-        long long n = (long long)B * ((H + 1) / 2) * ((W + 1) / 2) * CP4;
-        if (n == 0) return 0;
-        bn_act_pool_kernel<<<ceil_div(n, 256), 256, 0, s>>>(a);
+        long long nwin = (long long)B * ((H + 1) / 2) * ((W + 1) / 2);
+        if (nwin == 0) return 0;
+        const int TC = CP4 >= 32 ? 32 : (CP4 >= 16 ? 16 : (CP4 >= 8 ? 8 : (CP4 >= 4 ? 4 : (CP4 >= 2 ? 2 : 1))));
+        const int TY = 256 / TC;
+        dim3 block(TC, TY), grid((unsigned)ceil_div(nwin, TY));
+        if (a.yf || a.fh) bn_act_pool_kernel<true><<<grid, block, 0, s>>>(a);
+        else bn_act_pool_kernel<false><<<grid, block, 0, s>>>(a);
     }
     return launch_status("bn_act_fwd");
 }
 
 static int launch_bwd(bool apply, const BwdArgs& a, cudaStream_t s) {
-    FSDET_CHECK_ARG((long long)a.B * a.H * a.W < (1ll << 31), "bn_act_bwd: tensor too large for 32-bit indexing");
+    FSDET_CHECK_ARG((long long)a.B * a.H * a.W < (1ll << 31), "bn_act_bwd: tensor too large for 32-bit pixel indexing");
     int C4 = a.C / 4;
     int TC = C4 >= 32 ? 32 : (C4 >= 16 ? 16 : (C4 >= 8 ? 8 : (C4 >= 4 ? 4 : (C4 >= 2 ? 2 : 1))));
     int TY = 256 / TC;
     dim3 block(TC, TY), grid(bwd_rows(a.B, a.H, a.W), ceil_div(C4, TC));
-    if (apply) {
-        bn_act_bwd_kernel<true><<<grid, block, 0, s>>>(a);
+    const size_t smem = (size_t)TY * TC * 16 * sizeof(double);  // 32 KB (reduce pass)
+    const bool pool_only = !a.dyf && a.dyp && a.has_bn && a.slope >= 0.f && a.slope <= 1.f;
+    if (pool_only) {
+        if (apply) bn_act_bwd_pool_kernel<true><<<grid, block, 0, s>>>(a);
+        else bn_act_bwd_pool_kernel<false><<<grid, block, smem, s>>>(a);
     } else {
-        size_t smem = (size_t)TY * TC * 8 * sizeof(double);  // 16 KB
-        bn_act_bwd_kernel<false><<<grid, block, smem, s>>>(a);
+        if (apply) bn_act_bwd_kernel<true><<<grid, block, 0, s>>>(a);
+        else bn_act_bwd_kernel<false><<<grid, block, smem, s>>>(a);
     }
     return launch_status(apply ? "bn_act_bwd_apply" : "bn_act_bwd_reduce");
 }
@@ -507,40 +701,44 @@ extern "C" int fsdet_bn_act_bwd_reduce(const float* z, int ldz, const float* dy_
     FSDET_CHECK_ARG(C % 4 == 0 && ldz % 4 == 0 && ld_dyf % 4 == 0 && ld_dyp % 4 == 0, "bn_act_bwd_reduce: alignment");
     BwdArgs a;
     a.z = z; a.dyf = dy_full; a.dyp = dy_pool; a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd;
-    a.coef = nullptr; a.dz = nullptr; a.amax_out = nullptr; a.partial = partial; a.ldz = ldz; a.ld_dyf = ld_dyf; a.ld_dyp = ld_dyp; a.lddz = 0;
+    a.coef = nullptr; a.dz = nullptr; a.dh = nullptr; a.dl = nullptr; a.amax = nullptr; a.partial = partial;
+    a.ldz = ldz; a.ld_dyf = ld_dyf; a.ld_dyp = ld_dyp; a.lddz = 0; a.cpad = 0;
     a.B = B; a.H = H; a.W = W; a.C = C; a.slope = slope; a.has_bn = has_bn;
     return launch_bwd(false, a, (cudaStream_t)stream);
 }
 
 extern "C" int fsdet_bn_bwd_finalize(const double* partial, int nparts, double count, const float* gamma,
-                                     const float* invstd, float* dgamma, float* dbeta, double* coef, int C, int has_bn,
-                                     void* stream) {
-    FSDET_CHECK_ARG(partial && nparts > 0 && C > 0 && (!has_bn || coef), "bn_bwd_finalize: bad args");
+                                     const float* invstd, float* dgamma, float* dbeta, double* coef, float* amax_bound,
+                                     int C, int has_bn, void* stream) {
+    FSDET_CHECK_ARG(partial && nparts > 0 && C > 0 && (!has_bn || (coef && gamma && invstd)), "bn_bwd_finalize: bad args");
     cudaStream_t s = (cudaStream_t)stream;
-    double* sums = const_cast<double*>(partial) + (size_t)nparts * 2 * C;  // the extra row
-    dim3 block(32, 32), grid(ceil_div(2 * C, 32));
-    colsum_dd_kernel<<<grid, block, 0, s>>>(partial, nparts, 2 * C, sums);
+    double* sums = const_cast<double*>(partial) + (size_t)nparts * 4 * C;  // the extra row
+    dim3 block(32, 32), grid(ceil_div(4 * C, 32));
+    colsum_dd_kernel<<<grid, block, 0, s>>>(partial, nparts, 4 * C, 2 * C, sums);
     int st = launch_status("bn_bwd_finalize/colsum");
     if (st) return st;
-    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(sums, count, gamma, invstd, dgamma, dbeta, coef, C, has_bn);
+    if (amax_bound) {
+        cudaError_t e = cudaMemsetAsync(amax_bound, 0, sizeof(float), s);
+        if (e != cudaSuccess) { set_error("bn_bwd_finalize: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(sums, count, gamma, invstd, dgamma, dbeta, coef, amax_bound, C, has_bn);
     return launch_status("bn_bwd_finalize");
 }
 
 extern "C" int fsdet_bn_act_bwd_apply(const float* z, int ldz, const float* dy_full, int ld_dyf, const float* dy_pool,
                                       int ld_dyp, const float* scale, const float* shift, const float* mean,
                                       const float* invstd, const double* coef, float slope, float* dz, int lddz,
-                                      float* amax_out, int B, int H, int W, int C, int has_bn, void* stream) {
-    FSDET_CHECK_ARG(z && scale && shift && dz && (dy_full || dy_pool), "bn_act_bwd_apply: null pointer");
+                                      void* dz_hi, void* dz_lo, int cpad, const float* amax, int B, int H, int W, int C,
+                                      int has_bn, void* stream) {
+    FSDET_CHECK_ARG(z && scale && shift && (dz || dz_hi) && (dy_full || dy_pool), "bn_act_bwd_apply: null pointer");
     FSDET_CHECK_ARG(!has_bn || (mean && invstd && coef), "bn_act_bwd_apply: BN needs mean/invstd/coef");
     FSDET_CHECK_ARG(C % 4 == 0 && ldz % 4 == 0 && ld_dyf % 4 == 0 && ld_dyp % 4 == 0 && lddz % 4 == 0,
                     "bn_act_bwd_apply: alignment");
+    FSDET_CHECK_ARG(!dz_hi || (dz_lo && amax && cpad == C), "bn_act_bwd_apply: planes need lo, amax and cpad == C (%d vs %d)", cpad, C);
     BwdArgs a;
     a.z = z; a.dyf = dy_full; a.dyp = dy_pool; a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd;
-    a.coef = coef; a.dz = dz; a.amax_out = amax_out; a.partial = nullptr; a.ldz = ldz; a.ld_dyf = ld_dyf; a.ld_dyp = ld_dyp; a.lddz = lddz;
+    a.coef = coef; a.dz = dz; a.dh = (__half*)dz_hi; a.dl = (__half*)dz_lo; a.amax = amax; a.partial = nullptr;
+    a.ldz = ldz; a.ld_dyf = ld_dyf; a.ld_dyp = ld_dyp; a.lddz = lddz; a.cpad = cpad;
     a.B = B; a.H = H; a.W = W; a.C = C; a.slope = slope; a.has_bn = has_bn;
-    if (amax_out) {
-        cudaError_t e = cudaMemsetAsync(amax_out, 0, sizeof(float), (cudaStream_t)stream);
-        if (e != cudaSuccess) { set_error("bn_act_bwd_apply: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    }
     return launch_bwd(true, a, (cudaStream_t)stream);
 }

@@ -433,153 +433,290 @@ __device__ __forceinline__ float in_px(const float* __restrict__ in0, int C0, co
     return 0.f;
 }
 
-// forward: lane = output channel (its 9x4 filter lives in registers), one warp walks along an image row keeping the
-// 3x3 input window in registers (3 broadcast shared-memory loads + 36 FMAs per pixel, one coalesced 128-byte store).
-// CTA tile = FT_H rows (one per warp) x FT_W columns.
-constexpr int FT_H = 8, FT_W = 104;
-__global__ void __launch_bounds__(256) conv_first_fwd_kernel(const float* __restrict__ in0, int C0, const float* __restrict__ in1,
-                                                             int C1, const float* __restrict__ w /* [Cout][9][4] */,
-                                                             float* __restrict__ z, int ldz, int B, int H, int W, int Cout) {
-    __shared__ float4 xs[FT_H + 2][FT_W + 2];
+// packed fp32 pairs: FFMA2 (fma.rn.f32x2) issues two IEEE fp32 FMAs per lane from one instruction slot, each half
+// rounding exactly like fmaf()
+typedef unsigned long long f32x2;
+__device__ __forceinline__ void fma2(f32x2& acc, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b)); }
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+// pair arithmetic in two flavours (same rounding): packed FFMA2 or two scalar FFMAs
+template <bool PACKED> struct Pair;
+template <> struct Pair<true> {
+    f32x2 v;
+    __device__ __forceinline__ static Pair make(float lo, float hi) { Pair p; p.v = pack2(lo, hi); return p; }
+    __device__ __forceinline__ static Pair raw(f32x2 bits) { Pair p; p.v = bits; return p; }
+    __device__ __forceinline__ void fma(const Pair& a, const Pair& b) { fma2(v, a.v, b.v); }
+    __device__ __forceinline__ float2 get() const { return unpack2(v); }
+};
+template <> struct Pair<false> {
+    float2 v;
+    __device__ __forceinline__ static Pair make(float lo, float hi) { Pair p; p.v = make_float2(lo, hi); return p; }
+    __device__ __forceinline__ static Pair raw(f32x2 bits) { Pair p; p.v = unpack2(bits); return p; }
+    __device__ __forceinline__ void fma(const Pair& a, const Pair& b) { v.x = fmaf(a.v.x, b.v.x, v.x); v.y = fmaf(a.v.y, b.v.y, v.y); }
+    __device__ __forceinline__ float2 get() const { return v; }
+};
+
+__device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const float* src, bool valid) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const float* src, bool valid) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// forward: lane = output channel (its 9x4 filter lives in registers as pairs), one warp walks along an image row
+// keeping the 3x3 input window in registers (3 broadcast shared-memory loads + 36 FMAs per pixel, one coalesced
+// 128-byte store).  The walk is unrolled by three so the window rotates by renaming, not by moves.  Persistent CTAs
+// (two per SM) loop over tiles of FT_H rows (one per warp) x FT_W columns; the next tile's input is fetched with
+// asynchronous copies into the other half of a double buffer while the current one is being computed.
+constexpr int FT_H = 8, FT_W = 104, FT_NPX = (FT_H + 2) * (FT_W + 2);
+template <bool PK> struct Px4 { Pair<PK> lo, hi; };   // one pixel: channels (0,1) and (2,3)
+template <bool PK> __device__ __forceinline__ Px4<PK> lds_px(const float4* p) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+    Px4<PK> r; r.lo = Pair<PK>::raw(v.x); r.hi = Pair<PK>::raw(v.y);
+    return r;
+}
+template <bool PK>
+__global__ void __launch_bounds__(256, 2) conv_first_fwd_kernel(const float* __restrict__ in0, int C0, const float* __restrict__ in1,
+                                                                int C1, const float* __restrict__ w /* [Cout][9][4] */,
+                                                                float* __restrict__ z, int ldz, int B, int H, int W, int Cout) {
+    __shared__ float4 xs[2][FT_NPX];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_w = (W + FT_W - 1) / FT_W, tiles_h = (H + FT_H - 1) / FT_H;
-    int t = blockIdx.x;
-    const int tw = t % tiles_w; t /= tiles_w;
-    const int th = t % tiles_h;
-    const int b = t / tiles_h;
-    const int h0 = th * FT_H, w0 = tw * FT_W;
-    // stage the input tile (+halo) channel plane by channel plane: one 32-bit-indexed load per element, batches of
-    // 4 independent loads per thread for memory-level parallelism
-    constexpr int NPX = (FT_H + 2) * (FT_W + 2);
+    const int tiles = B * tiles_h * tiles_w;
     const int HW = H * W;
-    float* xsf = reinterpret_cast<float*>(&xs[0][0]);
+    // input tile (+halo) of tile t, channel plane by channel plane, 4-byte async copies (zero fill outside the image)
+    auto stage = [&](int t, int buf) {
+        const int tw = t % tiles_w; t /= tiles_w;
+        const int th = t % tiles_h;
+        const int b = t / tiles_h;
+        const int h0 = th * FT_H, w0 = tw * FT_W;
+        // warp = tile row (two passes cover the FT_H + 2 rows), lane + 32 j = tile column
+        bool cok_[4];
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-        const float* plane = ch < C0 ? in0 + ((long long)b * C0 + ch) * HW
-                                     : (ch < C0 + C1 ? in1 + ((long long)b * C1 + (ch - C0)) * HW : nullptr);
-        for (int base = 0; base < NPX; base += 4 * 256) {
-            float v[4];
+        for (int j = 0; j < 4; ++j) {
+            const int c = lane + 32 * j, ww = w0 + c - 1;
+            cok_[j] = c < FT_W + 2 && ww >= 0 && ww < W;
+        }
+        for (int r = warp; r < FT_H + 2; r += 8) {
+            const int h = h0 + r - 1;
+            const bool rok = h >= 0 && h < H;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&xs[buf][r * (FT_W + 2) + lane]);
+            const long long off = (long long)(rok ? h : 0) * W + (w0 - 1 + lane);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = base + u * 256 + tid;
-                const int r = i / (FT_W + 2), c = i - r * (FT_W + 2);
-                const int h = h0 + r - 1, ww = w0 + c - 1;
-                v[u] = (plane && i < NPX && h >= 0 && h < H && ww >= 0 && ww < W) ? __ldg(plane + h * W + ww) : 0.f;
-            }
+            for (int ch = 0; ch < 4; ++ch) {
+                const float* plane = ch < C0 ? in0 + ((long long)b * C0 + ch) * HW
+                                             : (ch < C0 + C1 ? in1 + ((long long)b * C1 + (ch - C0)) * HW : nullptr);
+                const bool pok = rok && plane != nullptr;
+                const float* src = pok ? plane + off : in0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = base + u * 256 + tid;
-                if (i < NPX) xsf[i * 4 + ch] = v[u];
+                for (int j = 0; j < 4; ++j) {
+                    if (lane + 32 * j < FT_W + 2) {
+                        const bool ok = pok && cok_[j];
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (32 * j * 4 + ch) * 4),
+                                     "l"(ok ? src + 32 * j : in0), "r"(ok ? 4 : 0) : "memory");
+                    }
+                }
             }
         }
-    }
-    float4 wr[9];
+    };
+    Px4<PK> wr[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) wr[k] = lane < Cout ? ldg4(w + (lane * 9 + k) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    const int h = h0 + warp;
-    if (h >= H) return;
-    const int wn = min(FT_W, W - w0);
-    float4 x00 = xs[warp][0], x01 = xs[warp][1], x10 = xs[warp + 1][0], x11 = xs[warp + 1][1], x20 = xs[warp + 2][0], x21 = xs[warp + 2][1];
-    float* zr = z + (((long long)b * H + h) * W + w0) * ldz + lane;
-#pragma unroll 2
-    for (int c = 0; c < wn; ++c) {
-        const float4 x02 = xs[warp][c + 2], x12 = xs[warp + 1][c + 2], x22 = xs[warp + 2][c + 2];
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent FMA chains (one per input channel)
-#define FSDET_TAP(X, Wv) a0 = fmaf(X.x, Wv.x, a0); a1 = fmaf(X.y, Wv.y, a1); a2 = fmaf(X.z, Wv.z, a2); a3 = fmaf(X.w, Wv.w, a3);
-        FSDET_TAP(x00, wr[0]) FSDET_TAP(x01, wr[1]) FSDET_TAP(x02, wr[2])
-        FSDET_TAP(x10, wr[3]) FSDET_TAP(x11, wr[4]) FSDET_TAP(x12, wr[5])
-        FSDET_TAP(x20, wr[6]) FSDET_TAP(x21, wr[7]) FSDET_TAP(x22, wr[8])
+    for (int k = 0; k < 9; ++k) {
+        const float4 v = lane < Cout ? ldg4(w + (lane * 9 + k) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wr[k].lo = Pair<PK>::make(v.x, v.y); wr[k].hi = Pair<PK>::make(v.z, v.w);
+    }
+    const bool cok = lane < Cout;
+    int buf = 0;
+    if ((int)blockIdx.x < tiles) stage(blockIdx.x, 0);
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, buf ^= 1) {
+        cp_async_wait_all();
+        __syncthreads();            // tile t has landed; everyone is done with the other buffer
+        if (t + (int)gridDim.x < tiles) stage(t + gridDim.x, buf ^ 1);
+        int tt = t;
+        const int tw = tt % tiles_w; tt /= tiles_w;
+        const int th = tt % tiles_h;
+        const int b = tt / tiles_h;
+        const int h = th * FT_H + warp, w0 = tw * FT_W;
+        if (h >= H) continue;
+        const int wn = min(FT_W, W - w0);
+        const float4* r0 = &xs[buf][warp * (FT_W + 2)];
+        const float4* r1 = r0 + (FT_W + 2);
+        const float4* r2 = r1 + (FT_W + 2);
+        float* zr = z + (((long long)b * H + h) * W + w0) * ldz + lane;
+        // window columns: P = c, Q = c + 1, R = c + 2 (rows 0..2)
+        Px4<PK> p0 = lds_px<PK>(r0), p1 = lds_px<PK>(r1), p2 = lds_px<PK>(r2);
+        Px4<PK> q0 = lds_px<PK>(r0 + 1), q1 = lds_px<PK>(r1 + 1), q2 = lds_px<PK>(r2 + 1);
+        Px4<PK> s0, s1, s2;
+#define FSDET_TAP(X, K) alo.fma(X.lo, wr[K].lo); ahi.fma(X.hi, wr[K].hi);
+#define FSDET_PIXEL(A0, A1, A2, B0, B1, B2, C0_, C1_, C2_, COL)                                           \
+    {                                                                                                     \
+        C0_ = lds_px<PK>(r0 + (COL) + 2); C1_ = lds_px<PK>(r1 + (COL) + 2); C2_ = lds_px<PK>(r2 + (COL) + 2); \
+        Pair<PK> alo = Pair<PK>::make(0.f, 0.f), ahi = alo;   /* one accumulator per input channel */      \
+        FSDET_TAP(A0, 0) FSDET_TAP(B0, 1) FSDET_TAP(C0_, 2)                                                \
+        FSDET_TAP(A1, 3) FSDET_TAP(B1, 4) FSDET_TAP(C1_, 5)                                                \
+        FSDET_TAP(A2, 6) FSDET_TAP(B2, 7) FSDET_TAP(C2_, 8)                                                \
+        const float2 l = alo.get(), u = ahi.get();                                                        \
+        if (cok) *zr = (l.x + l.y) + (u.x + u.y);                                                         \
+        zr += ldz;                                                                                        \
+    }
+        int c = 0;
+#pragma unroll 1
+        for (; c + 3 <= wn; c += 3) {
+            FSDET_PIXEL(p0, p1, p2, q0, q1, q2, s0, s1, s2, c)
+            FSDET_PIXEL(q0, q1, q2, s0, s1, s2, p0, p1, p2, c + 1)
+            FSDET_PIXEL(s0, s1, s2, p0, p1, p2, q0, q1, q2, c + 2)
+        }
+        if (c < wn) {
+            FSDET_PIXEL(p0, p1, p2, q0, q1, q2, s0, s1, s2, c)
+            if (c + 1 < wn) FSDET_PIXEL(q0, q1, q2, s0, s1, s2, p0, p1, p2, c + 1)
+        }
+#undef FSDET_PIXEL
 #undef FSDET_TAP
-        if (lane < Cout) zr[(long long)c * ldz] = (a0 + a1) + (a2 + a3);
-        x00 = x01; x01 = x02; x10 = x11; x11 = x12; x20 = x21; x21 = x22;
     }
 }
 
-// weight gradient: dw[co][tap][ci] = sum_p dz[p][co] * x[p+tap][ci].  One CTA walks image rows: the dz row and the
-// three x rows it needs are staged in shared memory.  Thread (co, filter row ty, column segment) keeps the 3 taps of
-// its filter row x 4 input channels in registers and slides a 3-pixel window along its third of the image row
-// (one new x pixel + one dz value per step feed 12 FMAs); partials are reduced in a fixed order afterwards.
-constexpr int FW_SEG = 3;   // column segments per row (thread groups)
-__global__ void __launch_bounds__(288) conv_first_wgrad_kernel(const float* __restrict__ in0, int C0, const float* __restrict__ in1,
-                                                               int C1, const float* __restrict__ dz, int lddz,
-                                                               float* __restrict__ part, int B, int H, int W, int Cout) {
+// weight gradient: dw[co][tap][ci] = sum_p dz[p][co] * x[p+tap][ci].  One persistent CTA per SM walks a contiguous
+// run of image rows.  The dz row is double buffered and the x rows live in a 6-slot ring in shared memory (one new
+// x row per step, three at an image boundary); the next row is fetched with asynchronous copies while the current
+// one is computed.  Thread (co, filter row ty, column segment) keeps the 3 taps of its filter row x 4 input channels
+// in registers and slides a 3-pixel window along its segment of the image row (one new x pixel + one dz value per
+// step feed 12 FMAs); partials are reduced in a fixed order afterwards.
+constexpr int FW_SEG = 6;                       // column segments per row (thread groups)
+constexpr int FW_THREADS = 32 * 3 * FW_SEG;
+constexpr int FW_SLOTS = 6;
+template <bool PK>
+__global__ void __launch_bounds__(FW_THREADS, 1) conv_first_wgrad_kernel(const float* __restrict__ in0, int C0,
+                                                                         const float* __restrict__ in1, int C1,
+                                                                         const float* __restrict__ dz, int lddz,
+                                                                         float* __restrict__ part, int B, int H, int W, int Cout) {
     extern __shared__ __align__(16) float sm[];
-    float4* xs = reinterpret_cast<float4*>(sm);              // [3][W + 2] pixels of 4 channels (zero halo)
-    float* ds = sm + 3 * (W + 2) * 4;                        // [W][32]
+    float4* xs = reinterpret_cast<float4*>(sm);              // [FW_SLOTS][W + 2] pixels of 4 channels (zero halo)
+    float* ds = sm + FW_SLOTS * (W + 2) * 4;                 // [2][W][32]
     const int tid = threadIdx.x;
     const int co = tid & 31;
     const int ty = (tid >> 5) % 3;                           // filter row
     const int seg = (tid >> 5) / 3;                          // column segment 0..FW_SEG-1
     const int wseg = (W + FW_SEG - 1) / FW_SEG;
     const int wbeg = seg * wseg, wend = min(W, wbeg + wseg);
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;   // taps (ty, 0), (ty, 1), (ty, 2)
+    const int HW = H * W;
+    Pair<PK> acc[3][2];                                      // taps (ty, 0..2) x channel pairs
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc[i][0] = acc[i][1] = Pair<PK>::make(0.f, 0.f);
     const long long rows = (long long)B * H;
-    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const long long per = (rows + gridDim.x - 1) / gridDim.x;
+    const long long rbeg = (long long)blockIdx.x * per, rend = min(rows, rbeg + per);
+    // ring state of the most recently staged row: x rows have_h-1 .. have_h+1 of image have_b sit in slots win..win+2
+    int have_b = -1, have_h = -2, win = 0;
+    auto stage = [&](long long row, int buf) {
         const int b = (int)(row / H), h = (int)(row - (long long)b * H);
-        __syncthreads();
-        // staging, channel plane by channel plane, in batches of 4 independent loads per thread
-        {
-            const int HW = H * W, NX = 3 * (W + 2);
-            float* xsf = reinterpret_cast<float*>(xs);
+        const bool step = (b == have_b && h == have_h + 1);
+        const int nnew = step ? 1 : 3;
+        win = (win + nnew) % FW_SLOTS;                       // step: window slides by one; else a fresh window
+        for (int c = tid; c < W + 2; c += FW_THREADS) {      // x rows: thread = column (one pass unless W + 2 > FW_THREADS)
+            const bool cok_ = c >= 1 && c <= W;
+            for (int k = 3 - nnew; k < 3; ++k) {
+                const int q = h - 1 + k;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(xs + ((win + k) % FW_SLOTS) * (W + 2) + c);
+                const bool ok = cok_ && q >= 0 && q < H;
+                const long long off = (long long)(ok ? q : 0) * W + (c - 1);
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                const float* plane = ch < C0 ? in0 + ((long long)b * C0 + ch) * HW
-                                             : (ch < C0 + C1 ? in1 + ((long long)b * C1 + (ch - C0)) * HW : nullptr);
-                for (int base = 0; base < NX; base += 4 * 288) {
-                    float v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = base + u * 288 + tid;
-                        const int r = i / (W + 2), c = i - r * (W + 2);
-                        const int hh = h + r - 1, ww = c - 1;
-                        v[u] = (plane && i < NX && hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(plane + hh * W + ww) : 0.f;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = base + u * 288 + tid;
-                        if (i < NX) xsf[i * 4 + ch] = v[u];
-                    }
+                for (int ch = 0; ch < 4; ++ch) {
+                    const float* plane = ch < C0 ? in0 + ((long long)b * C0 + ch) * HW
+                                                 : (ch < C0 + C1 ? in1 + ((long long)b * C1 + (ch - C0)) * HW : nullptr);
+                    const bool okc = ok && plane != nullptr;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + ch * 4), "l"(okc ? plane + off : in0),
+                                 "r"(okc ? 4 : 0) : "memory");
                 }
             }
         }
-        const float* drow = dz + (row * W) * lddz;
-        for (int base = 0; base < W * 8; base += 6 * 288) {  // 8 float4 per pixel (32 channels, zero beyond Cout)
-            float4 v[6];
-#pragma unroll
-            for (int u = 0; u < 6; ++u) {
-                const int i = base + u * 288 + tid;
-                const int pw = i >> 3, c4 = (i & 7) * 4;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < W * 8 && c4 < Cout) v[u] = ldg4(drow + (long long)pw * lddz + c4);
-            }
-#pragma unroll
-            for (int u = 0; u < 6; ++u) {
-                const int i = base + u * 288 + tid;
-                if (i < W * 8) *reinterpret_cast<float4*>(ds + (i >> 3) * 32 + (i & 7) * 4) = v[u];
-            }
+        have_b = b; have_h = h;
+        // dz row: FW_THREADS is a multiple of 8, so a thread keeps its channel quad and strides over pixels
+        {
+            const int c4 = (tid & 7) * 4, pstep = FW_THREADS / 8;
+            const bool ok = c4 < Cout;
+            const float* src = dz + (row * W + (tid >> 3)) * lddz + c4;
+            unsigned dst = (unsigned)__cvta_generic_to_shared(ds + buf * W * 32 + tid * 4);
+            const long long sstep = (long long)pstep * lddz;
+            for (int pw = tid >> 3; pw < W; pw += pstep, src += sstep, dst += FW_THREADS * 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(ok ? src : dz), "r"(ok ? 16 : 0) : "memory");
         }
-        __syncthreads();
-        const float4* xr = xs + ty * (W + 2);                // xr[w + tx] = x[h + ty - 1][w + tx - 1]
+    };
+    if (rbeg < rend) stage(rbeg, 0);
+    int buf = 0;
+    for (long long row = rbeg; row < rend; ++row, buf ^= 1) {
+        cp_async_wait_all();
+        __syncthreads();            // this row has landed; everyone is done with the previous one
+        const int wcur = win;
+        if (row + 1 < rend) stage(row + 1, buf ^ 1);
+        const float4* xr = xs + ((wcur + ty) % FW_SLOTS) * (W + 2);   // image row h + ty - 1;  xr[w + tx] = x[.][w + tx - 1]
+        const float* dcur = ds + buf * W * 32 + co;
         if (wbeg < wend) {
-            float4 x0 = xr[wbeg], x1 = xr[wbeg + 1];
-#pragma unroll 4
-            for (int w = wbeg; w < wend; ++w) {
-                const float4 x2 = xr[w + 2];
-                const float d = ds[w * 32 + co];
-                a0.x = fmaf(d, x0.x, a0.x); a0.y = fmaf(d, x0.y, a0.y); a0.z = fmaf(d, x0.z, a0.z); a0.w = fmaf(d, x0.w, a0.w);
-                a1.x = fmaf(d, x1.x, a1.x); a1.y = fmaf(d, x1.y, a1.y); a1.z = fmaf(d, x1.z, a1.z); a1.w = fmaf(d, x1.w, a1.w);
-                a2.x = fmaf(d, x2.x, a2.x); a2.y = fmaf(d, x2.y, a2.y); a2.z = fmaf(d, x2.z, a2.z); a2.w = fmaf(d, x2.w, a2.w);
-                x0 = x1; x1 = x2;
+            Px4<PK> x0 = lds_px<PK>(xr + wbeg), x1 = lds_px<PK>(xr + wbeg + 1), x2;
+#define FSDET_STEP(X0, X1, X2, WW)                                                               \
+    {                                                                                            \
+        X2 = lds_px<PK>(xr + (WW) + 2);                                                          \
+        const float d = dcur[(WW) * 32];                                                         \
+        const Pair<PK> dd = Pair<PK>::make(d, d);                                                \
+        acc[0][0].fma(dd, X0.lo); acc[0][1].fma(dd, X0.hi);                                      \
+        acc[1][0].fma(dd, X1.lo); acc[1][1].fma(dd, X1.hi);                                      \
+        acc[2][0].fma(dd, X2.lo); acc[2][1].fma(dd, X2.hi);                                      \
+    }
+            int w = wbeg;
+#pragma unroll 1
+            for (; w + 3 <= wend; w += 3) {
+                FSDET_STEP(x0, x1, x2, w)
+                FSDET_STEP(x1, x2, x0, w + 1)
+                FSDET_STEP(x2, x0, x1, w + 2)
             }
+            if (w < wend) {
+                FSDET_STEP(x0, x1, x2, w)
+                if (w + 1 < wend) FSDET_STEP(x1, x2, x0, w + 1)
+            }
+#undef FSDET_STEP
         }
     }
     if (co < Cout) {
         float* dst = part + (((long long)blockIdx.x * FW_SEG + seg) * Cout + co) * 36 + ty * 12;
-        *reinterpret_cast<float4*>(dst) = a0;
-        *reinterpret_cast<float4*>(dst + 4) = a1;
-        *reinterpret_cast<float4*>(dst + 8) = a2;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float2 l = acc[i][0].get(), u = acc[i][1].get();
+            *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(l.x, l.y, u.x, u.y);
+        }
     }
+}
+
+// fixed-order reduction of the first-layer partials: one CTA per float4 of dw, threads stride over the partials,
+// then a shared-memory tree
+__global__ void __launch_bounds__(128) first_wgrad_reduce_kernel(const float4* __restrict__ ws, float4* __restrict__ out, int n4,
+                                                                 int parts) {
+    __shared__ float4 red[128];
+    const int i = blockIdx.x;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = threadIdx.x; k < parts; k += 128) {
+        const float4 v = ws[(long long)k * n4 + i];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const float4 a = red[threadIdx.x], b = red[threadIdx.x + o];
+            red[threadIdx.x] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[i] = red[0];
 }
 
 static int wgrad_splits(long long M, int Cin, int Cout, int ks, int bmc) {
@@ -687,7 +824,7 @@ extern "C" int fsdet_pad_channels(const float* in, int cin, float* out, int cout
 
 static int first_wgrad_ctas(int B, int H) {
     long long rows = (long long)B * H;
-    long long n = 3LL * kNumSMs;
+    long long n = kNumSMs;
     return (int)(rows < n ? rows : n);
 }
 
@@ -704,7 +841,9 @@ extern "C" int fsdet_conv_first_fwd(const float* in0, int C0, const float* in1, 
     long long tiles = (long long)B * ceil_div(H, FT_H) * ceil_div(W, FT_W);
     if (tiles == 0) return 0;
     FSDET_CHECK_ARG(tiles < (1ll << 31), "conv_first_fwd: too many tiles");
-    conv_first_fwd_kernel<<<(unsigned)tiles, 256, 0, (cudaStream_t)stream>>>(in0, C0, in1, C1, w_pad4, z, ldz, B, H, W, Cout);
+    const unsigned ctas = (unsigned)(tiles < 2LL * kNumSMs ? tiles : 2LL * kNumSMs);
+    // packed FFMA2 flavour: fewer issue slots per pixel (measured 705 us vs 750 us at B=64, 416x416)
+    conv_first_fwd_kernel<true><<<ctas, 256, 0, (cudaStream_t)stream>>>(in0, C0, in1, C1, w_pad4, z, ldz, B, H, W, Cout);
     return launch_status("conv_first_fwd");
 }
 
@@ -717,20 +856,21 @@ extern "C" int fsdet_conv_first_wgrad(const float* in0, int C0, const float* in1
     const int ctas = first_wgrad_ctas(B, H);
     FSDET_CHECK_ARG(workspace_floats >= (size_t)ctas * FW_SEG * Cout * 36, "conv_first_wgrad: workspace too small");
     if (ctas == 0) return 0;
-    const size_t smem = ((size_t)3 * (W + 2) * 4 + (size_t)W * 32) * sizeof(float);
-    FSDET_CHECK_ARG(smem <= 200 * 1024, "conv_first_wgrad: image width %d too large", W);
+    const size_t smem = ((size_t)FW_SLOTS * (W + 2) * 4 + (size_t)2 * W * 32) * sizeof(float);
+    FSDET_CHECK_ARG(smem <= 227 * 1024, "conv_first_wgrad: image width %d too large", W);
     cudaStream_t s = (cudaStream_t)stream;
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_first_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_first_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("conv_first_wgrad: %s", cudaGetErrorString(e)); return (int)e; }
         smem_set = smem;
     }
-    conv_first_wgrad_kernel<<<ctas, 288, smem, s>>>(in0, C0, in1, C1, dz, lddz, workspace, B, H, W, Cout);
+    // scalar FFMA flavour (the packed one is register-bandwidth bound here: 900 us vs 873 us)
+    conv_first_wgrad_kernel<false><<<ctas, FW_THREADS, smem, s>>>(in0, C0, in1, C1, dz, lddz, workspace, B, H, W, Cout);
     int st = launch_status("conv_first_wgrad");
     if (st) return st;
     long long n4 = (long long)Cout * 36 / 4;
-    splitk_reduce_kernel<<<ceil_div(n4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(workspace), reinterpret_cast<float4*>(dw),
-                                                          n4, ctas * FW_SEG);
+    first_wgrad_reduce_kernel<<<(unsigned)n4, 128, 0, s>>>(reinterpret_cast<const float4*>(workspace), reinterpret_cast<float4*>(dw),
+                                                           (int)n4, ctas * FW_SEG);
     return launch_status("conv_first_wgrad_reduce");
 }

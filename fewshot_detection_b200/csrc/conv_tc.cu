@@ -94,33 +94,35 @@ __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__
         float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
         float mn[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (cv < C4)
-            for (long long p = p0 + threadIdx.y; p < p1; p += TY) {
-                float4 v = ldg4(z + p * ld + cv * 4);
-                const float f[4] = {v.x, v.y, v.z, v.w};
+            for (long long p = p0 + threadIdx.y; p < p1; p += 4 * TY) {   // four loads in flight, accumulated in row order
+                float4 v[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    s[k] += f[k]; q[k] += f[k] * f[k]; mn[k] = fminf(mn[k], f[k]); mx[k] = fmaxf(mx[k], f[k]);
+                for (int u = 0; u < 4; ++u)
+                    if (p + u * TY < p1) v[u] = ldg4(z + (p + u * TY) * ld + cv * 4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (p + u * TY >= p1) break;
+                    const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        s[k] += f[k]; q[k] += f[k] * f[k]; mn[k] = fminf(mn[k], f[k]); mx[k] = fmaxf(mx[k], f[k]);
+                    }
                 }
             }
         float* mine = red + ((size_t)threadIdx.y * TC + threadIdx.x) * 16;
 #pragma unroll
         for (int k = 0; k < 4; ++k) { mine[k] = s[k]; mine[4 + k] = q[k]; mine[8 + k] = mn[k]; mine[12 + k] = mx[k]; }
         __syncthreads();
-        if (threadIdx.y == 0 && cv < C4) {
-            float ts[4] = {0, 0, 0, 0}, tq[4] = {0, 0, 0, 0};
-            float tn[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, tx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            for (int r = 0; r < TY; ++r) {
-                const float* o = red + ((size_t)r * TC + threadIdx.x) * 16;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    ts[k] += o[k]; tq[k] += o[4 + k]; tn[k] = fminf(tn[k], o[8 + k]); tx[k] = fmaxf(tx[k], o[12 + k]);
-                }
+        // column j = (channel lane, statistic, component) reduced over the TY pixel lanes in a fixed order, all threads busy
+        for (int j = threadIdx.y * TC + threadIdx.x; j < TC * 16; j += TC * TY) {
+            const int lane = j >> 4, stat = (j >> 2) & 3, comp = j & 3;
+            if (cv0 + lane >= C4) continue;
+            float t = red[j];
+            for (int r = 1; r < TY; ++r) {
+                const float o = red[(size_t)r * TC * 16 + j];
+                t = stat < 2 ? t + o : (stat == 2 ? fminf(t, o) : fmaxf(t, o));
             }
-            float* dst = part + (long long)blockIdx.x * 4 * C;
-            *reinterpret_cast<float4*>(dst + cv * 4) = make_float4(ts[0], ts[1], ts[2], ts[3]);
-            *reinterpret_cast<float4*>(dst + C + cv * 4) = make_float4(tq[0], tq[1], tq[2], tq[3]);
-            *reinterpret_cast<float4*>(dst + 2 * C + cv * 4) = make_float4(tn[0], tn[1], tn[2], tn[3]);
-            *reinterpret_cast<float4*>(dst + 3 * C + cv * 4) = make_float4(tx[0], tx[1], tx[2], tx[3]);
+            part[(long long)blockIdx.x * 4 * C + stat * C + (cv0 + lane) * 4 + comp] = t;
         }
         __syncthreads();
     }
@@ -817,8 +819,13 @@ extern "C" int fsdet_split_f16(const float* src, int ld, int C, int Cpad, size_t
     return launch_status("split_f16");
 }
 
-static const int kStatStrip = 256;
-extern "C" int fsdet_colstats_rows(size_t npix) { return ceil_div((long long)npix, kStatStrip); }
+// pixels per partial row: large tensors use long strips (few partial rows, little reduction work afterwards), small
+// ones short strips so that every SM still gets CTAs
+static int stat_strip(size_t npix) {
+    long long s = (long long)(npix / (8 * kNumSMs)) / 32 * 32;
+    return (int)(s < 32 ? 32 : (s > 1024 ? 1024 : s));
+}
+extern "C" int fsdet_colstats_rows(size_t npix) { return ceil_div((long long)npix, stat_strip(npix)); }
 
 extern "C" int fsdet_colstats(const float* z, int ld, size_t npix, int C, float* partial, void* stream) {
     FSDET_CHECK_ARG(z && partial && C % 4 == 0 && ld % 4 == 0 && aligned16(z), "colstats: C=%d ld=%d", C, ld);
@@ -828,7 +835,7 @@ extern "C" int fsdet_colstats(const float* z, int ld, size_t npix, int C, float*
     int TY = 256 / TCx;
     dim3 block(TCx, TY);
     size_t smem = (size_t)TY * TCx * 16 * sizeof(float);
-    colstats_kernel<<<fsdet_colstats_rows(npix), block, smem, (cudaStream_t)stream>>>(z, ld, (long long)npix, C, kStatStrip, partial);
+    colstats_kernel<<<fsdet_colstats_rows(npix), block, smem, (cudaStream_t)stream>>>(z, ld, (long long)npix, C, stat_strip(npix), partial);
     return launch_status("colstats");
 }
 

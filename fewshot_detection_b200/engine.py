@@ -700,11 +700,16 @@ class NetRunner(object):
         g, acc = x.grad_for_write()
         self._conv('dgrad', dz, wt, None, g, None, cout, cin_p, k, acc, st)
 
+    @staticmethod
+    def _wgrad_tc_ok(cin_p, cout, k):
+        return bool(USE_TC and 'wgrad' in TC_PARTS and cin_p >= 32 and cout >= 32 and _lib.lib.fsdet_conv_tc_wgrad_supported(
+            _round_up(cin_p, 64), _round_up(cout, 64), k))
+
     def _wgrad(self, x, dz, out_tensor, cin_p, cout, k, st):
         dev = x.dev
         flops = 2.0 * x.npix * cout * k * k * cin_p
         ci64, co64 = _round_up(cin_p, 64), _round_up(cout, 64)
-        if USE_TC and 'wgrad' in TC_PARTS and cin_p >= 32 and cout >= 32 and _lib.lib.fsdet_conv_tc_wgrad_supported(ci64, co64, k):
+        if x.nchw is None and self._wgrad_tc_ok(cin_p, cout, k):
             xh, xl, xa = self._planes(x, st)
             dh, dl, da = self._planes(dz, st)
             nws = _lib.lib.fsdet_conv_tc_wgrad_workspace_floats(x.B, x.H, x.W, ci64, co64, k)
@@ -746,18 +751,34 @@ class NetRunner(object):
             self._done(conv.weight, bn.weight, bn.bias)
             return
         rows = _lib.lib.fsdet_bn_bwd_rows(B, H, W)
-        part = _empty(rows + 1, 2 * s.cout, dtype=torch.float64, device=dev)
+        part = _empty(rows + 1, 4 * s.cout, dtype=torch.float64, device=dev)
         coef = _empty(2, s.cout, dtype=torch.float64, device=dev)
         a_gf = (gf.ptr, gf.ld) if gf is not None else (None, 0)
         a_gp = (gp.ptr, gp.ld) if gp is not None else (None, 0)
         call('fsdet_bn_act_bwd_reduce', z.ptr, z.ld, a_gf[0], a_gf[1], a_gp[0], a_gp[1], ptr(vec[2]), ptr(vec[3]),
              ptr(vec[0]), ptr(vec[1]), s.slope, ptr(part), B, H, W, s.cout, 1, st)
+        # which GEMMs will read dz, and in which form: the tensor-core ones take fp16 planes, written directly by
+        # the apply pass (scaled by the bound of max|dz| from the finalize step); fp32 dz only if a SIMT kernel needs it
+        cin_p = x.C
+        wg_tc = self._wgrad_tc_ok(cin_p, s.cout, s.k)
+        dg_tc = x.needs_grad and 'dgrad' in TC_PARTS and self._tc_ok(s.cout, cin_p, s.k)
+        want_planes = USE_TC and s.cout % 64 == 0 and (wg_tc or dg_tc)
+        want_f32 = (not want_planes) or (not wg_tc) or (x.needs_grad and not dg_tc)
+        amax = _empty(1, device=dev) if want_planes else None
         call('fsdet_bn_bwd_finalize', ptr(part), rows, float(x.npix), ptr(bn.weight), ptr(vec[1]), ptr(gg), ptr(gb),
-             ptr(coef), s.cout, 1, st)
-        dz = Act.new(B, H, W, s.cout, dev, False)
-        dz.amax = _empty(1, device=dev) if USE_TC else None
+             ptr(coef), ptr(amax), s.cout, 1, st)
+        planes = None
+        if want_planes:
+            planes = (torch.empty(x.npix, s.cout, dtype=torch.float16, device=dev),
+                      torch.empty(x.npix, s.cout, dtype=torch.float16, device=dev), amax)
+        if want_f32:
+            dz = Act.new(B, H, W, s.cout, dev, False)
+            dz.planes = planes
+        else:
+            dz = Act.planes_only(B, H, W, s.cout, dev, planes)
         call('fsdet_bn_act_bwd_apply', z.ptr, z.ld, a_gf[0], a_gf[1], a_gp[0], a_gp[1], ptr(vec[2]), ptr(vec[3]),
-             ptr(vec[0]), ptr(vec[1]), ptr(coef), s.slope, dz.ptr, dz.ld, ptr(dz.amax), B, H, W, s.cout, 1, st)
+             ptr(vec[0]), ptr(vec[1]), ptr(coef), s.slope, dz.ptr if want_f32 else None, dz.ld if want_f32 else 0,
+             ptr(planes[0]) if planes else None, ptr(planes[1]) if planes else None, s.cout, ptr(amax), B, H, W, s.cout, 1, st)
         cin_p = x.C
         if cin_p != s.cin:
             gwp = _empty(s.cout, s.k * s.k, cin_p, device=dev)
@@ -793,19 +814,19 @@ class NetRunner(object):
             ones = torch.ones(cout_p, device=dev)
             zeros = torch.zeros(cout_p, device=dev)
         rows = _lib.lib.fsdet_bn_bwd_rows(B, H, W)
-        part = _empty(rows + 1, 2 * cout_p, dtype=torch.float64, device=dev)
+        part = _empty(rows + 1, 4 * cout_p, dtype=torch.float64, device=dev)
         dbp = _empty(cout_p, device=dev)
         a_gf = (gf.ptr, gf.ld) if gf is not None else (None, 0)
         a_gp = (gp.ptr, gp.ld) if gp is not None else (None, 0)
         call('fsdet_bn_act_bwd_reduce', z.ptr, z.ld, a_gf[0], a_gf[1], a_gp[0], a_gp[1], ptr(ones), ptr(zeros), None, None,
              s.slope, ptr(part), B, H, W, cout_p, 0, st)
-        call('fsdet_bn_bwd_finalize', ptr(part), rows, float(x.npix), None, None, None, ptr(dbp), None, cout_p, 0, st)
+        call('fsdet_bn_bwd_finalize', ptr(part), rows, float(x.npix), None, None, None, ptr(dbp), None, None, cout_p, 0, st)
         if full is z and gp is None:
             dz = gf  # linear, unpooled: dZ is the incoming gradient itself
         else:
             dz = Act.new(B, H, W, cout_p, dev, False)
             call('fsdet_bn_act_bwd_apply', z.ptr, z.ld, a_gf[0], a_gf[1], a_gp[0], a_gp[1], ptr(ones), ptr(zeros), None,
-                 None, None, s.slope, dz.ptr, dz.ld, None, B, H, W, cout_p, 0, st)
+                 None, None, s.slope, dz.ptr, dz.ld, None, None, 0, None, B, H, W, cout_p, 0, st)
         cin_p = x.C
         kk = s.k * s.k
         gwp = _empty(cout_p, kk, cin_p, device=dev)

@@ -155,27 +155,37 @@ int fsdet_bn_act_fwd(const float* z, int ldz, const float* scale, const float* s
                      int ld_full, float* y_pool, int ld_pool, void* full_hi, void* full_lo, void* pool_hi,
                      void* pool_lo, int Cpad, const float* amax, int B, int H, int W, int C, void* stream);
 /* Backward of the block above.  dy_full / dy_pool: gradients w.r.t. the two
- * outputs (either may be NULL).  Pass 1 reduces  sum(du), sum(du*xhat) into
- * partials double [fsdet_bn_bwd_rows(B,H,W) + 1][2*C] (the extra row receives
- * the totals in fsdet_bn_bwd_finalize); pass 2 (after fsdet_bn_bwd_finalize)
- * writes dz.  Sums, coefficients and the projection
- * dz = scale*(du - mean(du) - xhat*mean(du*xhat)) are evaluated in float64: the
- * projection cancels heavily and float32 sums lose 2-3 digits there (torch's
- * CPU kernel uses double accumulators for the same reason).  With has_bn == 0
- * (conv + bias + act): xhat terms are skipped, dbeta = bias gradient, dz = du. */
+ * outputs (either may be NULL).  Pass 1 reduces, per CTA row,
+ * [sum(du) | sum(du*xhat) | max|du| | max|xhat|] into partials double
+ * [fsdet_bn_bwd_rows(B,H,W) + 1][4*C] (the extra row receives the totals in
+ * fsdet_bn_bwd_finalize); pass 2 (after fsdet_bn_bwd_finalize) writes dz.
+ * The projection dz = scale*(du - mean(du) - xhat*mean(du*xhat)) cancels
+ * heavily and float32 sums lose 2-3 digits there (torch's CPU kernel uses double
+ * accumulators for the same reason): sums are accumulated to double accuracy
+ * (compensated fp32 per thread, double across threads), coefficients are
+ * double, and the apply pass subtracts mean(du) as a (hi, lo) float pair.
+ * With has_bn == 0 (conv + bias + act): xhat terms are skipped, dbeta = bias
+ * gradient, dz = du. */
 int fsdet_bn_act_bwd_reduce(const float* z, int ldz, const float* dy_full, int ld_dyf, const float* dy_pool,
                             int ld_dyp, const float* scale, const float* shift, const float* mean,
                             const float* invstd, float slope, double* partial, int B, int H, int W, int C,
                             int has_bn, void* stream);
 int fsdet_bn_bwd_rows(int B, int H, int W);
-/* dgamma, dbeta and the two per-channel coefficients used by the apply pass */
+/* dgamma, dbeta, the two per-channel coefficients used by the apply pass and
+ * (optional) *amax_bound >= max|dz|, from |dz| <= |scale|*(max|du| + |c1| +
+ * max|xhat|*|c2|): the power-of-two scale of dz's fp16 planes. */
 int fsdet_bn_bwd_finalize(const double* partial, int nparts, double count, const float* gamma, const float* invstd,
-                          float* dgamma, float* dbeta, double* coef /* [2*C] */, int C, int has_bn, void* stream);
+                          float* dgamma, float* dbeta, double* coef /* [2*C] */, float* amax_bound, int C, int has_bn,
+                          void* stream);
+/* dz as fp32 (dz, may be NULL) and/or directly as the scaled fp16 hi/lo planes
+ * [pixels][cpad] read by the tensor-core GEMMs (dz_hi/dz_lo, may be NULL;
+ * cpad == C; scaled by the power of two derived from *amax, which must bound
+ * max|dz| - use fsdet_bn_bwd_finalize's amax_bound). */
 int fsdet_bn_act_bwd_apply(const float* z, int ldz, const float* dy_full, int ld_dyf, const float* dy_pool,
                            int ld_dyp, const float* scale, const float* shift, const float* mean,
-                           const float* invstd, const double* coef, float slope, float* dz, int lddz,
-                           float* amax_out /* optional: absolute maximum of dz */, int B, int H, int W, int C,
-                           int has_bn, void* stream);
+                           const float* invstd, const double* coef, float slope, float* dz, int lddz, void* dz_hi,
+                           void* dz_lo, int cpad, const float* amax, int B, int H, int W, int C, int has_bn,
+                           void* stream);
 
 /* ---- stand-alone pooling / reorg / route (darknet_meta.py:47-74,157-171) */
 /* size 2; stride 2 (floor) or stride 1 with replicate pad right/bottom

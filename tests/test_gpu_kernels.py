@@ -161,18 +161,30 @@ def test_bn_act_pool_fwd_bwd(L, B, H, W, C, pool, full):
     if pool:
         gp = nhwc(gouts[gi])
     rows = L.lib.fsdet_bn_bwd_rows(B, H, W)
-    part = torch.empty(rows + 1, 2 * C, dtype=torch.float64, device='cuda')
+    part = torch.empty(rows + 1, 4 * C, dtype=torch.float64, device='cuda')
     coef = torch.empty(2, C, dtype=torch.float64, device='cuda')
     dgam, dbet = torch.empty(C, device='cuda'), torch.empty(C, device='cuda')
     a = (zb.data_ptr(), C, gf.data_ptr() if full else None, C, gp.data_ptr() if pool else None, C, vec[2].data_ptr(),
          vec[3].data_ptr(), vec[0].data_ptr(), vec[1].data_ptr())
     L.call('fsdet_bn_act_bwd_reduce', *a, 0.1, part.data_ptr(), B, H, W, C, 1, st())
+    dzmax = torch.full((1,), 123.0, device='cuda')
     L.call('fsdet_bn_bwd_finalize', part.data_ptr(), rows, float(npix), gamma.data_ptr(), vec[1].data_ptr(), dgam.data_ptr(),
-           dbet.data_ptr(), coef.data_ptr(), C, 1, st())
+           dbet.data_ptr(), coef.data_ptr(), dzmax.data_ptr(), C, 1, st())
     dz = torch.empty(npix, C, device='cuda')
-    dzmax = torch.zeros(1, device='cuda')
-    L.call('fsdet_bn_act_bwd_apply', *a, coef.data_ptr(), 0.1, dz.data_ptr(), C, dzmax.data_ptr(), B, H, W, C, 1, st())
-    assert dzmax.item() == dz.abs().max().item()
+    dh = torch.full((npix, C), 7.0, dtype=torch.float16, device='cuda')
+    dl = torch.full((npix, C), 7.0, dtype=torch.float16, device='cuda')
+    L.call('fsdet_bn_act_bwd_apply', *a, coef.data_ptr(), 0.1, dz.data_ptr(), C, dh.data_ptr(), dl.data_ptr(), C,
+           dzmax.data_ptr(), B, H, W, C, 1, st())
+    # the plane scale comes from an upper bound of max|dz| (never below it, and not uselessly loose)
+    true_max = dz.abs().max().item()
+    assert true_max <= dzmax.item() <= 16 * true_max
+    scd = 2.0 ** (10 - math.frexp(dzmax.item())[1])
+    assert rel((dh.float() + dl.float()) / scd, dz) < 1e-5
+    # planes only (no fp32 dz) gives the same planes
+    dh2, dl2 = torch.empty_like(dh), torch.empty_like(dl)
+    L.call('fsdet_bn_act_bwd_apply', *a, coef.data_ptr(), 0.1, None, 0, dh2.data_ptr(), dl2.data_ptr(), C,
+           dzmax.data_ptr(), B, H, W, C, 1, st())
+    assert torch.equal(dh, dh2) and torch.equal(dl, dl2)
     assert rel(dgam, gamma.grad) < 1e-4
     assert rel(dbet, beta.grad) < 1e-4
     assert rel(nchw(dz, B, H, W), z.grad) < 1e-4
@@ -259,7 +271,8 @@ def test_fused_sgd_matches_torch(L):
         assert rel(pa, pb) < 1e-6
 
 
-@pytest.mark.parametrize('B,H,W,Cout,C0,C1', [(2, 13, 17, 32, 3, 0), (3, 64, 64, 16, 3, 1), (1, 5, 3, 8, 2, 1), (2, 416, 416, 32, 3, 1)])
+@pytest.mark.parametrize('B,H,W,Cout,C0,C1', [(2, 13, 17, 32, 3, 0), (3, 64, 64, 16, 3, 1), (1, 5, 3, 8, 2, 1), (2, 416, 416, 32, 3, 1),
+                                                (5, 200, 130, 32, 3, 1), (7, 100, 211, 24, 3, 0), (1, 40, 608, 32, 3, 0)])
 def test_conv_first_layer_fwd_wgrad(L, B, H, W, Cout, C0, C1):
     g = torch.Generator(device='cuda').manual_seed(H + W)
     a = torch.rand(B, C0, H, W, device='cuda', generator=g)
