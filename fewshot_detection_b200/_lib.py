@@ -41,12 +41,12 @@ SIGNATURES = {
     'fsdet_colstats': ('pizipp', 'i'),
     'fsdet_colstats_rows': ('z', 'i'),
     'fsdet_debug_im2col_tile': ('piiiiiqiipp', 'i'),
-    'fsdet_bn_finalize': ('pidppppffppppfpiip', 'i'),
+    'fsdet_bn_finalize': ('pidppppffppppfppiip', 'i'),
     'fsdet_bn_stat_scratch_rows': ('', 'i'),
     'fsdet_bn_act_fwd': ('pippfpipippppipiiiip', 'i'),
     'fsdet_bn_act_bwd_reduce': ('pipipippppfpiiiiip', 'i'),
     'fsdet_bn_bwd_rows': ('iii', 'i'),
-    'fsdet_bn_bwd_finalize': ('pidppppppiip', 'i'),
+    'fsdet_bn_bwd_finalize': ('pidpppppppiip', 'i'),
     'fsdet_bn_act_bwd_apply': ('pipipipppppfpippipiiiiip', 'i'),
     'fsdet_maxpool_fwd': ('pipiiiiiip', 'i'),
     'fsdet_maxpool_bwd': ('pipipiiiiiip', 'i'),

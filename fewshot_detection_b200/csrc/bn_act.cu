@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restri
                                                           float momentum, float eps, float* __restrict__ mean,
                                                           float* __restrict__ invstd, float* __restrict__ scale,
                                                           float* __restrict__ shift, float slope, float* __restrict__ amax_y,
-                                                          int C, int training) {
+                                                          float* __restrict__ xhat_absmax, int C, int training) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     float ymax = 0.f;
     if (c < C) {
@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restri
         float mn = INFINITY, mx = -INFINITY;
         if (training) {
             double s = 0.0, q = 0.0;
+#pragma unroll 8
             for (int i = 0; i < S; ++i) {
                 const double* row = red + (long long)i * 4 * C;
                 s += row[c]; q += row[C + c];
@@ -156,8 +157,13 @@ __global__ void __launch_bounds__(128) bn_finalize_kernel(const double* __restri
         if (invstd) invstd[c] = is;
         scale[c] = sc;
         shift[c] = sh;
-        if (training && mn <= mx)
+        if (training && mn <= mx) {
             ymax = fmaxf(fabsf(leaky(fmaf(mn, sc, sh), slope)), fabsf(leaky(fmaf(mx, sc, sh), slope)));
+            // max |xhat| with xhat = (z - mean) * invstd evaluated exactly as the backward kernels do (monotone in z)
+            if (xhat_absmax) xhat_absmax[c] = fmaxf(fabsf((mn - m) * is), fabsf((mx - m) * is));
+        } else if (xhat_absmax) {
+            xhat_absmax[c] = 0.f;
+        }
     }
     if (amax_y && training) {
 #pragma unroll
@@ -298,13 +304,13 @@ __device__ __forceinline__ void kahan_add(float& s, float& e, float x) {
 }
 
 // reduce-pass epilogue: red[blockDim.y][TC*16] doubles (per thread: 4 x sum(du), 4 x sum(du*xhat), 4 x max|du|,
-// 4 x max|xhat|) -> one partial row; column j is reduced over the blockDim.y lanes in a fixed order, all threads busy
+// 4 unused) -> one partial row [3C]; column j is reduced over the blockDim.y lanes in a fixed order, all threads busy
 __device__ __forceinline__ void bwd_block_reduce(const double* red, double* dst, int C, int cv0) {
     const int TC = blockDim.x, TY = blockDim.y;
     for (int j = threadIdx.y * TC + threadIdx.x; j < TC * 16; j += TC * TY) {
         const int lane = j >> 4, stat = (j >> 2) & 3, comp = j & 3;
         const int ch = (cv0 + lane) * 4 + comp;
-        if (ch >= C) continue;
+        if (ch >= C || stat == 3) continue;
         double t = red[j];
         for (int r = 1; r < TY; ++r) {
             const double o = red[(size_t)r * TC * 16 + j];
@@ -318,7 +324,7 @@ __device__ __forceinline__ void bwd_block_reduce(const double* red, double* dst,
 // by its per-channel mean.  The sums are therefore accumulated to double-precision accuracy (compensated fp32 per
 // thread, double across threads), the coefficients are computed in double, and the apply pass subtracts mean(du)
 // as a (hi, lo) float pair: a difference of close floats is exact, so nothing is lost to the cancellation.
-// REDUCE writes per CTA row [sum(du) | sum(du*xhat) | max|du| | max|xhat|] (4C doubles).
+// REDUCE writes per CTA row [sum(du) | sum(du*xhat) | max|du|] (3C doubles).
 // APPLY writes dz as fp32 and/or directly as the scaled fp16 (hi, lo) planes the tensor-core GEMMs read.
 template <bool APPLY>
 __global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_kernel(const BwdArgs a) {
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_kernel(const Bw
     }
     const float psc = (APPLY && a.dh) ? plane_scale(__ldg(a.amax)) : 1.f;
     float s1[4] = {0, 0, 0, 0}, e1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, e2[4] = {0, 0, 0, 0};
-    float md[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};
+    float md[4] = {0, 0, 0, 0};
 
     for (unsigned wi = blockIdx.x * blockDim.y + threadIdx.y; cok && wi < (unsigned)nwin; wi += gridDim.x * blockDim.y) {
         const unsigned t = wi / W2;
@@ -417,7 +423,6 @@ __global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_kernel(const Bw
                     kahan_add(s1[k], e1[k], d);
                     kahan_add(s2[k], e2[k], d * xh);
                     md[k] = fmaxf(md[k], fabsf(d));
-                    mx[k] = fmaxf(mx[k], fabsf(xh));
                 }
             }
             if (APPLY) {
@@ -437,10 +442,9 @@ __global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_kernel(const Bw
             mine[k] = (double)s1[k] - (double)e1[k];
             mine[4 + k] = (double)s2[k] - (double)e2[k];
             mine[8 + k] = (double)md[k];
-            mine[12 + k] = (double)mx[k];
         }
         __syncthreads();
-        bwd_block_reduce(red, a.partial + (long long)blockIdx.x * 4 * a.C, a.C, blockIdx.y * TC);
+        bwd_block_reduce(red, a.partial + (long long)blockIdx.x * 3 * a.C, a.C, blockIdx.y * TC);
     }
 }
 
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_pool_kernel(con
     const float psc = (APPLY && a.dh) ? plane_scale(__ldg(a.amax)) : 1.f;
     const float slope = a.slope;
     float s1[4] = {0, 0, 0, 0}, e1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, e2[4] = {0, 0, 0, 0};
-    float md[4] = {0, 0, 0, 0}, mx[4] = {0, 0, 0, 0};
+    float md[4] = {0, 0, 0, 0};
 
     for (unsigned wi = blockIdx.x * blockDim.y + threadIdx.y; cok && wi < nwin; wi += gridDim.x * blockDim.y) {
         const unsigned t = wi / W2;
@@ -527,9 +531,6 @@ __global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_pool_kernel(con
                     o[q][k] = scv[k] * fmaf(-xh, c2f[k], (whole && q == best) ? tb : t0[k]);
                 }
             } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (ok[q]) mx[k] = fmaxf(mx[k], fabsf((zv[q][k] - muv[k]) * isv[k]));
                 if (whole) {
                     const float xh = (zb - muv[k]) * isv[k];
                     kahan_add(s1[k], e1[k], d);
@@ -558,19 +559,18 @@ __global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_pool_kernel(con
             mine[k] = (double)s1[k] - (double)e1[k];
             mine[4 + k] = (double)s2[k] - (double)e2[k];
             mine[8 + k] = (double)md[k];
-            mine[12 + k] = (double)mx[k];
         }
         __syncthreads();
-        bwd_block_reduce(red, a.partial + (long long)blockIdx.x * 4 * a.C, a.C, blockIdx.y * TC);
+        bwd_block_reduce(red, a.partial + (long long)blockIdx.x * 3 * a.C, a.C, blockIdx.y * TC);
     }
 }
 
-// sums row [4C] -> dgamma, dbeta, the projection coefficients, and an upper bound of max|dz| (the scale of dz's fp16
+// sums row [3C] -> dgamma, dbeta, the projection coefficients, and an upper bound of max|dz| (the scale of dz's fp16
 // planes): |dz| <= |scale| * (max|du| + |c1| + max|xhat| * |c2|)
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
-                                       const float* __restrict__ invstd, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, double* __restrict__ coef, float* __restrict__ amax_bound,
-                                       int C, int has_bn) {
+                                       const float* __restrict__ invstd, const float* __restrict__ xhat_absmax,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, double* __restrict__ coef,
+                                       float* __restrict__ amax_bound, int C, int has_bn) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     double sdu = sums[c], sdux = sums[C + c];
@@ -581,7 +581,7 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, double c
         const double c1 = sdu / count, c2 = sdux / count;
         coef[c] = c1;
         coef[C + c] = c2;
-        bound = fabs((double)gamma[c] * (double)invstd[c]) * (bound + fabs(c1) + sums[3 * C + c] * fabs(c2));
+        if (amax_bound) bound = fabs((double)gamma[c] * (double)invstd[c]) * (bound + fabs(c1) + (double)xhat_absmax[c] * fabs(c2));
     }
     if (amax_bound) {
         const float bf = (float)(bound * 1.0001);
@@ -607,8 +607,8 @@ extern "C" int fsdet_bn_bwd_rows(int B, int H, int W) { return bwd_rows(B, H, W)
 
 extern "C" int fsdet_bn_finalize(const float* stat_partial, int nparts, double count, const float* gamma,
                                  const float* beta, float* running_mean, float* running_var, float momentum, float eps,
-                                 float* mean, float* invstd, float* scale, float* shift, float slope, float* amax_y, int C,
-                                 int training, void* stream) {
+                                 float* mean, float* invstd, float* scale, float* shift, float slope, float* amax_y,
+                                 float* xhat_absmax, int C, int training, void* stream) {
     FSDET_CHECK_ARG(scale && shift && C > 0, "bn_finalize: bad args");
     cudaStream_t s = (cudaStream_t)stream;
     if (training) {
@@ -636,7 +636,7 @@ extern "C" int fsdet_bn_finalize(const float* stat_partial, int nparts, double c
         red = scratch;
     }
     bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(red, S, count, gamma, beta, running_mean, running_var, momentum, eps, mean,
-                                                        invstd, scale, shift, slope, amax_y, C, training);
+                                                        invstd, scale, shift, slope, amax_y, xhat_absmax, C, training);
     return launch_status("bn_finalize");
 }
 
@@ -708,20 +708,21 @@ extern "C" int fsdet_bn_act_bwd_reduce(const float* z, int ldz, const float* dy_
 }
 
 extern "C" int fsdet_bn_bwd_finalize(const double* partial, int nparts, double count, const float* gamma,
-                                     const float* invstd, float* dgamma, float* dbeta, double* coef, float* amax_bound,
-                                     int C, int has_bn, void* stream) {
+                                     const float* invstd, const float* xhat_absmax, float* dgamma, float* dbeta, double* coef,
+                                     float* amax_bound, int C, int has_bn, void* stream) {
     FSDET_CHECK_ARG(partial && nparts > 0 && C > 0 && (!has_bn || (coef && gamma && invstd)), "bn_bwd_finalize: bad args");
+    FSDET_CHECK_ARG(!(amax_bound && has_bn) || xhat_absmax, "bn_bwd_finalize: the bound of max|dz| needs xhat_absmax");
     cudaStream_t s = (cudaStream_t)stream;
-    double* sums = const_cast<double*>(partial) + (size_t)nparts * 4 * C;  // the extra row
-    dim3 block(32, 32), grid(ceil_div(4 * C, 32));
-    colsum_dd_kernel<<<grid, block, 0, s>>>(partial, nparts, 4 * C, 2 * C, sums);
+    double* sums = const_cast<double*>(partial) + (size_t)nparts * 3 * C;  // the extra row
+    dim3 block(32, 32), grid(ceil_div(3 * C, 32));
+    colsum_dd_kernel<<<grid, block, 0, s>>>(partial, nparts, 3 * C, 2 * C, sums);
     int st = launch_status("bn_bwd_finalize/colsum");
     if (st) return st;
     if (amax_bound) {
         cudaError_t e = cudaMemsetAsync(amax_bound, 0, sizeof(float), s);
         if (e != cudaSuccess) { set_error("bn_bwd_finalize: memset: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(sums, count, gamma, invstd, dgamma, dbeta, coef, amax_bound, C, has_bn);
+    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(sums, count, gamma, invstd, xhat_absmax, dgamma, dbeta, coef, amax_bound, C, has_bn);
     return launch_status("bn_bwd_finalize");
 }
 

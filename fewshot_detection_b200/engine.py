@@ -302,7 +302,7 @@ class NetRunner(object):
         return self._tc_ok(cin, c.cout, c.k) and c.cout >= 32 and bool(
             _lib.lib.fsdet_conv_tc_wgrad_supported(_round_up(cin, 64), _round_up(c.cout, 64), c.k))
 
-    def _conv(self, name, x, w_ohwi, bias, z, stat_rows_out, cin, cout, k, acc, st):
+    def _conv(self, name, x, w_ohwi, bias, z, stat_rows_out, cin, cout, k, acc, st, w_amax=None):
         """z = conv(x, w) through the tensor-core kernel when the shape allows, else SIMT.
         Returns the number of BN partial rows written to `stat_rows_out` (a float tensor or None)."""
         flops = 2.0 * x.npix * cout * k * k * cin
@@ -318,7 +318,9 @@ class NetRunner(object):
         if bias is None and name in TC_PARTS and self._tc_ok(cin, cout, k):
             cpad = _round_up(cin, 64)
             xh, xl, xa = self._planes(x, st)
-            wh, wl, wa = self._split_tensor(ptr(w_ohwi), cin, cin, cout * k * k, x.dev, st, cpad)
+            wh, wl, wa = self._split_tensor(ptr(w_ohwi), cin, cin, cout * k * k, x.dev, st, cpad, w_amax)
+            if name == 'fwd':   # the flip-transposed copy used by the input-gradient GEMM has the same absolute maximum
+                w_ohwi._fsdet_amax = (wa, w_ohwi._version)
             self._timed('conv_tc', flops, 'fsdet_conv_tc_fwd', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(xa), ptr(wa), z.ptr, z.ld,
                         x.B, x.H, x.W, _round_up(cin, 32), cpad, cout, k, acc, st)
             if stat_rows_out is not None:
@@ -514,14 +516,15 @@ class NetRunner(object):
             rows_cap = max(_lib.lib.fsdet_conv_stat_rows(npix), _lib.lib.fsdet_colstats_rows(npix))
             stat = _empty(rows_cap + _lib.lib.fsdet_bn_stat_scratch_rows(), 4 * s.cout, device=dev) if use_batch_stats else None
             rows = self._conv('fwd', x, wuse, None, z, stat, cin_p, s.cout, s.k, 0, st)
-            vec = _empty(4, s.cout, device=dev)  # mean, invstd, scale, shift
+            vec = _empty(5, s.cout, device=dev)  # mean, invstd, scale, shift, max|xhat| (batch statistics only)
+            vec.xh_ok = bool(use_batch_stats)
             amax_y = _empty(1, device=dev) if use_batch_stats else None
             upd = training and bn.track_running_stats
             call('fsdet_bn_finalize', ptr(stat), rows, float(npix), ptr(bn.weight), ptr(bn.bias),
                  ptr(bn.running_mean) if (upd or not use_batch_stats) else None,
                  ptr(bn.running_var) if (upd or not use_batch_stats) else None,
                  BN_MOMENTUM if bn.momentum is None else float(bn.momentum), float(bn.eps),
-                 ptr(vec[0]), ptr(vec[1]), ptr(vec[2]), ptr(vec[3]), s.slope, ptr(amax_y), s.cout,
+                 ptr(vec[0]), ptr(vec[1]), ptr(vec[2]), ptr(vec[3]), s.slope, ptr(amax_y), ptr(vec[4]), s.cout,
                  1 if use_batch_stats else 0, st)
             if upd and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked += 1
@@ -698,7 +701,9 @@ class NetRunner(object):
         wt = _empty(cin_p, kk, cout, device=dev)
         call('fsdet_weight_flip_transpose', ptr(w_ohwi), ptr(wt), cout, kk, cin_p, st)
         g, acc = x.grad_for_write()
-        self._conv('dgrad', dz, wt, None, g, None, cout, cin_p, k, acc, st)
+        known = getattr(w_ohwi, '_fsdet_amax', None)
+        w_amax = known[0] if (known is not None and known[1] == w_ohwi._version) else None
+        self._conv('dgrad', dz, wt, None, g, None, cout, cin_p, k, acc, st, w_amax)
 
     @staticmethod
     def _wgrad_tc_ok(cin_p, cout, k):
@@ -751,7 +756,7 @@ class NetRunner(object):
             self._done(conv.weight, bn.weight, bn.bias)
             return
         rows = _lib.lib.fsdet_bn_bwd_rows(B, H, W)
-        part = _empty(rows + 1, 4 * s.cout, dtype=torch.float64, device=dev)
+        part = _empty(rows + 1, 3 * s.cout, dtype=torch.float64, device=dev)
         coef = _empty(2, s.cout, dtype=torch.float64, device=dev)
         a_gf = (gf.ptr, gf.ld) if gf is not None else (None, 0)
         a_gp = (gp.ptr, gp.ld) if gp is not None else (None, 0)
@@ -762,10 +767,10 @@ class NetRunner(object):
         cin_p = x.C
         wg_tc = self._wgrad_tc_ok(cin_p, s.cout, s.k)
         dg_tc = x.needs_grad and 'dgrad' in TC_PARTS and self._tc_ok(s.cout, cin_p, s.k)
-        want_planes = USE_TC and s.cout % 64 == 0 and (wg_tc or dg_tc)
+        want_planes = USE_TC and s.cout % 64 == 0 and (wg_tc or dg_tc) and getattr(vec, 'xh_ok', False)
         want_f32 = (not want_planes) or (not wg_tc) or (x.needs_grad and not dg_tc)
         amax = _empty(1, device=dev) if want_planes else None
-        call('fsdet_bn_bwd_finalize', ptr(part), rows, float(x.npix), ptr(bn.weight), ptr(vec[1]), ptr(gg), ptr(gb),
+        call('fsdet_bn_bwd_finalize', ptr(part), rows, float(x.npix), ptr(bn.weight), ptr(vec[1]), ptr(vec[4]), ptr(gg), ptr(gb),
              ptr(coef), ptr(amax), s.cout, 1, st)
         planes = None
         if want_planes:
@@ -814,13 +819,13 @@ class NetRunner(object):
             ones = torch.ones(cout_p, device=dev)
             zeros = torch.zeros(cout_p, device=dev)
         rows = _lib.lib.fsdet_bn_bwd_rows(B, H, W)
-        part = _empty(rows + 1, 4 * cout_p, dtype=torch.float64, device=dev)
+        part = _empty(rows + 1, 3 * cout_p, dtype=torch.float64, device=dev)
         dbp = _empty(cout_p, device=dev)
         a_gf = (gf.ptr, gf.ld) if gf is not None else (None, 0)
         a_gp = (gp.ptr, gp.ld) if gp is not None else (None, 0)
         call('fsdet_bn_act_bwd_reduce', z.ptr, z.ld, a_gf[0], a_gf[1], a_gp[0], a_gp[1], ptr(ones), ptr(zeros), None, None,
              s.slope, ptr(part), B, H, W, cout_p, 0, st)
-        call('fsdet_bn_bwd_finalize', ptr(part), rows, float(x.npix), None, None, None, ptr(dbp), None, None, cout_p, 0, st)
+        call('fsdet_bn_bwd_finalize', ptr(part), rows, float(x.npix), None, None, None, None, ptr(dbp), None, None, cout_p, 0, st)
         if full is z and gp is None:
             dz = gf  # linear, unpooled: dZ is the incoming gradient itself
         else:

@@ -141,11 +141,13 @@ int fsdet_debug_im2col_tile(const void* x_plane, int B, int H, int W, int C, int
  * absolute maximum of y = leaky(z*scale+shift, slope) over the tensor, derived
  * from the per-channel range of z (scale of the fp16 planes of y).  In eval mode
  * (training == 0) scale/shift come from the running statistics, stat_partial is
- * ignored and amax_y is not written. */
+ * ignored and amax_y is not written.  xhat_absmax (optional, [C]): max over
+ * the batch of |(z - mean) * invstd| per channel (used by the backward pass
+ * to bound max|dz|). */
 int fsdet_bn_finalize(const float* stat_partial, int nparts, double count, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, float momentum, float eps, float* mean,
-                      float* invstd, float* scale, float* shift, float slope, float* amax_y, int C, int training,
-                      void* stream);
+                      float* invstd, float* scale, float* shift, float slope, float* amax_y, float* xhat_absmax,
+                      int C, int training, void* stream);
 int fsdet_bn_stat_scratch_rows(void);
 /* y = leaky(z*scale+shift, slope), written in one pass as any subset of: fp32
  * full resolution (y_full), fp32 MaxPool2d(2,2) (floor) output (y_pool), and the
@@ -156,8 +158,8 @@ int fsdet_bn_act_fwd(const float* z, int ldz, const float* scale, const float* s
                      void* pool_lo, int Cpad, const float* amax, int B, int H, int W, int C, void* stream);
 /* Backward of the block above.  dy_full / dy_pool: gradients w.r.t. the two
  * outputs (either may be NULL).  Pass 1 reduces, per CTA row,
- * [sum(du) | sum(du*xhat) | max|du| | max|xhat|] into partials double
- * [fsdet_bn_bwd_rows(B,H,W) + 1][4*C] (the extra row receives the totals in
+ * [sum(du) | sum(du*xhat) | max|du|] into partials double
+ * [fsdet_bn_bwd_rows(B,H,W) + 1][3*C] (the extra row receives the totals in
  * fsdet_bn_bwd_finalize); pass 2 (after fsdet_bn_bwd_finalize) writes dz.
  * The projection dz = scale*(du - mean(du) - xhat*mean(du*xhat)) cancels
  * heavily and float32 sums lose 2-3 digits there (torch's CPU kernel uses double
@@ -173,10 +175,11 @@ int fsdet_bn_act_bwd_reduce(const float* z, int ldz, const float* dy_full, int l
 int fsdet_bn_bwd_rows(int B, int H, int W);
 /* dgamma, dbeta, the two per-channel coefficients used by the apply pass and
  * (optional) *amax_bound >= max|dz|, from |dz| <= |scale|*(max|du| + |c1| +
- * max|xhat|*|c2|): the power-of-two scale of dz's fp16 planes. */
+ * max|xhat|*|c2|) with max|xhat| = xhat_absmax from fsdet_bn_finalize: the
+ * power-of-two scale of dz's fp16 planes. */
 int fsdet_bn_bwd_finalize(const double* partial, int nparts, double count, const float* gamma, const float* invstd,
-                          float* dgamma, float* dbeta, double* coef /* [2*C] */, float* amax_bound, int C, int has_bn,
-                          void* stream);
+                          const float* xhat_absmax, float* dgamma, float* dbeta, double* coef /* [2*C] */,
+                          float* amax_bound, int C, int has_bn, void* stream);
 /* dz as fp32 (dz, may be NULL) and/or directly as the scaled fp16 hi/lo planes
  * [pixels][cpad] read by the tensor-core GEMMs (dz_hi/dz_lo, may be NULL;
  * cpad == C; scaled by the power of two derived from *amax, which must bound

@@ -128,12 +128,14 @@ def test_bn_act_pool_fwd_bwd(L, B, H, W, C, pool, full):
     stat = torch.zeros(srows + L.lib.fsdet_bn_stat_scratch_rows(), 4 * C, device='cuda')
     L.call('fsdet_colstats', zb.data_ptr(), C, npix, C, stat.data_ptr(), st())
     rm2, rv2 = torch.zeros(C, device='cuda'), torch.ones(C, device='cuda')
-    vec = torch.empty(4, C, device='cuda')
+    vec = torch.empty(5, C, device='cuda')
     amax = torch.zeros(1, device='cuda')
     L.call('fsdet_bn_finalize', stat.data_ptr(), srows, float(npix), gamma.data_ptr(), beta.data_ptr(), rm2.data_ptr(),
            rv2.data_ptr(), 0.1, 1e-5, vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(), vec[3].data_ptr(), 0.1,
-           amax.data_ptr(), C, 1, st())
+           amax.data_ptr(), vec[4].data_ptr(), C, 1, st())
     assert rel(rm2, rm) < 1e-5 and rel(rv2, rv) < 1e-5
+    xh = (z.detach() - vec[0].view(1, C, 1, 1)) * vec[1].view(1, C, 1, 1)
+    assert torch.equal(vec[4], xh.abs().amax(dim=(0, 2, 3)))
     assert abs(amax.item() - y.abs().max().item()) <= 1e-5 * y.abs().max().item()
     yf = torch.empty(npix, C, device='cuda') if full else None
     ypb = torch.empty(B * (H // 2) * (W // 2), C, device='cuda') if pool else None
@@ -161,15 +163,15 @@ def test_bn_act_pool_fwd_bwd(L, B, H, W, C, pool, full):
     if pool:
         gp = nhwc(gouts[gi])
     rows = L.lib.fsdet_bn_bwd_rows(B, H, W)
-    part = torch.empty(rows + 1, 4 * C, dtype=torch.float64, device='cuda')
+    part = torch.empty(rows + 1, 3 * C, dtype=torch.float64, device='cuda')
     coef = torch.empty(2, C, dtype=torch.float64, device='cuda')
     dgam, dbet = torch.empty(C, device='cuda'), torch.empty(C, device='cuda')
     a = (zb.data_ptr(), C, gf.data_ptr() if full else None, C, gp.data_ptr() if pool else None, C, vec[2].data_ptr(),
          vec[3].data_ptr(), vec[0].data_ptr(), vec[1].data_ptr())
     L.call('fsdet_bn_act_bwd_reduce', *a, 0.1, part.data_ptr(), B, H, W, C, 1, st())
     dzmax = torch.full((1,), 123.0, device='cuda')
-    L.call('fsdet_bn_bwd_finalize', part.data_ptr(), rows, float(npix), gamma.data_ptr(), vec[1].data_ptr(), dgam.data_ptr(),
-           dbet.data_ptr(), coef.data_ptr(), dzmax.data_ptr(), C, 1, st())
+    L.call('fsdet_bn_bwd_finalize', part.data_ptr(), rows, float(npix), gamma.data_ptr(), vec[1].data_ptr(), vec[4].data_ptr(),
+           dgam.data_ptr(), dbet.data_ptr(), coef.data_ptr(), dzmax.data_ptr(), C, 1, st())
     dz = torch.empty(npix, C, device='cuda')
     dh = torch.full((npix, C), 7.0, dtype=torch.float16, device='cuda')
     dl = torch.full((npix, C), 7.0, dtype=torch.float16, device='cuda')
