@@ -64,6 +64,9 @@ SIGNATURES = {
     'fsdet_region_loss_grad': ('ppppp iiiiiiii ppppppppp ff ii p p'.replace(' ', ''), 'i'),
     'fsdet_sgd_step': ('ppppppiiffffipp', 'i'),
     'fsdet_fill': ('pfzp', 'i'),
+    'fsdet_region_detect': ('ppiiiiiiiidpppp', 'i'),
+    'fsdet_nms': ('ppiiiidppp', 'i'),
+    'fsdet_rw_running_mean': ('pppppiiip', 'i'),
 }
 
 

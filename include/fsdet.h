@@ -265,6 +265,31 @@ int fsdet_sgd_step(float* const* params, const float* const* grads, float* const
                    float lr, float momentum, float dampening, float weight_decay, int first_step,
                    const float* hyper_dev, void* stream);
 
+/* ---- evaluation: detection decode + NMS ------------- */
+/* utils.get_region_boxes (utils.py:112-193; v2 = 0, n_models = 1) and utils.get_region_boxes_v2 (utils.py:195-290;
+ * v2 = 1: rows are (image, class) pairs, image-major, and the class score is the softmax ACROSS the n_models rows of
+ * an image).  output: float32 [N][A*(5+nC)][H][W] (the head output).  For every row n the anchor-cells with
+ * (only_objectness ? det_conf : det_conf*cls_max_conf) > conf_thresh (float64 test, as the reference's Python-float
+ * arithmetic) are written in the reference's loop order (cy, cx, anchor) to cand[n][0..count[n])[8] =
+ * {xs, ys, ws, hs (grid units, float32), det_conf, cls_max_conf, (int32 bits) cls_max_id, (int32 bits) a*H*W + cell};
+ * capacity per row = A*H*W.  cls_dense (optional, float32 [N*A*H*W][nC]) receives the softmax scores that the
+ * reference's `validation=True` branch reads (utils.py:176-181).  No device->host copy, no synchronisation. */
+int fsdet_region_detect(const float* output, const float* anchors_f32 /* [2A] */, int N, int A, int nC, int H, int W,
+                        int n_models, int v2, int only_objectness, double conf_thresh, float* cand, int32_t* count,
+                        float* cls_dense, void* stream);
+/* utils.nms (utils.py:85-104) for all N rows at once: boxes normalised in float64 (x/W, y/H, w/W, h/H), sorted by
+ * float32(1 - det_conf) ascending (ties: candidate order), greedy suppression with the float64 utils.bbox_iou
+ * (utils.py:21-52) > nms_thresh.  keep[n][0..keep_count[n]) = candidate slots of the survivors in that order.
+ * cap = candidates per row of `cand` (<= 4096). */
+int fsdet_nms(const float* cand, const int32_t* count, int N, int cap, int H, int W, double nms_thresh, int32_t* keep,
+              int32_t* keep_count, void* stream);
+/* Running mean of the support net's reweighting vectors per class, valid_ensemble.py:86-100:
+ * for i in 0..n-1: c = ids[i]; enews[c] = enews[c]*cnt[c]/(cnt[c]+1) + dw[i]/(cnt[c]+1); cnt[c] += 1 (float32, the
+ * reference's operation order).  enews float32 [n_cls][C] (zero before the first call), dw float32 [n][C];
+ * cnt_in / cnt_out int32 [n_cls] must be different buffers. */
+int fsdet_rw_running_mean(float* enews, const int32_t* cnt_in, int32_t* cnt_out, const float* dw, const int32_t* ids,
+                          int n, int n_cls, int C, void* stream);
+
 /* ---- misc --------------------------------------------------------------- */
 int fsdet_fill(float* p, float v, size_t n, void* stream);
 
