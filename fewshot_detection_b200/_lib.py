@@ -66,6 +66,7 @@ SIGNATURES = {
     'fsdet_fill': ('pfzp', 'i'),
     'fsdet_region_detect': ('ppiiiiiiiidpppp', 'i'),
     'fsdet_nms': ('ppiiiidppp', 'i'),
+    'fsdet_nms_boxes64': ('ppiidppp', 'i'),
     'fsdet_rw_running_mean': ('pppppiiip', 'i'),
 }
 

@@ -12,6 +12,13 @@
 // (utils.bbox_iou, utils.py:21-52, operation order kept, no FMA contraction).
 #include "common.cuh"
 
+// tools/host_emul compiles this file with g++ (threads = OS threads) to test the block-level logic without a GPU
+#ifdef FSDET_HOST_EMULATION
+#define FSDET_DYN_SMEM(name) unsigned char* name = emul::g_dyn_smem
+#else
+#define FSDET_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 namespace fsdet {
 
 constexpr int kDetThreads = 256;
@@ -134,10 +141,13 @@ __device__ __forceinline__ double nms_iou(const double4 p, const double4 q) {
 // One CTA per row: bitonic sort of (float32(1 - det_conf), slot) ascending = torch.sort of utils.py:89-93 with list
 // order on ties, then the greedy suppression loop of utils.py:95-103 with the inner loop spread over the block.
 // Dynamic shared memory: P * (8 + 32 + 1) bytes, P = power of two >= cap.
-__global__ void __launch_bounds__(kDetThreads) nms_kernel(const float* __restrict__ cand, const int32_t* __restrict__ count,
-                                                          int cap, int P, int H, int W, double thresh,
-                                                          int32_t* __restrict__ keep, int32_t* __restrict__ keep_count) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// boxes64 != nullptr: rows of already-normalised float64 boxes [N][cap][5] = {x, y, w, h, det_conf} (the list-of-lists
+// form utils.nms receives) instead of `cand`.
+__global__ void __launch_bounds__(kDetThreads) nms_kernel(const float* __restrict__ cand, const double* __restrict__ boxes64,
+                                                          const int32_t* __restrict__ count, int cap, int P, int H, int W,
+                                                          double thresh, int32_t* __restrict__ keep,
+                                                          int32_t* __restrict__ keep_count) {
+    FSDET_DYN_SMEM(smem_raw);
     double4* box = reinterpret_cast<double4*>(smem_raw);                                   // [P]
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(box + P);             // [P]
     unsigned char* alive = reinterpret_cast<unsigned char*>(keys + P);                     // [P]
@@ -150,12 +160,13 @@ __global__ void __launch_bounds__(kDetThreads) nms_kernel(const float* __restric
     }
     int Pn = 1;
     while (Pn < n) Pn <<= 1;
-    const float* c = cand + (size_t)row * cap * kCandFloats;
+    const float* c = cand ? cand + (size_t)row * cap * kCandFloats : nullptr;
+    const double* c64 = boxes64 ? boxes64 + (size_t)row * cap * 5 : nullptr;
     for (int t = threadIdx.x; t < Pn; t += kDetThreads) {
         unsigned long long key = ~0ull;
         if (t < n) {
-            const float det = c[(size_t)t * kCandFloats + 4];
-            const float kf = (float)__dsub_rn(1.0, (double)det);   // det_confs[i] = 1 - boxes[i][4] into a FloatTensor
+            const double det = c64 ? c64[(size_t)t * 5 + 4] : (double)c[(size_t)t * kCandFloats + 4];
+            const float kf = (float)__dsub_rn(1.0, det);   // det_confs[i] = 1 - boxes[i][4] into a FloatTensor
             key = ((unsigned long long)__float_as_uint(kf) << 32) | (unsigned)t;
         }
         keys[t] = key;
@@ -176,11 +187,17 @@ __global__ void __launch_bounds__(kDetThreads) nms_kernel(const float* __restric
     }
     for (int t = threadIdx.x; t < n; t += kDetThreads) {
         const int slot = (int)(keys[t] & 0xffffffffu);
-        const float4 v = *reinterpret_cast<const float4*>(c + (size_t)slot * kCandFloats);
-        const float det = c[(size_t)slot * kCandFloats + 4];
-        box[t] = make_double4(__ddiv_rn((double)v.x, (double)W), __ddiv_rn((double)v.y, (double)H),
-                              __ddiv_rn((double)v.z, (double)W), __ddiv_rn((double)v.w, (double)H));
-        alive[t] = det > 0.f ? 1 : 0;
+        if (c64) {
+            const double* q = c64 + (size_t)slot * 5;
+            box[t] = make_double4(q[0], q[1], q[2], q[3]);
+            alive[t] = q[4] > 0.0 ? 1 : 0;
+        } else {
+            const float4 v = *reinterpret_cast<const float4*>(c + (size_t)slot * kCandFloats);
+            const float det = c[(size_t)slot * kCandFloats + 4];
+            box[t] = make_double4(__ddiv_rn((double)v.x, (double)W), __ddiv_rn((double)v.y, (double)H),
+                                  __ddiv_rn((double)v.z, (double)W), __ddiv_rn((double)v.w, (double)H));
+            alive[t] = det > 0.f ? 1 : 0;
+        }
     }
     __syncthreads();
     for (int i = 0; i < n; ++i) {
@@ -227,6 +244,7 @@ static inline int next_pow2(int v) {
 
 }  // namespace fsdet
 
+#ifndef FSDET_HOST_EMULATION
 using namespace fsdet;
 
 extern "C" int fsdet_region_detect(const float* output, const float* anchors_f32, int N, int A, int nC, int H, int W,
@@ -246,19 +264,30 @@ extern "C" int fsdet_region_detect(const float* output, const float* anchors_f32
     return launch_status("region_detect");
 }
 
-extern "C" int fsdet_nms(const float* cand, const int32_t* count, int N, int cap, int H, int W, double nms_thresh,
-                         int32_t* keep, int32_t* keep_count, void* stream) {
-    FSDET_CHECK_ARG(cand && count && keep && keep_count, "nms: null pointer");
-    FSDET_CHECK_ARG(aligned16(cand), "nms: cand must be 16-byte aligned");
-    FSDET_CHECK_ARG(cap > 0 && cap <= 4096, "nms: %d candidates per row (max 4096)", cap);
+static int launch_nms(const float* cand, const double* boxes64, const int32_t* count, int N, int cap, int H, int W,
+                      double nms_thresh, int32_t* keep, int32_t* keep_count, void* stream) {
+    FSDET_CHECK_ARG((cand || boxes64) && count && keep && keep_count, "nms: null pointer");
+    FSDET_CHECK_ARG(!cand || aligned16(cand), "nms: cand must be 16-byte aligned");
+    FSDET_CHECK_ARG(cap > 0 && cap <= 4096, "nms: %d candidates per row (1..4096)", cap);
     FSDET_CHECK_ARG(H > 0 && W > 0 && N >= 0, "nms: bad shape");
     if (N == 0) return 0;
     const int P = next_pow2(cap);
     const size_t smem = (size_t)P * (sizeof(double4) + sizeof(unsigned long long) + 1);
     cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("nms: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-    nms_kernel<<<N, kDetThreads, smem, (cudaStream_t)stream>>>(cand, count, cap, P, H, W, nms_thresh, keep, keep_count);
+    nms_kernel<<<N, kDetThreads, smem, (cudaStream_t)stream>>>(cand, boxes64, count, cap, P, H, W, nms_thresh, keep,
+                                                               keep_count);
     return launch_status("nms");
+}
+
+extern "C" int fsdet_nms(const float* cand, const int32_t* count, int N, int cap, int H, int W, double nms_thresh,
+                         int32_t* keep, int32_t* keep_count, void* stream) {
+    return launch_nms(cand, nullptr, count, N, cap, H, W, nms_thresh, keep, keep_count, stream);
+}
+
+extern "C" int fsdet_nms_boxes64(const double* boxes, const int32_t* count, int N, int cap, double nms_thresh,
+                                 int32_t* keep, int32_t* keep_count, void* stream) {
+    return launch_nms(nullptr, boxes, count, N, cap, 1, 1, nms_thresh, keep, keep_count, stream);
 }
 
 extern "C" int fsdet_rw_running_mean(float* enews, const int32_t* cnt_in, int32_t* cnt_out, const float* dw,
@@ -270,3 +299,4 @@ extern "C" int fsdet_rw_running_mean(float* enews, const int32_t* cnt_in, int32_
     rw_running_mean_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(enews, cnt_in, cnt_out, dw, ids, n, n_cls, C);
     return launch_status("rw_running_mean");
 }
+#endif  // FSDET_HOST_EMULATION

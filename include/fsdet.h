@@ -283,6 +283,10 @@ int fsdet_region_detect(const float* output, const float* anchors_f32 /* [2A] */
  * cap = candidates per row of `cand` (<= 4096). */
 int fsdet_nms(const float* cand, const int32_t* count, int N, int cap, int H, int W, double nms_thresh, int32_t* keep,
               int32_t* keep_count, void* stream);
+/* Same for rows of already-normalised float64 boxes [N][cap][5] = {x, y, w, h, det_conf}: the list-of-lists form in
+ * which utils.nms (utils.py:85) receives boxes from any caller (e.g. utils.do_detect, utils.py:410-458). */
+int fsdet_nms_boxes64(const double* boxes, const int32_t* count, int N, int cap, double nms_thresh, int32_t* keep,
+                      int32_t* keep_count, void* stream);
 /* Running mean of the support net's reweighting vectors per class, valid_ensemble.py:86-100:
  * for i in 0..n-1: c = ids[i]; enews[c] = enews[c]*cnt[c]/(cnt[c]+1) + dw[i]/(cnt[c]+1); cnt[c] += 1 (float32, the
  * reference's operation order).  enews float32 [n_cls][C] (zero before the first call), dw float32 [n][C];

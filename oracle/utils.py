@@ -92,17 +92,40 @@ def _collect(batch, h, w, nA, nC, xs, ys, ws, hs, det, cmax, cid, cls_confs, con
     return all_boxes
 
 
+def region_arrays(output, num_classes, anchors, num_anchors, n_models=None):
+    """The float32 tensors both decode functions compute before their triple loop, flat in the reference's
+    `ind = b*A*HW + a*HW + cy*W + cx` order: (xs, ys, ws, hs, det_confs, cls_max_confs, cls_max_ids, cls_confs).
+    n_models=None: get_region_boxes (utils.py:121-143); else get_region_boxes_v2 (utils.py:211-243)."""
+    output = torch.as_tensor(output, dtype=torch.float32)
+    if output.dim() == 3:
+        output = output.unsqueeze(0)
+    batch, ch, h, w = output.shape
+    nA, nC = num_anchors, num_classes
+    assert ch == (5 + nC) * nA
+    o, xs, ys, ws, hs, det = _decode(output, anchors, nA)
+    if n_models is None:
+        cls_confs = torch.softmax(o[5:5 + nC].transpose(0, 1), dim=1)
+    else:
+        cs = n_models
+        assert batch % cs == 0
+        bs = batch // cs
+        cls = output.view(batch, nA, 5 + nC, h, w)[:, :, 5:5 + nC].squeeze()
+        cls = cls.reshape(bs, cs, nA * nC * h * w).transpose(1, 2).contiguous().view(bs * nA * nC * h * w, cs)
+        cls = torch.softmax(cls, dim=1)
+        cls_confs = cls.view(bs, nA * nC * h * w, cs).transpose(1, 2).contiguous().view(bs * cs * nA, nC, h * w) \
+            .transpose(1, 2).reshape(bs * cs * nA * h * w, nC)
+    cmax, cid = torch.max(cls_confs, 1)
+    return xs, ys, ws, hs, det, cmax.view(-1), cid.view(-1), cls_confs
+
+
 def get_region_boxes(output, conf_thresh, num_classes, anchors, num_anchors, only_objectness=1, validation=False):
     """utils.py:112-193 (plain detector: softmax over the nC class logits of each anchor-cell)."""
     output = torch.as_tensor(output, dtype=torch.float32)
     if output.dim() == 3:
         output = output.unsqueeze(0)
     batch, ch, h, w = output.shape
-    assert ch == (5 + num_classes) * num_anchors
-    o, xs, ys, ws, hs, det = _decode(output, anchors, num_anchors)
-    cls_confs = torch.softmax(o[5:5 + num_classes].transpose(0, 1), dim=1)
-    cmax, cid = torch.max(cls_confs, 1)
-    return _collect(batch, h, w, num_anchors, num_classes, xs, ys, ws, hs, det, cmax.view(-1), cid.view(-1), cls_confs,
+    xs, ys, ws, hs, det, cmax, cid, cls_confs = region_arrays(output, num_classes, anchors, num_anchors)
+    return _collect(batch, h, w, num_anchors, num_classes, xs, ys, ws, hs, det, cmax, cid, cls_confs,
                     conf_thresh, only_objectness, validation)
 
 
@@ -114,18 +137,8 @@ def get_region_boxes_v2(output, n_models, conf_thresh, num_classes, anchors, num
     if output.dim() == 3:
         output = output.unsqueeze(0)
     batch, ch, h, w = output.shape
-    nA, nC, cs = num_anchors, num_classes, n_models
-    assert ch == (5 + nC) * nA
-    assert batch % cs == 0
-    bs = batch // cs
-    cls = output.view(batch, nA, 5 + nC, h, w)[:, :, 5:5 + nC].squeeze()
-    cls = cls.reshape(bs, cs, nA * nC * h * w).transpose(1, 2).contiguous().view(bs * nA * nC * h * w, cs)
-    cls = torch.softmax(cls, dim=1)
-    cls_confs = cls.view(bs, nA * nC * h * w, cs).transpose(1, 2).contiguous().view(bs * cs * nA, nC, h * w) \
-        .transpose(1, 2).reshape(bs * cs * nA * h * w, nC)
-    o, xs, ys, ws, hs, det = _decode(output, anchors, nA)
-    cmax, cid = torch.max(cls_confs, 1)
-    return _collect(batch, h, w, nA, nC, xs, ys, ws, hs, det, cmax.view(-1), cid.view(-1), cls_confs,
+    xs, ys, ws, hs, det, cmax, cid, cls_confs = region_arrays(output, num_classes, anchors, num_anchors, n_models)
+    return _collect(batch, h, w, num_anchors, num_classes, xs, ys, ws, hs, det, cmax, cid, cls_confs,
                     conf_thresh, only_objectness, validation)
 
 
