@@ -373,6 +373,25 @@ def main():
     torch.cuda.synchronize()
     bt_gpu_ms = e0.elapsed_time(e1) / 20
 
+    # ---- evaluation decode + NMS: head output -> thresholded candidates -> NMS survivors for all
+    # B*n_cls (image, class) rows, device resident (valid_ensemble.py:145-162 does this in Python loops on the host)
+    from fewshot_detection_b200.utils import region_detections
+    gdet = torch.Generator().manual_seed(5)
+    head = torch.randn(nB, 30, G, G, generator=gdet)
+    head.view(nB, 5, 6, G, G)[:, :, 4] -= 2.0
+    head_dev = head.to(dev)
+    for _ in range(2):
+        dets = region_detections(head_dev, 0.005, 1, anchors, 5, 0, 1, n_models=ncls).nms(0.45)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        dets = region_detections(head_dev, 0.005, 1, anchors, 5, 0, 1, n_models=ncls).nms(0.45)
+    e1.record()
+    torch.cuda.synchronize()
+    det_gpu_ms = e0.elapsed_time(e1) / 10
+    det_kept = int(dets.keep_count.sum().item())
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -380,6 +399,7 @@ def main():
 
     cpu_baseline = None
     bt_cpu_ms = None
+    det_cpu_ms = None
     if world == 1 and not args.no_cpu_baseline:
         threads = cpu_threads()
         cstep, cstate = cpu_step_factory(ncls, side, args.ref_batch, threads)
@@ -393,6 +413,13 @@ def main():
                                   'port: torch-CPU ops + Python build_targets); %d of %d host cores used, see cpu_threads()'
                                   % (args.ref_batch, ncls, side, side, threads, os.cpu_count() or 1)}
         bt_cpu_ms = cpu_build_targets_ms(B, ncls, G)
+        # decode + NMS of ONE image's n_cls rows with the oracle port (Python loops, as the reference's)
+        from oracle import utils as OU
+        t0 = time.perf_counter()
+        ob = OU.get_region_boxes_v2(head[:ncls], ncls, 0.005, 1, anchors, 5, 0, 1)
+        for row in ob:
+            OU.nms(row, 0.45)
+        det_cpu_ms = (time.perf_counter() - t0) * 1e3
 
     line = {
         'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -412,6 +439,9 @@ def main():
         'roofline': roofline,
         'cpu_baseline': cpu_baseline,
         'build_targets_ms': {'gpu': bt_gpu_ms, 'cpu_oracle': bt_cpu_ms, 'rows': nB, 'grid': G},
+        'detect_nms_ms': {'gpu': det_gpu_ms, 'rows': nB, 'survivors': det_kept, 'cpu_oracle_one_image': det_cpu_ms,
+                          'cpu_rows': ncls, 'note': 'decode + threshold 0.005 + NMS 0.45 of all (image, class) rows; the CPU '
+                                                    'figure is the oracle port on the first image only (n_cls rows)'},
     }
     print(json.dumps(line))
     if world > 1:

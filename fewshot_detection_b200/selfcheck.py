@@ -50,4 +50,13 @@ def smoke_check():
         d = (p.grad.detach().cpu().contiguous().double() - q.grad.double()).norm() / max(q.grad.double().norm().item(), 1e-30)
         worst = max(worst, d.item())
     assert worst < 1e-3, ('gradient mismatch vs oracle', worst)
-    print('smoke ok: loss %.6f (oracle %.6f), worst grad rel err %.2e' % (loss.item(), lo.item(), worst))
+    # evaluation decode + NMS of the same head output (csrc/detect.cu) vs the oracle's Python loops
+    from fewshot_detection_b200 import utils as U
+    from oracle import utils as OU
+    kept = U.region_detections(out.detach(), 0.005, 1, m.anchors, 5, 0, 1, n_models=cs).kept_boxes(0.45)
+    want = [OU.nms(r, 0.45) for r in OU.get_region_boxes_v2(out.detach().cpu(), cs, 0.005, 1, om.anchors, 5, 0, 1)]
+    assert len(kept) == len(want) == bs * cs
+    assert sum(abs(len(a) - len(b)) for a, b in zip(kept, want)) <= 1, ('NMS survivors differ from the oracle',
+                                                                        [len(a) for a in kept], [len(b) for b in want])
+    print('smoke ok: loss %.6f (oracle %.6f), worst grad rel err %.2e, %d NMS survivors'
+          % (loss.item(), lo.item(), worst, sum(len(a) for a in kept)))
