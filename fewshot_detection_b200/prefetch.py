@@ -1,0 +1,58 @@
+"""Host -> device input staging for the training loop (the `data.cuda()` of train_meta.py:209-213, pipelined).
+
+The reference copies each batch synchronously right before the forward pass (`data, metax, mask = data.cuda(),
+metax.cuda(), mask.cuda()`), so the PCIe transfer of step i (190 MB at config 2, ~3.5 ms) is serial with its compute.
+`DevicePrefetcher` issues the copy of batch i+1 on a side stream while step i runs; the training stream only waits on
+an event.  Host tensors should be pinned (DataLoader(pin_memory=True), train_meta.py:107) for the copy to be
+asynchronous.  `host_fields` stay on the host untouched (the float64 target, which RegionLoss takes as a CPU tensor,
+train_meta.py:211)."""
+import torch
+
+
+class DevicePrefetcher(object):
+    def __init__(self, batches, device, host_fields=()):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise TypeError('DevicePrefetcher stages batches for a CUDA device')
+        self.host_fields = set(host_fields)
+        self.stream = torch.cuda.Stream(self.device)
+        self.h2d_bytes = 0
+        self._next = None
+        self._event = None
+        self._preload()
+
+    def _preload(self):
+        try:
+            batch = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        out = []
+        with torch.cuda.stream(self.stream):
+            for i, t in enumerate(batch):
+                if i in self.host_fields or not torch.is_tensor(t):
+                    out.append(t)
+                else:
+                    out.append(t.to(self.device, non_blocking=True))
+                    self.h2d_bytes += t.numel() * t.element_size()
+        self._event = torch.cuda.Event()
+        self._event.record(self.stream)
+        self._next = tuple(out)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._next is None:
+            raise StopIteration
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self._event)
+        batch = self._next
+        for t in batch:
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(cur)   # allocated on the copy stream, consumed on the training stream
+        self._preload()
+        return batch
+
+    next = __next__
