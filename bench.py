@@ -263,13 +263,15 @@ def main():
 
     host_ms = {}
 
-    def timed(fn, steps, tag=None):
+    def timed(fn, steps, tag=None, flush=None):
         sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
         for i in range(steps):
             fn(i)
+        if flush is not None:
+            flush()
         e1.record()
         if tag:
             host_ms[tag] = (time.perf_counter() - t0) * 1e3 / steps   # host-side enqueue time per step
@@ -350,15 +352,24 @@ def main():
     # serially in train_meta.py:209-213), the float64 target stays on the host (train_meta.py:211) and is uploaded
     # inside the loss, and the loss is read back to the host.  The prefetcher is primed before the timed region,
     # so the region contains exactly `steps` input copies (those of batches 2..steps+1).
-    from fewshot_detection_b200.prefetch import DevicePrefetcher
+    # The loss of every step is read back to the host (AsyncLossReader: a 4-byte copy into pinned memory behind the
+    # step, consumed one step late so that the launch of step i+1 does not wait for step i; the last value is
+    # drained inside the timed region).
+    from fewshot_detection_b200.prefetch import DevicePrefetcher, AsyncLossReader
     pf = DevicePrefetcher((host[i % 2] for i in range(args.steps + 2)), dev, host_fields=(3,))
+    reader = AsyncLossReader(depth=2)
+    e2e_losses = []
 
     def e2e_step(i):
         x, metax, mask, tgt = next(pf)
         loss = step(x, metax, mask, tgt)
-        return loss.item()                    # device -> host read of the step's result
+        reader.push(loss)                     # device -> host read of the step's result ...
+        if reader.count == 2:
+            e2e_losses.append(reader.pop())   # ... consumed while the next step is already queued
     e2e_step(0)
-    ms_e2e = timed(e2e_step, args.steps)
+    e2e_losses.extend(reader.drain())
+    ms_e2e = timed(e2e_step, args.steps, flush=lambda: e2e_losses.extend(reader.drain()))
+    assert len(e2e_losses) == args.steps + 1 and all(np.isfinite(v) for v in e2e_losses)
     e2e_value = global_batch * args.steps / (ms_e2e / 1e3)
 
     # ---- build_targets ms/batch (decode output -> 9 target tensors + counters, device resident)
@@ -439,7 +450,8 @@ def main():
                          % (B * 105e6 / 1e9)},
         'e2e': {'value': e2e_value, 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
-                'input_staging': 'pinned host -> device on a copy stream, one batch ahead (prefetch.DevicePrefetcher)'},
+                'input_staging': 'pinned host -> device on a copy stream, one batch ahead (prefetch.DevicePrefetcher)',
+                'loss_readback': 'every step, 4 bytes into pinned memory, read one step late (prefetch.AsyncLossReader)'},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': roofline,

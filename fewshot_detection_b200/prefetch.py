@@ -56,3 +56,41 @@ class DevicePrefetcher(object):
         return batch
 
     next = __next__
+
+
+class AsyncLossReader(object):
+    """Device -> host read-back of per-step scalars (the loss train_meta.py:221-223 logs) without stalling the launch
+    of the next step: `push(loss)` enqueues a 4-byte copy into pinned memory behind the step, `pop()` returns the
+    oldest outstanding value (blocking only on ITS event).  With depth 2 the training loop reads step i-1's loss
+    while step i is already running, so the GPU never idles waiting for the host."""
+
+    def __init__(self, depth=2):
+        self.depth = depth
+        self.buf = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.ev = [torch.cuda.Event() for _ in range(depth)]
+        self.head = 0      # next slot to pop
+        self.count = 0     # outstanding values
+
+    def push(self, loss):
+        if self.count == self.depth:
+            raise RuntimeError('AsyncLossReader: %d values outstanding, pop() first' % self.count)
+        slot = (self.head + self.count) % self.depth
+        self.buf[slot].copy_(loss.detach().reshape(1), non_blocking=True)
+        self.ev[slot].record()
+        self.count += 1
+
+    def pop(self):
+        if self.count == 0:
+            raise IndexError('AsyncLossReader: nothing outstanding')
+        slot = self.head
+        self.ev[slot].synchronize()
+        v = float(self.buf[slot][0])
+        self.head = (self.head + 1) % self.depth
+        self.count -= 1
+        return v
+
+    def drain(self):
+        out = []
+        while self.count:
+            out.append(self.pop())
+        return out

@@ -73,3 +73,23 @@ def test_device_prefetcher_order_values_and_host_fields():
         next(pf)
     with pytest.raises(TypeError):
         DevicePrefetcher(host, 'cpu')
+
+
+def test_async_loss_reader_values_in_order():
+    from fewshot_detection_b200.prefetch import AsyncLossReader
+    r = AsyncLossReader(depth=2)
+    static = torch.zeros((), device='cuda')          # a graph's static loss tensor is overwritten every step
+    got = []
+    for i in range(7):
+        static.fill_(float(i) + 0.5)
+        r.push(static)
+        if r.count == 2:
+            got.append(r.pop())
+    got += r.drain()
+    assert got == [i + 0.5 for i in range(7)]
+    with pytest.raises(IndexError):
+        r.pop()
+    r.push(static)
+    r.push(static)
+    with pytest.raises(RuntimeError):
+        r.push(static)
