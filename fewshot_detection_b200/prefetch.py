@@ -2,14 +2,21 @@
 
 The reference copies each batch synchronously right before the forward pass (`data, metax, mask = data.cuda(),
 metax.cuda(), mask.cuda()`), so the PCIe transfer of step i (190 MB at config 2, ~3.5 ms) is serial with its compute.
-`DevicePrefetcher` issues the copy of batch i+1 on a side stream while step i runs; the training stream only waits on
-an event.  Host tensors should be pinned (DataLoader(pin_memory=True), train_meta.py:107) for the copy to be
+`DevicePrefetcher` issues the copy of batch i+1 on a side stream (into reused staging buffers) while step i runs; the
+training stream only waits on an event.  Host tensors should be pinned (DataLoader(pin_memory=True), train_meta.py:107) for the copy to be
 asynchronous.  `host_fields` stay on the host untouched (the float64 target, which RegionLoss takes as a CPU tensor,
 train_meta.py:211)."""
 import torch
 
 
 class DevicePrefetcher(object):
+    """Iterator over device copies of host batches (tuples of tensors), one batch ahead.
+
+    Two fixed sets of device staging buffers are reused (no allocator traffic in steady state): while the training
+    stream consumes slot k, the copy stream fills slot k^1; events order both directions.  A batch handed out by
+    `next()` therefore stays valid until the FOLLOWING `next()` call (its slot is refilled after everything the
+    training stream had queued by then)."""
+
     def __init__(self, batches, device, host_fields=()):
         self.it = iter(batches)
         self.device = torch.device(device)
@@ -18,26 +25,42 @@ class DevicePrefetcher(object):
         self.host_fields = set(host_fields)
         self.stream = torch.cuda.Stream(self.device)
         self.h2d_bytes = 0
+        self._slots = [None, None]                 # per slot: list of device buffers (None for host fields)
+        self._ready = [torch.cuda.Event(), torch.cuda.Event()]   # recorded on the copy stream: slot filled
+        self._free = [None, None]                  # recorded on the training stream: slot may be overwritten
+        self._k = 0                                # slot holding the batch the next `next()` returns
         self._next = None
-        self._event = None
-        self._preload()
+        self._preload(0)
 
-    def _preload(self):
+    def _preload(self, slot):
         try:
             batch = next(self.it)
         except StopIteration:
             self._next = None
             return
+        bufs = self._slots[slot]
+        fresh = bufs is None or len(bufs) != len(batch)
+        if fresh:
+            bufs = [None] * len(batch)
         out = []
+        main = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self.stream):
+            if self._free[slot] is not None:
+                self.stream.wait_event(self._free[slot])
             for i, t in enumerate(batch):
                 if i in self.host_fields or not torch.is_tensor(t):
                     out.append(t)
-                else:
-                    out.append(t.to(self.device, non_blocking=True))
-                    self.h2d_bytes += t.numel() * t.element_size()
-        self._event = torch.cuda.Event()
-        self._event.record(self.stream)
+                    continue
+                b = bufs[i]
+                if b is None or b.shape != t.shape or b.dtype != t.dtype:
+                    b = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+                    b.record_stream(main)          # consumed on the training stream: keep the allocator informed
+                    bufs[i] = b
+                b.copy_(t, non_blocking=True)
+                self.h2d_bytes += t.numel() * t.element_size()
+                out.append(b)
+            self._ready[slot].record(self.stream)
+        self._slots[slot] = bufs
         self._next = tuple(out)
 
     def __iter__(self):
@@ -47,12 +70,15 @@ class DevicePrefetcher(object):
         if self._next is None:
             raise StopIteration
         cur = torch.cuda.current_stream(self.device)
-        cur.wait_event(self._event)
+        k = self._k
+        cur.wait_event(self._ready[k])
         batch = self._next
-        for t in batch:
-            if torch.is_tensor(t) and t.is_cuda:
-                t.record_stream(cur)   # allocated on the copy stream, consumed on the training stream
-        self._preload()
+        # everything queued so far on the training stream may still read the other slot (the previous batch)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._free[k ^ 1] = ev
+        self._k = k ^ 1
+        self._preload(k ^ 1)
         return batch
 
     next = __next__

@@ -60,14 +60,17 @@ def test_device_prefetcher_order_values_and_host_fields():
              torch.rand(4, 2, 250, generator=g, dtype=torch.float64), i) for i in range(5)]
     pf = DevicePrefetcher(host, 'cuda', host_fields=(2,))
     seen = 0
+    ptrs = set()
     for i, (a, b, t, k) in enumerate(pf):
         assert a.is_cuda and b.is_cuda and not t.is_cuda and k == i
+        ptrs.add(a.data_ptr())
         y = (a * 2).sum() + b.sum()                                    # consume on the current stream
         want = (host[i][0].double() * 2).sum() + host[i][1].double().sum()
         assert abs(y.item() - want.item()) < 1e-2
         assert t is host[i][2]
         seen += 1
     assert seen == 5
+    assert len(ptrs) == 2                                              # two staging slots, reused
     assert pf.h2d_bytes == sum(h[0].numel() * 4 + h[1].numel() * 4 for h in host)
     with pytest.raises(StopIteration):
         next(pf)
