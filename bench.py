@@ -349,14 +349,16 @@ def main():
     # ---- end-to-end through the public API with HOST buffers (e2e)
     # Every step: the step's inputs travel from pinned host memory to the device (DevicePrefetcher: the copy of
     # batch i+1 is issued on a side stream while step i computes - what DataLoader(pin_memory=True) + .cuda() does
-    # serially in train_meta.py:209-213), the float64 target stays on the host (train_meta.py:211) and is uploaded
-    # inside the loss, and the loss is read back to the host.  The prefetcher is primed before the timed region,
-    # so the region contains exactly `steps` input copies (those of batches 2..steps+1).
+    # serially in train_meta.py:209-213); the float64 target travels with them (the reference keeps it on the host
+    # because its build_targets runs there; RegionLoss here takes either).  It must NOT be uploaded on the training
+    # stream: a small H2D copy queued behind the 190 MB prefetch on the same copy engine delays the step by the whole
+    # transfer (measured with tools/e2e_probe.py: +2.9 ms/step).  The prefetcher is primed before the timed region,
+    # so the region contains exactly `steps` input copies.
     # The loss of every step is read back to the host (AsyncLossReader: a 4-byte copy into pinned memory behind the
     # step, consumed one step late so that the launch of step i+1 does not wait for step i; the last value is
     # drained inside the timed region).
     from fewshot_detection_b200.prefetch import DevicePrefetcher, AsyncLossReader
-    pf = DevicePrefetcher((host[i % 2] for i in range(args.steps + 4)), dev, host_fields=(3,))
+    pf = DevicePrefetcher((host[i % 2] for i in range(args.steps + 4)), dev)
     reader = AsyncLossReader(depth=2)
     e2e_losses = []
 
