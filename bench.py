@@ -346,6 +346,27 @@ def main():
                             'Per-kernel times are CUDA-event timed eager launches in this run (the timed region '
                             'replays the same kernels from a CUDA graph)'}
 
+    # Whole-step rooflines: the north star asks for images/s as a fraction of the conv-stack HBM roofline
+    # (fused algorithmic bytes: every layer reads its input and writes its output once, x3 for a training step, + 8
+    # passes over the 265 MB of parameters) next to the tensor-pipe figure of the MMA layers.
+    step_rooflines = None
+    try:
+        if side == 416:
+            hbm_gbs = float(peaks.get('hbm_gbs', 6577.7))
+            alg_bytes = 3.0 * (B * 100.7e6 + ncls * 57.4e6) + 8 * 265.2e6
+            alg_flops = 3.0 * (B * 29.48e9 + ncls * 9.05e9)
+            t = ms / args.steps / 1e3
+            step_rooflines = {
+                'hbm': {'algorithmic_bytes_per_step_per_gpu': alg_bytes, 'achieved_GBps': alg_bytes / t / 1e9,
+                        'peak_GBps': hbm_gbs, 'frac': alg_bytes / t / 1e9 / hbm_gbs, 'floor_ms': alg_bytes / hbm_gbs / 1e6},
+                'tensor': {'algorithmic_flops_per_step_per_gpu': alg_flops, 'achieved_TFLOPs': alg_flops / t / 1e12,
+                           'peak_TFLOPs': peak_tf, 'frac': alg_flops / t / 1e12 / peak_tf,
+                           'note': 'fp32-equivalent arithmetic = 3 tensor-core MACs per MAC: the reachable fraction is 1/3'}}
+            if roofline is not None:
+                roofline['whole_step'] = step_rooflines
+    except Exception as e:  # never lose the bench line over a derived figure
+        sys.stderr.write('step rooflines skipped: %r\n' % (e,))
+
     # ---- end-to-end through the public API with HOST buffers (e2e)
     # Every step: the step's inputs travel from pinned host memory to the device (DevicePrefetcher: the copy of
     # batch i+1 is issued on a side stream while step i computes - what DataLoader(pin_memory=True) + .cuda() does
