@@ -68,6 +68,9 @@ SIGNATURES = {
     'fsdet_nms': ('ppiiiidppp', 'i'),
     'fsdet_nms_boxes64': ('ppiidppp', 'i'),
     'fsdet_rw_running_mean': ('pppppiiip', 'i'),
+    'fsdet_augment_workspace_bytes': ('iiii', 'z'),
+    'fsdet_augment_batch': ('pppiiiiipzpppp', 'i'),
+    'fsdet_box_masks': ('piiipp', 'i'),
 }
 
 

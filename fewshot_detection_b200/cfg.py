@@ -37,6 +37,15 @@ cfg.repeat = 1
 cfg.save_interval = 10
 cfg.multiscale = True
 cfg.metain_type = 2       # 2 = support image + mask channel (cfg.py:37-38)
+# defaults of the few-shot bookkeeping that image.fill_truth_detection(_meta) reads (cfg.py:103-145): all 20 VOC
+# classes are base classes until a .data file says otherwise
+cfg.classes = cfg.voc_classes
+cfg.base_classes = list(cfg.voc_classes)
+cfg.base_ids = list(range(len(cfg.voc_classes)))
+cfg.novel_classes = []
+cfg.novel_ids = []
+cfg.yolo_joint = False
+cfg.metaids = []
 
 
 def _configure_net(netopt):

@@ -294,6 +294,27 @@ int fsdet_nms_boxes64(const double* boxes, const int32_t* count, int N, int cap,
 int fsdet_rw_running_mean(float* enews, const int32_t* cnt_in, int32_t* cnt_out, const float* dw, const int32_t* ids,
                           int n, int n_cls, int C, void* stream);
 
+/* ---- training-input augmentation ---------------------- */
+/* image.data_augmentation (image.py:52-87: crop with zero fill, PIL resize, horizontal flip, HSV jitter through
+ * image.distort_image :19-37) + transforms.ToTensor for n images in one launch pair.
+ *   src    device array of n pointers to decoded uint8 RGB images, HWC
+ *   geom   int32 [n][8] = {ow, oh, pleft, ptop, crop_w, crop_h, flip, distort}; the reference's crop box is
+ *          (pleft, ptop, pleft + swidth - 1, ptop + sheight - 1), i.e. crop_w = swidth - 1 (image.py:72)
+ *   color  float64 [n][3] = {dhue, dsat, dexp} (image.py:45-50)
+ *   filter 0 = PIL NEAREST, 3 = PIL BICUBIC (the default of `Image.resize` before / since Pillow 7)
+ *   kmax   bound on the resampling taps per output coordinate: >= 2*ceil(2*max(crop/out, 1)) + 1
+ *   out    float32 [n][3][H][W] = the uint8 result / 255; out_u8 (optional) uint8 [n][H][W][3] = that uint8 result
+ *   status int32[1]: 0, or 1 + index of an image whose taps did not fit kmax / whose crop is empty
+ * Bit-identical to Pillow's uint8 pipeline (integer resampling with 22-bit coefficients and a rounding after each
+ * pass; Convert.c colour conversions; `point` tables rounded half-to-even). */
+size_t fsdet_augment_workspace_bytes(int n, int W, int H, int kmax);
+int fsdet_augment_batch(const uint8_t* const* src, const int32_t* geom, const double* color, int n, int W, int H,
+                        int kmax, int filter, void* workspace, size_t workspace_bytes, float* out, uint8_t* out_u8,
+                        int32_t* status, void* stream);
+/* dataset.MetaDataset.get_img_mask (dataset.py:378-398): out float32 [n][H][W] = 1 inside rects[i] = {x1, y1, x2, y2}
+ * (half-open, already rounded and clamped by the caller as the reference does), else 0. */
+int fsdet_box_masks(const int32_t* rects, int n, int H, int W, float* out, void* stream);
+
 /* ---- misc --------------------------------------------------------------- */
 int fsdet_fill(float* p, float v, size_t n, void* stream);
 

@@ -68,6 +68,7 @@ static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
 static inline unsigned __float_as_uint(float f) { unsigned v; memcpy(&v, &f, 4); return v; }
+static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 
@@ -101,5 +102,22 @@ inline void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<v
     for (auto& t : ts) t.join();
     pthread_barrier_destroy(&g_block.bar);
     for (int w = 0; w < (nthreads + 31) / 32; ++w) pthread_barrier_destroy(&g_block.warp_bar[w]);
+}
+
+// Kernels WITHOUT barriers or warp collectives: run the threads one after another (much faster).
+inline void launch_serial(dim3 grid, dim3 block, const std::function<void()>& body) {
+    blockDim = block;
+    gridDim = grid;
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+                for (unsigned tz = 0; tz < block.z; ++tz)
+                    for (unsigned ty = 0; ty < block.y; ++ty)
+                        for (unsigned tx = 0; tx < block.x; ++tx) {
+                            threadIdx.x = tx; threadIdx.y = ty; threadIdx.z = tz;
+                            body();
+                        }
+            }
 }
 }  // namespace emul
