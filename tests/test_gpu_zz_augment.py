@@ -75,7 +75,8 @@ def test_full_batch_properties():
     out, u8 = I.augment_batch(srcs, (416, 416), ps, return_uint8=True)
     torch.cuda.synchronize()
     assert tuple(out.shape) == (64, 3, 416, 416)
-    assert torch.equal(out, u8.permute(0, 3, 1, 2).float() / 255)
+    # ToTensor divides on the CPU (IEEE division); torch's CUDA tensor/scalar division multiplies by a reciprocal
+    assert torch.equal(out.cpu(), u8.cpu().permute(0, 3, 1, 2).float() / 255)
     assert 0.0 <= out.min().item() and out.max().item() <= 1.0
     k = next(i for i, p in enumerate(ps) if p['flip'])
     unflipped = dict(ps[k], flip=0)
