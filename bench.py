@@ -432,6 +432,49 @@ def main():
     det_gpu_ms = e0.elapsed_time(e1) / 10
     det_kept = int(dets.keep_count.sum().item())
 
+    # ---- training-input augmentation ms/batch: B decoded 375x500 uint8 images -> crop, PIL-exact
+    # bicubic resize, flip, HSV jitter, /255 -> [B,3,side,side] float32, device resident.  Kept LAST among the GPU work and
+    # guarded: the newest kernel must never cost the bench line.
+    aug = None
+    try:
+        import random as _random
+        from fewshot_detection_b200 import image as IMG
+        rsa = np.random.RandomState(17)
+        _random.seed(17)
+        srcs = [torch.from_numpy(rsa.randint(0, 256, (375, 500, 3)).astype(np.uint8)).to(dev) for _ in range(B)]
+        aps = [IMG.draw_augmentation(500, 375, 0.2, 0.1, 1.5, 1.5) for _ in range(B)]
+        aug_out = torch.empty(B, 3, side, side, device=dev)
+        for _ in range(2):
+            IMG.augment_batch(srcs, (side, side), aps, out=aug_out)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            IMG.augment_batch(srcs, (side, side), aps, out=aug_out)
+        a1.record()
+        torch.cuda.synchronize()
+        aug = {'gpu_ms_per_batch': a0.elapsed_time(a1) / 10, 'images': B, 'source': '375x500 uint8 RGB', 'out': side,
+               'filter': 'PIL BICUBIC', 'out_mean': float(aug_out.mean().item())}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            try:
+                from PIL import Image as _PILImage      # what the reference's worker processes run per image
+                sys.path.insert(0, ROOT)
+                from oracle import image as OIMG         # noqa: F401  (the numpy oracle is ~100x slower; PIL is the fair CPU side)
+                t0 = time.perf_counter()
+                for k in range(8):
+                    pim = _PILImage.fromarray(srcs[k].cpu().numpy(), 'RGB')
+                    p = aps[k]
+                    pim = pim.crop((p['pleft'], p['ptop'], p['pleft'] + p['cw'], p['ptop'] + p['ch'])).resize((side, side))
+                    pim = pim.convert('HSV').convert('RGB')
+                    np.asarray(pim, dtype=np.float32) / 255
+                aug['cpu_pil_ms_per_image'] = (time.perf_counter() - t0) * 1e3 / 8
+                aug['cpu_note'] = 'Pillow crop + resize + HSV round trip + ToTensor on one host core, 8 images (the reference ' \
+                                  'runs this in 10 DataLoader workers, utils.py:463)'
+            except Exception as e:
+                aug['cpu_note'] = 'Pillow timing skipped: %r' % (e,)
+    except Exception as e:
+        sys.stderr.write('augment timing skipped: %r\n' % (e,))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -481,6 +524,7 @@ def main():
         'roofline': roofline,
         'cpu_baseline': cpu_baseline,
         'build_targets_ms': {'gpu': bt_gpu_ms, 'cpu_oracle': bt_cpu_ms, 'rows': nB, 'grid': G},
+        'augment': aug,
         'detect_nms_ms': {'gpu': det_gpu_ms, 'rows': nB, 'survivors': det_kept, 'cpu_oracle_one_image': det_cpu_ms,
                           'cpu_rows': ncls, 'note': 'decode + threshold 0.005 + NMS 0.45 of all (image, class) rows; the CPU '
                                                     'figure is the oracle port on the first image only (n_cls rows)'},

@@ -5,8 +5,12 @@ the reference's hot path (bingykang/Fewshot_Detection @ /root/reference):
 `darknet_meta.Darknet.forward`, `darknet.Darknet.forward`,
 `dynamic_conv.DynamicConv2d`, `pooling.GlobalMaxPool2d`,
 `region_loss.{neg_filter, build_targets, RegionLoss, RegionLossV2}` and
-`utils.{bbox_iou, bbox_ious}`.  Each function cites the reference file:line it
-follows.
+`utils.{bbox_iou, bbox_ious}`, and of the rows SURVEY.md 8f widens into:
+`utils.{get_region_boxes, get_region_boxes_v2, nms}` + the reweight ensembling
+and result-line format of valid_ensemble.py (oracle/utils.py), and
+`image.data_augmentation` with Pillow's uint8 resize / HSV / point algorithms
+restated in numpy (oracle/image.py).  Each function cites the reference
+file:line it follows.
 
 Who may import it: `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` /
 `--impl reference` legs of `bench.py` — as the checker or as the timed CPU
@@ -28,5 +32,8 @@ the reference's own `region_loss.py`, `darknet_meta.py`, `darknet.py`,
 (made runnable under Py3/torch-2 by in-memory mechanical substitutions listed in
 that script) and writes tests/golden/*.npz; tests/test_oracle_golden.py checks
 every oracle function against those files (bit-exact for masks / indices /
-counters / float32 IoUs, <=1e-6 relative for float tensors).
+counters / float32 IoUs, <=1e-6 relative for float tensors).  Likewise
+make_golden_detect.py -> detect.npz (tests/test_oracle_detect.py, bit-exact)
+and make_golden_augment.py -> augment.npz (the reference's image.py runs
+unmodified under Pillow 12.2; tests/test_oracle_augment.py, bit-exact).
 """
