@@ -458,8 +458,6 @@ def main():
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             try:
                 from PIL import Image as _PILImage      # what the reference's worker processes run per image
-                sys.path.insert(0, ROOT)
-                from oracle import image as OIMG         # noqa: F401  (the numpy oracle is ~100x slower; PIL is the fair CPU side)
                 t0 = time.perf_counter()
                 for k in range(8):
                     pim = _PILImage.fromarray(srcs[k].cpu().numpy(), 'RGB')
@@ -530,8 +528,12 @@ def main():
                                                     'figure is the oracle port on the first image only (n_cls rows)'},
     }
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception as e:
+            sys.stderr.write('destroy_process_group: %r\n' % (e,))
 
 
 if __name__ == '__main__':

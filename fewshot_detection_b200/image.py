@@ -130,7 +130,8 @@ def augment_batch(images, shape, params, filter=None, device=None, out=None, ret
     if out is None:
         out = torch.empty(n, 3, H, W, dtype=torch.float32, device=device)
     else:
-        assert out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == (n, 3, H, W) and out.is_contiguous()
+        assert out.device.type == device.type and out.dtype == torch.float32 and tuple(out.shape) == (n, 3, H, W) \
+            and out.is_contiguous()
     u8 = torch.empty(n, H, W, 3, dtype=torch.uint8, device=device) if return_uint8 else None
     call('fsdet_augment_batch', ptr(ptrs), ptr(geom_d), ptr(color_d), n, W, H, kmax, int(filter), ptr(ws), ws_bytes,
          ptr(out), ptr(u8), ptr(status), _st())

@@ -203,3 +203,48 @@ def test_box_masks_and_rects(emul):
         want = np.zeros((h, w), dtype=np.float32)
         want[y1:y2, x1:x2] = 1
         assert np.array_equal(out[i], want)
+
+
+def test_python_glue_of_augment_batch_through_the_emulated_entry_point(emul, gold, monkeypatch):
+    """image.augment_batch / data_augmentation / load_data_detection end to end on CPU tensors: the C-ABI call is
+    redirected to the host-emulated kernels with the SAME argument list (pointer table, geom / color tables, workspace
+    split), so argument order, dtypes and shapes of the real call are what is being tested."""
+    import torch
+    from fewshot_detection_b200 import image as I
+
+    def fake_call(name, *a):
+        assert name == 'fsdet_augment_batch'
+        src, geom, color, n, W, H, kmax, filt, ws, ws_bytes, out, out_u8, status, stream = a
+        L = max(W, H)
+        tbytes = n * 2 * L * (2 + kmax) * 4
+        assert ws_bytes >= tbytes + n * 768
+        emul.emul_augment_batch(ctypes.c_void_p(src), ctypes.c_void_p(geom), ctypes.c_void_p(color), n, W, H, kmax, filt,
+                                ctypes.c_void_p(ws), ctypes.c_void_p(ws + tbytes), ctypes.c_void_p(out),
+                                ctypes.c_void_p(out_u8) if out_u8 else None, ctypes.c_void_p(status))
+        return 0
+    monkeypatch.setattr(I, 'call', fake_call)
+    monkeypatch.setattr(I, '_st', lambda: None)
+    monkeypatch.setattr(torch.cuda, 'is_available', lambda: True)
+    for tag in ('a', 'd', 'f'):
+        W, H, seed, flag = [int(v) for v in gold[tag + '/args']]
+        random.seed(seed)
+        src = gold[tag + '/src']
+        p = I.draw_augmentation(src.shape[1], src.shape[0], 0.2, 0.1, 1.5, 1.5) if flag else \
+            I.identity_augmentation(src.shape[1], src.shape[0])
+        out, u8 = I.augment_batch([src], (W, H), [p], device='cpu', return_uint8=True)
+        assert np.array_equal(u8[0].numpy(), gold[tag + '/img'])
+        want = np.ascontiguousarray((gold[tag + '/img'].astype(np.float32) / np.float32(255)).transpose(2, 0, 1))
+        assert np.array_equal(out[0].numpy(), want)
+    # a batch of three differently sized sources into a caller-provided output
+    srcs, ps = [], []
+    for tag in ('a', 'f', 'c'):
+        random.seed(int(gold[tag + '/args'][2]))
+        s = gold[tag + '/src']
+        srcs.append(torch.from_numpy(s))
+        ps.append(I.draw_augmentation(s.shape[1], s.shape[0], 0.2, 0.1, 1.5, 1.5))
+    dst = torch.full((3, 3, 64, 64), -1.0)
+    I.augment_batch(srcs, (64, 64), ps, device='cpu', out=dst)
+    for i, tag in enumerate(('a', 'f')):
+        want = np.ascontiguousarray((gold[tag + '/img'].astype(np.float32) / np.float32(255)).transpose(2, 0, 1))
+        assert np.array_equal(dst[i].numpy(), want)
+    assert dst[2].min() >= 0
