@@ -37,6 +37,10 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _default_device():
+    return torch.device('cuda', torch.cuda.current_device())
+
+
 def rand_scale(s):
     """image.py:39-43."""
     scale = random.uniform(1, s)
@@ -114,7 +118,7 @@ def augment_batch(images, shape, params, filter=None, device=None, out=None, ret
     draw_augmentation / identity_augmentation).  shape = (W, H) like the reference's `shape` argument."""
     if not torch.cuda.is_available():
         raise RuntimeError('augment_batch runs on the GPU only (no CPU fallback)')
-    device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    device = _default_device() if device is None else torch.device(device)
     filter = DEFAULT_FILTER if filter is None else filter
     W, H = int(shape[0]), int(shape[1])
     n = len(images)
@@ -295,7 +299,7 @@ def box_masks(boxes, w, h, device=None):
     (the reference returns mask=None for those and re-draws the support image; see `mask_rect`)."""
     if not torch.cuda.is_available():
         raise RuntimeError('box_masks runs on the GPU only (no CPU fallback)')
-    device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    device = _default_device() if device is None else torch.device(device)
     n = len(boxes)
     rects = np.array([mask_rect(b, w, h) for b in boxes], dtype=np.int32).reshape(n, 4)
     out = torch.empty(n, 1, h, w, dtype=torch.float32, device=device)
