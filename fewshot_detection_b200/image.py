@@ -259,7 +259,7 @@ def load_label(labpath, w, h, flip, dx, dy, sx, sy):
 def _decode(img):
     if isinstance(img, str):
         from PIL import Image            # host JPEG decode, as the reference (image.py:240)
-        return np.asarray(Image.open(img).convert('RGB'))
+        return np.array(Image.open(img).convert('RGB'))
     return img
 
 
