@@ -322,6 +322,7 @@ __global__ void loss_total_kernel(double* losses) {
 
 }  // namespace fsdet
 
+#ifndef FSDET_HOST_EMULATION  // tools/host_emul compiles the kernels above with g++ for CPU logic tests
 using namespace fsdet;
 
 extern "C" int fsdet_region_decode(const float* output, const int32_t* inds, int nB, int A, int nC, int H, int W,
@@ -394,3 +395,4 @@ extern "C" int fsdet_region_loss_grad(const float* output, float* grad_output, c
     loss_total_kernel<<<1, 1, 0, s>>>(losses);
     return launch_status("region_loss_total");
 }
+#endif  // FSDET_HOST_EMULATION

@@ -35,6 +35,7 @@ struct Block {
     pthread_barrier_t bar;
     pthread_barrier_t warp_bar[kMaxThreads / 32];
     unsigned warp_flags[kMaxThreads / 32][32];
+    uint64_t warp_vals[kMaxThreads / 32][32];
 };
 extern Block g_block;
 extern unsigned char* g_dyn_smem;
@@ -69,6 +70,52 @@ static inline float __int_as_float(int v) { float f; memcpy(&f, &v, 4); return f
 static inline int __float_as_int(float f) { int v; memcpy(&v, &f, 4); return v; }
 static inline unsigned __float_as_uint(float f) { unsigned v; memcpy(&v, &f, 4); return v; }
 static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline double atomicAdd(double* p, double v) {   // CAS loop, like pre-sm_60 devices
+    uint64_t old_bits, new_bits;
+    double old;
+    do {
+        old_bits = __atomic_load_n(reinterpret_cast<uint64_t*>(p), __ATOMIC_SEQ_CST);
+        memcpy(&old, &old_bits, 8);
+        const double nv = old + v;
+        memcpy(&new_bits, &nv, 8);
+    } while (!__atomic_compare_exchange_n(reinterpret_cast<uint64_t*>(p), &old_bits, new_bits, false, __ATOMIC_SEQ_CST,
+                                          __ATOMIC_SEQ_CST));
+    return old;
+}
+static inline float atomicAdd(float* p, float v) {
+    uint32_t old_bits, new_bits;
+    float old;
+    do {
+        old_bits = __atomic_load_n(reinterpret_cast<uint32_t*>(p), __ATOMIC_SEQ_CST);
+        memcpy(&old, &old_bits, 4);
+        const float nv = old + v;
+        memcpy(&new_bits, &nv, 4);
+    } while (!__atomic_compare_exchange_n(reinterpret_cast<uint32_t*>(p), &old_bits, new_bits, false, __ATOMIC_SEQ_CST,
+                                          __ATOMIC_SEQ_CST));
+    return old;
+}
+static inline float __double2float_rn(double v) { return (float)v; }
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    memcpy(&emul::g_block.warp_vals[w][lane], &v, sizeof(T));
+    pthread_barrier_wait(&emul::g_block.warp_bar[w]);
+    T r;
+    memcpy(&r, &emul::g_block.warp_vals[w][lane ^ lane_mask], sizeof(T));
+    pthread_barrier_wait(&emul::g_block.warp_bar[w]);
+    return r;
+}
+template <typename T> static inline T __shfl_down_sync(unsigned, T v, int delta) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    memcpy(&emul::g_block.warp_vals[w][lane], &v, sizeof(T));
+    pthread_barrier_wait(&emul::g_block.warp_bar[w]);
+    T r = v;
+    if (lane + delta < 32) memcpy(&r, &emul::g_block.warp_vals[w][lane + delta], sizeof(T));
+    pthread_barrier_wait(&emul::g_block.warp_bar[w]);
+    return r;
+}
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 
