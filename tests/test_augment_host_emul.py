@@ -248,3 +248,41 @@ def test_python_glue_of_augment_batch_through_the_emulated_entry_point(emul, gol
         want = np.ascontiguousarray((gold[tag + '/img'].astype(np.float32) / np.float32(255)).transpose(2, 0, 1))
         assert np.array_equal(dst[i].numpy(), want)
     assert dst[2].min() >= 0
+
+
+@pytest.mark.skipif(not HAVE_PIL, reason='Pillow not installed')
+@pytest.mark.parametrize('h,w,W,H,pleft,ptop,cw,ch', [
+    (300, 400, 32, 24, 0, 0, 400, 300),        # 12.5x down-scaling: 51 taps per axis
+    (40, 50, 200, 160, 5, 5, 8, 6),            # 25x up-scaling of a tiny crop
+    (30, 30, 20, 20, 40, 40, 12, 12),          # crop entirely outside the image: all zero -> black
+    (25, 31, 17, 13, -3, 28, 40, 5),           # crop hanging over two edges
+    (64, 64, 64, 64, 0, 0, 64, 64),            # identity geometry: both passes skipped
+    (50, 70, 7, 1, 0, 0, 70, 50),              # single output row
+])
+def test_extreme_geometries_vs_pillow(emul, h, w, W, H, pleft, ptop, cw, ch):
+    rs = np.random.RandomState(h * 7 + W)
+    a = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    for filt, pil_filter in ((3, Image.BICUBIC), (0, Image.NEAREST)):
+        p = dict(pleft=pleft, ptop=ptop, cw=cw, ch=ch, flip=0, distort=0, dhue=0.0, dsat=1.0, dexp=1.0)
+        want = np.asarray(Image.fromarray(a, 'RGB').crop((pleft, ptop, pleft + cw, ptop + ch)).resize((W, H), pil_filter))
+        out, u8 = run_augment(emul, [a], (W, H), [p], filt)
+        assert np.array_equal(u8[0], want), filt
+
+
+def test_oracle_image_equals_emulated_kernel_on_random_parameters(emul):
+    """Differential test oracle/image.py (numpy) vs the kernel source, no Pillow needed: 10 seeded augmentations."""
+    from oracle import image as OI
+    from fewshot_detection_b200 import image as I
+    rs = np.random.RandomState(5)
+    for seed in range(10):
+        h, w = int(rs.randint(24, 90)), int(rs.randint(24, 90))
+        W, H = int(rs.randint(16, 80)), int(rs.randint(16, 80))
+        a = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        random.seed(seed)
+        want, flip, dx, dy, sx, sy = OI.data_augmentation(a, (W, H), 0.2, 0.1, 1.5, 1.5)
+        random.seed(seed)
+        p = I.draw_augmentation(w, h, 0.2, 0.1, 1.5, 1.5)
+        assert (p['flip'], p['dx'], p['dy'], p['sx'], p['sy']) == (flip, dx, dy, sx, sy)
+        out, u8 = run_augment(emul, [a], (W, H), [p], 3)
+        assert np.array_equal(u8[0], want), seed
+        assert np.array_equal(out[0], OI.to_tensor(want))
