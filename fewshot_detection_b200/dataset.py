@@ -152,6 +152,7 @@ class MetaBatcher(object):
         self.train, self.ensemble, self.with_ids, self.filter = train, ensemble, with_ids, filter
         self.meta_shape = (cfg.meta_width, cfg.meta_height)
         self.mask_shape = (cfg.mask_width, cfg.mask_height)
+        self.batch_size = len(self.classes)      # one support image per class per process (MetaDataset.batch_size / num_gpus)
 
     def __len__(self):
         return len(self.inds)
