@@ -99,7 +99,7 @@ class MetaTrainer(object):
         batcher = self.make_train_batcher(self.model.seen)     # train_meta.py:181: seen = cur_model.seen (updated at saves)
         meta = self.make_meta_batcher()
         lr = self.adjust_learning_rate(self.processed_batches)
-        self.log('epoch %d/%s, processed %d samples, lr %f' % (epoch, max_epochs, epoch * len(batcher), lr))
+        self.log('epoch %d/%s, processed %d samples, lr %f' % (epoch, max_epochs, epoch * len(batcher) * self.world, lr))
         self.model.train()
         n_meta = meta.batch_size
         nb = 0
@@ -110,11 +110,11 @@ class MetaTrainer(object):
             loss = self.train_step(data, metax, mask, target)
             self.losses.append(loss)
         dt = time.time() - t0
-        self.log('training with %f samples/s' % (len(batcher) / max(dt, 1e-9)))
+        self.log('training with %f samples/s' % (len(batcher) * self.world / max(dt, 1e-9)))
         if self.backupdir is not None and (epoch + 1) % self.save_interval == 0:
             path = '%s/%06d.weights' % (self.backupdir, epoch + 1)
             self.log('save weights to %s' % path)
-            self.model.seen = (epoch + 1) * len(batcher)
+            self.model.seen = (epoch + 1) * len(batcher) * self.world
             self.model.save_weights(path)
         return nb
 
