@@ -9,6 +9,7 @@ optimizer (`optim.FusedSGD` or `torch.optim.SGD`), factories for the epoch's `da
 `dataset.MetaBatcher`, optionally a `distributed.GradAllReducer` (one process per GPU instead of nn.DataParallel).
 `tools/train_meta_b200.py` is the command-line front end with the reference's four arguments.
 """
+import collections
 import math
 import time
 
@@ -73,7 +74,7 @@ class MetaTrainer(object):
         self.processed_batches = processed_batches
         self.region_loss.seen = model.seen           # train_meta.py:93
         self.log = log
-        self.losses = []
+        self.losses = collections.deque(maxlen=100)   # detached loss tensors of the most recent steps (no host sync)
 
     def adjust_learning_rate(self, batch):
         lr = learning_rate_at(batch, self.learning_rate, self.steps, self.scales)
@@ -108,7 +109,7 @@ class MetaTrainer(object):
             self.adjust_learning_rate(self.processed_batches)
             self.processed_batches = self.processed_batches + 1
             loss = self.train_step(data, metax, mask, target)
-            self.losses.append(loss)
+            self.losses.append(loss.detach())
         dt = time.time() - t0
         self.log('training with %f samples/s' % (len(batcher) * self.world / max(dt, 1e-9)))
         if self.backupdir is not None and (epoch + 1) % self.save_interval == 0:
