@@ -69,3 +69,18 @@ def test_library_is_sm100a_native():
     _build_if_needed()
     out = subprocess.run(['cuobjdump', '-lelf', LIB], capture_output=True, text=True).stdout
     assert 'sm_100a' in out, out
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import it."""
+    pkg = os.path.join(ROOT, 'fewshot_detection_b200')
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                if re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M):
+                    offenders.append(os.path.join(dirpath, f))
+    assert offenders == []
+    for f in os.listdir(os.path.join(ROOT, 'dropin')):
+        assert 'oracle' not in open(os.path.join(ROOT, 'dropin', f)).read()
