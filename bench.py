@@ -475,7 +475,10 @@ def main():
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            try:
+                dist.destroy_process_group()
+            except Exception as e:
+                sys.stderr.write('destroy_process_group: %r\n' % (e,))
         return
 
     cpu_baseline = None
