@@ -437,6 +437,8 @@ def main():
     # guarded: the newest kernel must never cost the bench line.
     aug = None
     try:
+        if world != 1:
+            raise RuntimeError('single-GPU runs only')
         import random as _random
         from fewshot_detection_b200 import image as IMG
         rsa = np.random.RandomState(17)
@@ -471,7 +473,8 @@ def main():
             except Exception as e:
                 aug['cpu_note'] = 'Pillow timing skipped: %r' % (e,)
     except Exception as e:
-        sys.stderr.write('augment timing skipped: %r\n' % (e,))
+        if world == 1:
+            sys.stderr.write('augment timing skipped: %r\n' % (e,))
 
     if rank != 0:
         if world > 1:
