@@ -13,6 +13,12 @@
 // tools/try_persist.sh is the first thing to run (under `timeout`) before trusting it.
 #pragma once
 
+#ifdef FSDET_HOST_EMULATION
+#define FSDET_TC_DYN_SMEM(name) uint8_t* name = emul::g_dyn_smem
+#else
+#define FSDET_TC_DYN_SMEM(name) extern __shared__ uint8_t name[]
+#endif
+
 template <int BN, int BK, int STAGES_, int NH>
 struct TcPersistCfg {
     static constexpr int ROW_BYTES = BK * 2;
@@ -35,7 +41,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_c
     constexpr int STAGES = Cfg::STAGES;
     constexpr int A_BYTES = Cfg::A_BYTES;
     static_assert(2 * Cfg::ACC_COLS <= 512, "two accumulator sets must fit in TMEM");
-    extern __shared__ uint8_t smem_raw[];
+    FSDET_TC_DYN_SMEM(smem_raw);
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* epi = smem + STAGES * Cfg::STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi + Cfg::EPI_BYTES);

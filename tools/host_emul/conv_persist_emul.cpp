@@ -1,0 +1,245 @@
+// Host build of csrc/conv_tc_persist.cuh against FUNCTIONAL MODELS of the PTX wrappers it uses (see
+// cuda_host_emul.h for the thread model).  What is modelled: mbarriers (arrival counts, transaction bytes, phase
+// parity), the im2col / tiled TMA loads (tiles land unswizzled), tcgen05.mma (fp16 x fp16 -> fp32 into a TMEM array),
+// tcgen05.commit, tcgen05.ld, the swizzled 32x32 TMA store / reduce-add.  What this validates: the kernel's CONTROL
+// FLOW - stage and accumulator-set phases, tile sequencing over a persistent grid, accumulate flags of the three-MMA
+// hi/lo scheme, epilogue staging, edge clipping - i.e. everything that is new relative to the GPU-verified
+// conv_tc_kernel, whose descriptors / swizzle modes / instruction descriptor the persistent kernel reuses unchanged.
+// A wrong phase shows up as a deadlock (reported after a timeout) or as a wrong result.  Test tooling only.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <atomic>
+#include <chrono>
+#include <map>
+#include <mutex>
+
+#include "../../fewshot_detection_b200/csrc/common.cuh"
+
+namespace emul {
+Block g_block;
+unsigned char* g_dyn_smem = nullptr;
+}  // namespace emul
+
+namespace fsdet {
+void set_error(const char*, ...) {}
+
+// ---- declarations shared with conv_tc.cu (kept in sync by hand: only the fields the kernel reads matter)
+struct TcArgs {
+    float* z;
+    const float* amax_a;
+    const float* amax_b;
+    int ldz;
+    int H, W, Cin, Cout, ks, pad;
+    int cpitch;
+    long long M;
+    int accumulate;
+};
+constexpr int TC_BM = 128;
+constexpr int tmem_cols(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : (n <= 256 ? 256 : 512))); }
+static inline float scale_from_amax(float a) {   // conv_tc.cu: power of two mapping amax into [512, 1024)
+    if (!(a > 0.f) || !std::isfinite(a)) return 1.f;
+    int ex = (int)((__float_as_uint(a) >> 23) & 0xff) - 126;
+    int e = 10 - ex;
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+    return __uint_as_float((uint32_t)(e + 127) << 23);
+}
+static inline float ldg_f32(const float* p) { return *p; }
+
+// ---- models
+static std::atomic<bool> g_deadlock{false};
+static std::mutex g_mu;
+struct Bar { int count, pending; long long tx; int phase; };
+static std::map<const void*, Bar> g_bars;
+static float g_tmem[128][512];
+
+struct MapModel {   // lives in the first bytes of a CUtensorMap
+    int kind;       // 0 = im2col activation plane, 1 = weight plane, 2 = fp32 output
+    const uint16_t* base;
+    float* z;
+    int B, H, W, C, cpitch, ks, pad, bk, box_rows, rows, ldz;
+    long long K, M;
+};
+static inline const MapModel* model(const CUtensorMap* m) { return reinterpret_cast<const MapModel*>(m); }
+
+static inline uint32_t smem_u32(const void* p) { return (uint32_t)((const unsigned char*)p - emul::g_dyn_smem); }
+
+static void bar_check(Bar& b) {
+    if (b.pending == 0 && b.tx == 0) { b.phase ^= 1; b.pending = b.count; }
+}
+static inline void mbar_init(uint64_t* bar, uint32_t count) {
+    std::lock_guard<std::mutex> l(g_mu);
+    g_bars[bar] = Bar{(int)count, (int)count, 0, 0};
+}
+static inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    std::lock_guard<std::mutex> l(g_mu);
+    Bar& b = g_bars[bar];
+    b.tx += bytes; b.pending -= 1;
+    bar_check(b);
+}
+static inline void bar_complete_tx(uint64_t* bar, uint32_t bytes) {
+    std::lock_guard<std::mutex> l(g_mu);
+    Bar& b = g_bars[bar];
+    b.tx -= bytes;
+    bar_check(b);
+}
+static inline void mbar_arrive(uint64_t* bar) {
+    std::lock_guard<std::mutex> l(g_mu);
+    Bar& b = g_bars[bar];
+    b.pending -= 1;
+    bar_check(b);
+}
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        {
+            std::lock_guard<std::mutex> l(g_mu);
+            if ((uint32_t)g_bars[bar].phase != parity) return;   // the phase with this parity has completed
+        }
+        if (g_deadlock.load()) return;
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) { g_deadlock.store(true); return; }
+        std::this_thread::yield();
+    }
+}
+static inline void fence_barrier_init() {}
+static inline void fence_proxy_async() {}
+static inline void tc_fence_before() {}
+static inline void tc_fence_after() {}
+static inline void tma_prefetch_desc(const CUtensorMap*) {}
+static inline void tma_store_commit() {}
+template <int N> static inline void tma_store_wait_read() {}
+static inline void tmem_alloc(uint32_t* slot, uint32_t) { *slot = 0; }
+static inline void tmem_dealloc(uint32_t, uint32_t) {}
+
+// 128 consecutive output pixels starting at the pixel whose filter window has its corner at (w, h) of image n;
+// one filter tap (off_w, off_h), channels c .. c+bk-1; zero outside the image / beyond the last pixel
+static inline void tma_load_im2col_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h, int n,
+                                      uint16_t off_w, uint16_t off_h) {
+    const MapModel* m = model(map);
+    uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+    long long pix0 = ((long long)n * m->H + (h + m->pad)) * m->W + (w + m->pad);
+    const long long total = (long long)m->B * m->H * m->W;
+    for (int i = 0; i < TC_BM; ++i) {
+        const long long pi = pix0 + i;
+        uint16_t* row = d + (size_t)i * m->bk;
+        bool ok = pi < total;
+        int img = 0, y = 0, x = 0;
+        if (ok) {
+            img = (int)(pi / ((long long)m->H * m->W));
+            const int rem = (int)(pi - (long long)img * m->H * m->W);
+            y = rem / m->W - m->pad + off_h;
+            x = rem % m->W - m->pad + off_w;
+            ok = y >= 0 && y < m->H && x >= 0 && x < m->W;
+        }
+        for (int k = 0; k < m->bk; ++k) {
+            const int ch = c + k;
+            row[k] = (ok && ch < m->C) ? m->base[(((size_t)img * m->H + y) * m->W + x) * m->cpitch + ch] : (uint16_t)0;
+        }
+    }
+    bar_complete_tx(bar, (uint32_t)(TC_BM * m->bk * 2));
+}
+static inline void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    const MapModel* m = model(map);
+    uint16_t* d = reinterpret_cast<uint16_t*>(dst);
+    for (int r = 0; r < m->box_rows; ++r)
+        for (int k = 0; k < m->bk; ++k) {
+            const long long row = c1 + r, col = c0 + k;
+            d[(size_t)r * m->bk + k] = (row < m->rows && col < m->K) ? m->base[(size_t)row * m->K + col] : (uint16_t)0;
+        }
+    bar_complete_tx(bar, (uint32_t)(m->box_rows * m->bk * 2));
+}
+static inline void store_box(const CUtensorMap* map, const void* src, int c0, int c1, bool add) {
+    const MapModel* m = model(map);
+    const unsigned char* s = reinterpret_cast<const unsigned char*>(src);
+    for (int r = 0; r < 32; ++r)
+        for (int j = 0; j < 32; ++j) {
+            if (c1 + r >= m->M || c0 + j >= m->rows) continue;      // clipped by the tensor map
+            float v;
+            memcpy(&v, s + r * 128 + ((((j >> 2) ^ (r & 7))) << 4) + (j & 3) * 4, 4);   // 128-byte swizzle
+            float* o = m->z + (size_t)(c1 + r) * m->ldz + c0 + j;
+            *o = add ? *o + v : v;
+        }
+}
+static inline void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) { store_box(map, src, c0, c1, false); }
+static inline void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) { store_box(map, src, c0, c1, true); }
+
+// model descriptors: [0,32) = byte offset >> 4 (so that the kernel's `+ adv` in 16-byte units works), [32,48) = row bytes
+static inline uint64_t umma_desc_k_sw128(uint32_t saddr) { return (uint64_t)(saddr >> 4) | ((uint64_t)128 << 32); }
+static inline uint64_t umma_desc_k_sw64(uint32_t saddr) { return (uint64_t)(saddr >> 4) | ((uint64_t)64 << 32); }
+static inline float h2f(uint16_t b) { __half_raw r; r.x = b; return __half2float(__half(r)); }
+static inline void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4;
+    const unsigned char* A = emul::g_dyn_smem + ((adesc & 0xffffffffu) << 4);
+    const unsigned char* Bm = emul::g_dyn_smem + ((bdesc & 0xffffffffu) << 4);
+    const int ra = (int)(adesc >> 32), rb = (int)(bdesc >> 32);
+    const int col0 = (int)(tmem_d & 0xffff);
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            float acc = accumulate ? g_tmem[m][col0 + n] : 0.f;
+            for (int k = 0; k < 16; ++k) {
+                uint16_t a, b;
+                memcpy(&a, A + (size_t)m * ra + k * 2, 2);
+                memcpy(&b, Bm + (size_t)n * rb + k * 2, 2);
+                acc += h2f(a) * h2f(b);
+            }
+            g_tmem[m][col0 + n] = acc;
+        }
+}
+static inline void umma_commit(uint64_t* bar) { mbar_arrive(bar); }
+static std::atomic<int> g_ld_delay_us{0};   // slows the epilogue down so that a missing accumulator hand-back shows
+static inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    if (g_ld_delay_us.load() > 0) std::this_thread::sleep_for(std::chrono::microseconds(g_ld_delay_us.load()));
+    const int row = (int)(taddr >> 16) + (int)(threadIdx.x & 31), col = (int)(taddr & 0xffff);
+    for (int j = 0; j < 32; ++j) memcpy(&r[j], &g_tmem[row][col + j], 4);
+}
+
+#include "../../fewshot_detection_b200/csrc/conv_tc_persist.cuh"
+
+}  // namespace fsdet
+
+using namespace fsdet;
+
+template <int BN, int PST>
+static int run(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo, const TcArgs& a, int B,
+               int ctas) {
+    using Cfg = TcPersistCfg<BN, 32, PST, 1>;
+    CUtensorMap mAh, mAl, mBh, mBl, mZ;
+    const long long K = (long long)a.ks * a.ks * a.cpitch;
+    auto act = [&](CUtensorMap* m, const uint16_t* base) {
+        MapModel mm{}; mm.kind = 0; mm.base = base; mm.B = B; mm.H = a.H; mm.W = a.W; mm.C = a.Cin; mm.cpitch = a.cpitch;
+        mm.ks = a.ks; mm.pad = a.pad; mm.bk = 32;
+        memset(m, 0, sizeof(*m)); memcpy(m, &mm, sizeof(mm));
+    };
+    auto wgt = [&](CUtensorMap* m, const uint16_t* base) {
+        MapModel mm{}; mm.kind = 1; mm.base = base; mm.rows = a.Cout; mm.K = K; mm.bk = 32; mm.box_rows = BN;
+        memset(m, 0, sizeof(*m)); memcpy(m, &mm, sizeof(mm));
+    };
+    static_assert(sizeof(MapModel) <= sizeof(CUtensorMap), "model must fit in the tensor map");
+    act(&mAh, x_hi); act(&mAl, x_lo); wgt(&mBh, w_hi); wgt(&mBl, w_lo);
+    { MapModel mm{}; mm.kind = 2; mm.z = a.z; mm.rows = a.Cout; mm.M = a.M; mm.ldz = a.ldz; memset(&mZ, 0, sizeof(mZ)); memcpy(&mZ, &mm, sizeof(mm)); }
+    const int tiles_n = ceil_div(a.Cout, BN);
+    const long long total = (long long)tiles_n * ceil_div(a.M, TC_BM);
+    g_deadlock.store(false);
+    emul::launch(dim3(ctas), dim3(192), Cfg::SMEM_BYTES, [&]() {
+        if (threadIdx.x == 0) { memset(g_tmem, 0, sizeof(g_tmem)); std::lock_guard<std::mutex> l(g_mu); g_bars.clear(); }
+        pthread_barrier_wait(&emul::g_block.bar);
+        conv_tc_persist_kernel<BN, 32, PST, 1>(mAh, mAl, mBh, mBl, mZ, a, tiles_n, (int)total);
+    });
+    return g_deadlock.load() ? -100 : 0;
+}
+
+// returns 0, or -100 when a barrier wait timed out (deadlock: wrong phase / arrival count)
+extern "C" int emul_conv_tc_persist(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
+                                    const float* amax_x, const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin,
+                                    int cpitch, int Cout, int ks, int accumulate, int bn, int stages, int ctas) {
+    TcArgs a;
+    a.z = z; a.amax_a = amax_x; a.amax_b = amax_w; a.ldz = ldz; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ks = ks;
+    a.pad = (ks - 1) / 2; a.cpitch = cpitch; a.M = (long long)B * H * W; a.accumulate = accumulate;
+    if (bn == 64 && stages == 6) return run<64, 6>(x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+    if (bn == 64 && stages == 2) return run<64, 2>(x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+    if (bn == 128 && stages == 4) return run<128, 4>(x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+    return -1;
+}
+
+// test knob: every tcgen05.ld of the model sleeps this long (0 = off)
+extern "C" void emul_set_ld_delay_us(int us) { fsdet::g_ld_delay_us.store(us); }

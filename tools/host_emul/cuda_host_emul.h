@@ -96,6 +96,11 @@ static inline float atomicAdd(float* p, float v) {
     return old;
 }
 static inline float __double2float_rn(double v) { return (float)v; }
+static inline float __uint_as_float(unsigned v) { float f; memcpy(&f, &v, 4); return f; }
+static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&emul::g_block.warp_bar[threadIdx.x >> 5]); }
+#ifndef __grid_constant__
+#define __grid_constant__
+#endif
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
     static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
