@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(float* const* __restrict
 
 }  // namespace fsdet
 
+#ifndef FSDET_HOST_EMULATION  // tools/host_emul compiles the kernel above with g++ for CPU logic tests
 using namespace fsdet;
 
 extern "C" int fsdet_sgd_step(float* const* params, const float* const* grads, float* const* moms, const long long* sizes,
@@ -70,3 +71,4 @@ extern "C" int fsdet_sgd_step(float* const* params, const float* const* grads, f
                                                                  chunk_elems, lr, momentum, dampening, weight_decay, first_step, hyper_dev);
     return launch_status("sgd_step");
 }
+#endif  // FSDET_HOST_EMULATION
