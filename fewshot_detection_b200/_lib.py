@@ -32,10 +32,11 @@ SIGNATURES = {
     'fsdet_weight_flip_transpose': ('ppiiip', 'i'),
     'fsdet_pad_channels': ('pipizp', 'i'),
     'fsdet_conv_tc_supported': ('iii', 'i'),
-    'fsdet_conv_tc_fwd': ('pppppppiiiiiiiiip', 'i'),
+    'fsdet_conv_tc_stat_rows': ('iiiiiii', 'i'),
+    'fsdet_conv_tc_fwd': ('pppppppiiiiiiiiiipp', 'i'),
     'fsdet_conv_tc_wgrad_supported': ('iii', 'i'),
-    'fsdet_conv_tc_wgrad_workspace_floats': ('iiiiii', 'z'),
-    'fsdet_conv_tc_wgrad': ('ppppppppziiiiiip', 'i'),
+    'fsdet_conv_tc_wgrad_workspace_floats': ('iiiiiii', 'z'),
+    'fsdet_conv_tc_wgrad': ('ppppppppziiiiiiip', 'i'),
     'fsdet_amax': ('piizpp', 'i'),
     'fsdet_split_f16': ('piiizpppp', 'i'),
     'fsdet_colstats': ('pizipp', 'i'),

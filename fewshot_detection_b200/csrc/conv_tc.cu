@@ -238,222 +238,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// ------------------------------------------------------------------ the kernel
-constexpr int NACC = 4;   // TMEM accumulators: NHI for the hi*hi products (k-blocks rotate over them) + one for the lo terms
-constexpr int NHI = 3;    // (the lo terms are 2^-11 smaller, so their accumulation error is negligible)
-
-struct TcArgs {
-    float* z;
-    const float* amax_a;
-    const float* amax_b;
-    int ldz;
-    int H, W, Cin, Cout, ks, pad;
-    int cpitch;   // channel pitch of the weight planes' K axis: k = tap * cpitch + c
-    long long M;  // B*H*W
-    int accumulate;
-};
-
-constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;                       // halves per 128-byte row (im2col debug tile, weight-gradient tiles)
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB per plane
-
-constexpr int tmem_cols(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : (n <= 256 ? 256 : 512))); }
-
-// Two flavours of the same kernel:
-//   BK = 64 (128-byte rows), 3 hi accumulators, 1 CTA / SM : large-K layers (long accumulation chains)
-//   BK = 32 ( 64-byte rows), 1 hi accumulator,  2 CTAs / SM: small-K layers (K = k*k*Cin <= 2304) and 32-channel
-//        inputs; the two co-resident CTAs overlap one's epilogue / prologue with the other's MMAs.
-template <int BN, int BK, int STAGES_, int NH>
-struct TcCfg {
-    static constexpr int ROW_BYTES = BK * 2;
-    static constexpr int A_BYTES = TC_BM * ROW_BYTES;
-    static constexpr int B_BYTES = BN * ROW_BYTES;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = STAGES_;
-    static constexpr int TMEM_COLS = tmem_cols((NH + 1) * BN);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-};
-
-template <int BN, int BK, int STAGES_, int NH, int MINB>
-__global__ void __launch_bounds__(192, MINB)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
-               const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
-               const __grid_constant__ CUtensorMap tmZ, const TcArgs p) {
-    using Cfg = TcCfg<BN, BK, STAGES_, NH>;
-    constexpr int STAGES = Cfg::STAGES;
-    constexpr int A_BYTES = Cfg::A_BYTES;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x;
-    const long long m0 = (long long)blockIdx.y * TC_BM;
-    const int kchunks = p.Cin / BK;
-    const int nk = p.ks * p.ks * kchunks;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmAhi);
-        tma_prefetch_desc(&tmAlo);
-        tma_prefetch_desc(&tmBhi);
-        tma_prefetch_desc(&tmBlo);
-        tma_prefetch_desc(&tmZ);
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
-        }
-        mbar_init(tmem_full_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == 1) {  // whole warp: allocate the fp32 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            const int HW = p.H * p.W;
-            const int img = (int)(m0 / HW);
-            const int rem = (int)(m0 - (long long)img * HW);
-            const int ph = rem / p.W, pw = rem - ph * p.W;
-            for (int kb = 0; kb < nk; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
-                uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-                mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-                const int tap = kb / kchunks;
-                const int c0 = (kb - tap * kchunks) * BK;
-                const int r = tap / p.ks, sx = tap - r * p.ks;
-                tma_load_im2col_4d(st, &tmAhi, &full_bar[s], c0, pw - p.pad, ph - p.pad, img, (uint16_t)sx, (uint16_t)r);
-                tma_load_im2col_4d(st + A_BYTES, &tmAlo, &full_bar[s], c0, pw - p.pad, ph - p.pad, img, (uint16_t)sx, (uint16_t)r);
-                tma_load_2d(st + 2 * A_BYTES, &tmBhi, &full_bar[s], tap * p.cpitch + c0, n_tile * BN);
-                tma_load_2d(st + 2 * A_BYTES + Cfg::B_BYTES, &tmBlo, &full_bar[s], tap * p.cpitch + c0, n_tile * BN);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=f16, both K-major, N=BN, M=128
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            for (int kb = 0; kb < nk; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&full_bar[s], (kb / STAGES) & 1);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                uint64_t ahi, alo, bhi, blo;
-                if constexpr (BK == 64) {
-                    ahi = umma_desc_k_sw128(sa); alo = umma_desc_k_sw128(sa + A_BYTES);
-                    bhi = umma_desc_k_sw128(sa + 2 * A_BYTES); blo = umma_desc_k_sw128(sa + 2 * A_BYTES + Cfg::B_BYTES);
-                } else {
-                    ahi = umma_desc_k_sw64(sa); alo = umma_desc_k_sw64(sa + A_BYTES);
-                    bhi = umma_desc_k_sw64(sa + 2 * A_BYTES); blo = umma_desc_k_sw64(sa + 2 * A_BYTES + Cfg::B_BYTES);
-                }
-#pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 halves = 32 B along K inside the swizzle atom
-                    const uint32_t dhi = tmem_base + (uint32_t)((kb % NH) * BN);
-                    const uint32_t dlo = tmem_base + (uint32_t)(NH * BN);
-                    umma_f16(dhi, ahi + adv, bhi + adv, idesc, (kb >= NH || k > 0) ? 1u : 0u);
-                    umma_f16(dlo, alo + adv, bhi + adv, idesc, (kb | k) ? 1u : 0u);
-                    umma_f16(dlo, ahi + adv, blo + adv, idesc, 1u);
-                }
-                umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs have read it
-            }
-            umma_commit(tmem_full_bar);      // accumulator complete
-        }
-    } else {
-        // epilogue warps 2..5 -> TMEM lane quarters (warp % 4).  Each warp owns 32 output pixels.  In the short-K
-        // flavour it stages each 32x32 fp32 chunk in (128-byte-swizzled) shared memory - the operand stages are free
-        // once the accumulator is complete - and one lane issues a TMA tensor store (reduce-add when accumulating), so
-        // the global writes are full 128-byte rows, asynchronous, and clipped at the tensor edges by the hardware.
-        const int quarter = warp & 3;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const float inv = 1.f / (scale_from_amax(p.amax_a ? __ldg(p.amax_a) : 0.f) * scale_from_amax(p.amax_b ? __ldg(p.amax_b) : 0.f));
-        const int nhi = nk < NH ? nk : NH;
-        uint8_t* stage_buf = smem + quarter * 8192;          // two 4 KB buffers per warp
-        const long long mrow = m0 + quarter * 32;
-        const long long m = mrow + lane;
-        float* zr = p.z + (m < p.M ? m : 0) * p.ldz;
-#pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
-            uint32_t r[32];
-            float acc[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32;
-            tmem_ld32(taddr + NH * BN, r);  // lo terms first (small), then the hi*hi partial sums
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-            for (int a = nhi - 1; a >= 0; --a) {
-                tmem_ld32(taddr + a * BN, r);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
-            }
-            const int n0 = n_tile * BN + ch * 32;
-            if constexpr (MINB == 2) {
-                // short-K flavour (output bytes per MMA are high): TMA tensor store of a swizzled shared-memory tile
-                if (n0 < p.Cout && mrow < p.M) {             // warp-uniform
-                    uint8_t* buf = stage_buf + (ch & 1) * 4096;
-                    if (ch >= 2) {                           // the store that last read this buffer must have drained
-                        if (lane == 0) tma_store_wait_read<1>();
-                        __syncwarp();
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 v = make_float4(acc[4 * j] * inv, acc[4 * j + 1] * inv, acc[4 * j + 2] * inv, acc[4 * j + 3] * inv);
-                        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (p.accumulate) tma_reduce_add_2d(&tmZ, buf, n0, (int)mrow);
-                        else tma_store_2d(&tmZ, buf, n0, (int)mrow);
-                        tma_store_commit();
-                    }
-                }
-            } else if (m < p.M) {
-                // long-K flavour: the epilogue is a small fraction of the tile, plain vector stores
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int n = n0 + j;
-                    if (n + 3 < p.Cout) {
-                        float4 v = make_float4(acc[j] * inv, acc[j + 1] * inv, acc[j + 2] * inv, acc[j + 3] * inv);
-                        if (p.accumulate) {
-                            float4 o = *reinterpret_cast<const float4*>(zr + n);
-                            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                        }
-                        *reinterpret_cast<float4*>(zr + n) = v;
-                    } else {
-                        for (int t = 0; t < 4; ++t)
-                            if (n + t < p.Cout) zr[n + t] = acc[j + t] * inv + (p.accumulate ? zr[n + t] : 0.f);
-                    }
-                }
-            }
-        }
-        if constexpr (MINB == 2) {
-            if (lane == 0) tma_store_wait_read<0>();         // shared memory must outlive the bulk reads
-            __syncwarp();
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS));
-    }
-}
-
-// ------------------------------------------------------------------ persistent variant: see conv_tc_persist.cuh
+// ------------------------------------------------------------------ wrappers used by conv_tc_kernels.cuh
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {   // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -462,8 +250,16 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {   /
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols));
 }
 __device__ __forceinline__ float ldg_f32(const float* p) { return __ldg(p); }
+// barrier over `nthreads` threads of the CTA (the epilogue warps), id 1..15
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
-#include "conv_tc_persist.cuh"   // inside namespace fsdet
+constexpr int NHI = 3;    // hi*hi accumulators of the long-K fp32-grade flavour (k-blocks rotate over them)
+constexpr int TC_BK = 64;                       // halves per 128-byte row (im2col debug tile, weight-gradient tiles)
+constexpr int TC_A_BYTES = 128 * TC_BK * 2;     // 16 KB per plane
+
+#include "conv_tc_kernels.cuh"   // inside namespace fsdet
 
 // ------------------------------------------------------------------ weight gradient
 //   dw[co][tap][ci] = sum_p dz[p][co] * x[p + tap][ci]
@@ -490,22 +286,33 @@ struct TcWgArgs {
 };
 
 constexpr int WG_BP = 64;                      // pixels per stage
-constexpr int WG_BLK = WG_BP * 128;            // one [64 pixels][64 channels] bf16 block = 8 KB
+constexpr int WG_BLK = WG_BP * 128;            // one [64 pixels][64 channels] fp16 block = 8 KB
 
-template <int BN>
+// TERMS as in conv_tc_kernel (A = dz, B = x): bit 0 adds dz_lo * x_hi, bit 1 adds dz_hi * x_lo
+template <int BN, int TERMS, int NH>
 struct WgCfg {
     static constexpr int A_BYTES = 2 * WG_BLK;            // 128 co
     static constexpr int B_BYTES = (BN / 64) * WG_BLK;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int STAGES = (BN == 128) ? 3 : 4;
+    static constexpr int NA = 1 + (TERMS & 1);
+    static constexpr int NBP = 1 + ((TERMS >> 1) & 1);
+    static constexpr int STAGE_BYTES = NA * A_BYTES + NBP * B_BYTES;
+    static constexpr int OFF_ALO = A_BYTES;
+    static constexpr int OFF_BHI = NA * A_BYTES;
+    static constexpr int OFF_BLO = OFF_BHI + B_BYTES;
+    static constexpr int BUDGET = 227 * 1024 - 1024 - 256;
+    static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
+    static constexpr int NACC = NH + (TERMS ? 1 : 0);
+    static constexpr int TMEM_COLS = tmem_cols(NACC * BN);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static_assert(NACC * BN <= 512, "accumulators must fit in TMEM");
+    static_assert(STAGES >= 2, "at least two pipeline stages");
 };
 
-template <int BN, int TAPS>   // N tile = TAPS filter taps x (BN / TAPS) input channels
+template <int BN, int TAPS, int TERMS, int NH>   // N tile = TAPS filter taps x (BN / TAPS) input channels
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant__ CUtensorMap tmDlo,
                 const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__ CUtensorMap tmXlo, const TcWgArgs p) {
-    using Cfg = WgCfg<BN>;
+    using Cfg = WgCfg<BN, TERMS, NH>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -516,7 +323,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    constexpr int CIB = BN / TAPS;                      // input channels per tap in this tile (64 or 128)
+    constexpr int CIB = BN / TAPS;                      // input channels per tap in this tile (64, 128 or 256)
     const int kk = p.ks * p.ks;
     const int ci_tiles = (p.Cin + CIB - 1) / CIB;
     const int tap0 = (blockIdx.x / ci_tiles) * TAPS;
@@ -529,9 +336,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmDhi);
-        tma_prefetch_desc(&tmDlo);
+        if (TERMS & 1) tma_prefetch_desc(&tmDlo);
         tma_prefetch_desc(&tmXhi);
-        tma_prefetch_desc(&tmXlo);
+        if (TERMS & 2) tma_prefetch_desc(&tmXlo);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -539,10 +346,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(NACC * BN)));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -563,7 +367,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     tma_load_2d(st + j * WG_BLK, &tmDhi, &full_bar[s], co0 + 64 * j, (int)p0);
-                    tma_load_2d(st + Cfg::A_BYTES + j * WG_BLK, &tmDlo, &full_bar[s], co0 + 64 * j, (int)p0);
+                    if (TERMS & 1) tma_load_2d(st + Cfg::OFF_ALO + j * WG_BLK, &tmDlo, &full_bar[s], co0 + 64 * j, (int)p0);
                 }
 #pragma unroll
                 for (int j = 0; j < BN / 64; ++j) {
@@ -571,10 +375,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
                     if (tap >= kk) tap = kk - 1;      // tail group: duplicate load, its columns are not stored
                     const int r = tap / p.ks, sx = tap - r * p.ks;
                     const int ci = ci0 + (j * 64) % CIB;
-                    tma_load_im2col_4d(st + 2 * Cfg::A_BYTES + j * WG_BLK, &tmXhi, &full_bar[s], ci, pw - p.pad, ph - p.pad, img,
+                    tma_load_im2col_4d(st + Cfg::OFF_BHI + j * WG_BLK, &tmXhi, &full_bar[s], ci, pw - p.pad, ph - p.pad, img,
                                        (uint16_t)sx, (uint16_t)r);
-                    tma_load_im2col_4d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES + j * WG_BLK, &tmXlo, &full_bar[s], ci, pw - p.pad,
-                                       ph - p.pad, img, (uint16_t)sx, (uint16_t)r);
+                    if (TERMS & 2)
+                        tma_load_im2col_4d(st + Cfg::OFF_BLO + j * WG_BLK, &tmXlo, &full_bar[s], ci, pw - p.pad, ph - p.pad, img,
+                                           (uint16_t)sx, (uint16_t)r);
                 }
             }
         }
@@ -582,22 +387,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
         if (lane == 0) {
             // D=f32, A=B=f16, both MN-major, N=BN, M=128
             const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            uint32_t lo_started = 0;
             for (int kb = 0; kb < nk; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait(&full_bar[s], (kb / STAGES) & 1);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint64_t ahi = umma_desc_mn_sw128(sa, WG_BLK), alo = umma_desc_mn_sw128(sa + Cfg::A_BYTES, WG_BLK);
-                const uint64_t bhi = umma_desc_mn_sw128(sa + 2 * Cfg::A_BYTES, WG_BLK);
-                const uint64_t blo = umma_desc_mn_sw128(sa + 2 * Cfg::A_BYTES + Cfg::B_BYTES, WG_BLK);
+                const uint64_t ahi = umma_desc_mn_sw128(sa, WG_BLK), alo = umma_desc_mn_sw128(sa + Cfg::OFF_ALO, WG_BLK);
+                const uint64_t bhi = umma_desc_mn_sw128(sa + Cfg::OFF_BHI, WG_BLK);
+                const uint64_t blo = umma_desc_mn_sw128(sa + Cfg::OFF_BLO, WG_BLK);
 #pragma unroll
                 for (int k = 0; k < WG_BP / 16; ++k) {
                     const uint64_t adv = (uint64_t)(k * 2048 >> 4);  // 16 pixels = two 8-row groups of 1024 B
-                    const uint32_t dhi = tmem_base + (uint32_t)((kb % NHI) * BN);
-                    const uint32_t dlo = tmem_base + (uint32_t)(NHI * BN);
-                    umma_f16(dhi, ahi + adv, bhi + adv, idesc, (kb >= NHI || k > 0) ? 1u : 0u);
-                    umma_f16(dlo, alo + adv, bhi + adv, idesc, (kb | k) ? 1u : 0u);
-                    umma_f16(dlo, ahi + adv, blo + adv, idesc, 1u);
+                    const uint32_t dhi = tmem_base + (uint32_t)((kb % NH) * BN);
+                    const uint32_t dlo = tmem_base + (uint32_t)(NH * BN);
+                    umma_f16(dhi, ahi + adv, bhi + adv, idesc, (kb >= NH || k > 0) ? 1u : 0u);
+                    if (TERMS & 1) { umma_f16(dlo, alo + adv, bhi + adv, idesc, lo_started); lo_started = 1u; }
+                    if (TERMS & 2) { umma_f16(dlo, ahi + adv, blo + adv, idesc, lo_started); lo_started = 1u; }
                 }
                 umma_commit(&empty_bar[s]);
             }
@@ -613,7 +419,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
             tc_fence_after();
         }
         const float inv = 1.f / (scale_from_amax(p.amax_a ? __ldg(p.amax_a) : 0.f) * scale_from_amax(p.amax_b ? __ldg(p.amax_b) : 0.f));
-        const int nhi = nk < NHI ? nk : NHI;
+        const int nhi = nk < NH ? nk : NH;
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
             uint32_t r[32];
@@ -621,8 +427,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = 0.f;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + ch * 32;
-            if (nk > 0) {
-                tmem_ld32(taddr + NHI * BN, r);
+            if (TERMS != 0 && nk > 0) {
+                tmem_ld32(taddr + NH * BN, r);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
             }
@@ -646,7 +452,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NACC * BN)));
+        tmem_dealloc(tmem_base, (uint32_t)Cfg::TMEM_COLS);
     }
 }
 
@@ -698,26 +504,36 @@ typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static PFN_encodeTiled g_encodeTiled = nullptr;
-static PFN_encodeIm2col g_encodeIm2col = nullptr;
+// driver entry points, resolved once (thread-safe static initialisation, immutable afterwards)
+struct DriverFns {
+    PFN_encodeTiled encodeTiled = nullptr;
+    PFN_encodeIm2col encodeIm2col = nullptr;
+    bool ok = false;
+};
+
+static const DriverFns& driver_fns() {
+    static const DriverFns fns = [] {
+        DriverFns f;
+        void* f1 = nullptr;
+        void* f2 = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f1, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !f1) return f;
+        e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f2, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !f2) return f;
+        f.encodeTiled = (PFN_encodeTiled)f1;
+        f.encodeIm2col = (PFN_encodeIm2col)f2;
+        f.ok = true;
+        return f;
+    }();
+    return fns;
+}
 
 static int load_driver_fns() {
-    if (g_encodeTiled && g_encodeIm2col) return 0;
-    void* f1 = nullptr;
-    void* f2 = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f1, cudaEnableDefault, &q);
-    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !f1) {
-        set_error("cuTensorMapEncodeTiled entry point unavailable");
+    if (!driver_fns().ok) {
+        set_error("cuTensorMapEncodeTiled / cuTensorMapEncodeIm2col entry points unavailable");
         return -2;
     }
-    e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f2, cudaEnableDefault, &q);
-    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !f2) {
-        set_error("cuTensorMapEncodeIm2col entry point unavailable");
-        return -2;
-    }
-    g_encodeTiled = (PFN_encodeTiled)f1;
-    g_encodeIm2col = (PFN_encodeIm2col)f2;
     return 0;
 }
 
@@ -731,7 +547,7 @@ static int make_im2col_map(CUtensorMap* map, const void* base, int B, int H, int
     int lower[2] = {-pad, -pad};
     int upper[2] = {pad - (ks - 1), pad - (ks - 1)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encodeIm2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
+    CUresult r = driver_fns().encodeIm2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
                                 (cuuint32_t)bk, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -753,7 +569,7 @@ static int make_tiled_map(CUtensorMap* map, const void* base, long long rows, lo
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
     cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = driver_fns().encodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -763,72 +579,105 @@ static int make_tiled_map(CUtensorMap* map, const void* base, long long rows, lo
     return 0;
 }
 
-static bool tc_persist_enabled() {
-    static const bool on = [] { const char* e = getenv("FSDET_TC_PERSIST"); return e && e[0] == '1'; }();
-    return on;
+// ---- tile plan of one convolution: which kernel flavour runs, its grid and the number of statistics rows
+//   mode bits 0-1 = TERMS (operand precision, see conv_tc_kernels.cuh), bit 4 = persistent tile loop (short-K only)
+struct TcPlan {
+    int bn, bk, nh, terms;
+    bool persist;
+    int tiles_n, tiles_m, grid;
+};
+
+static TcPlan tc_plan(long long M, int Cin, int Cout, int ksize, int mode) {
+    TcPlan pl;
+    pl.terms = mode & 3;
+    const bool small_k = (Cin % 64 != 0) || (ksize * ksize * Cin <= 2304);
+    pl.bn = Cout >= 128 ? 128 : 64;
+    pl.bk = small_k ? 32 : 64;
+    pl.nh = (!small_k && pl.terms == 3) ? NHI : 1;
+    pl.persist = small_k && (mode & 16);
+    pl.tiles_n = ceil_div(Cout, pl.bn);
+    pl.tiles_m = ceil_div(M, TC_BM);
+    const long long total = (long long)pl.tiles_n * pl.tiles_m;
+    if (pl.persist) {
+        long long g = total < kNumSMs ? total : kNumSMs;
+        g = g / pl.tiles_n * pl.tiles_n;          // every CTA keeps one channel range (statistics in registers)
+        pl.grid = (int)(g < pl.tiles_n ? pl.tiles_n : g);
+    } else {
+        pl.grid = (int)total;
+    }
+    return pl;
 }
 
-template <int BN, int BK, int STAGES_, int NH, int MINB>
-static int launch_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int B, const TcArgs& a, cudaStream_t s) {
-    using Cfg = TcCfg<BN, BK, STAGES_, NH>;
+template <int BN, int BK, int NH, int TERMS, bool PERSIST, int MINB>
+static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                     const CUtensorMap& zmap, const TcArgs& a, int grid, cudaStream_t s) {
+    using Cfg = TcCfg<BN, BK, NH, TERMS, PERSIST, MINB>;
+    auto kern = conv_tc_kernel<BN, BK, NH, TERMS, PERSIST, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+        set_error("conv_tc: cudaFuncSetAttribute(%d bytes): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+        return (int)e;
+    }
+    kern<<<grid, 192, Cfg::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, zmap, a);
+    return launch_status(PERSIST ? "conv_tc(persistent)" : "conv_tc");
+}
+
+template <int BN, int BK, int NH, bool PERSIST, int MINB>
+static int launch_tc_terms(int terms, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                           const CUtensorMap& b_lo, const CUtensorMap& zmap, const TcArgs& a, int grid, cudaStream_t s) {
+    switch (terms) {
+        case 0: return launch_tc<BN, BK, 1, 0, PERSIST, MINB>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, s);
+        case 1: return launch_tc<BN, BK, 1, 1, PERSIST, MINB>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, s);
+        case 2: return launch_tc<BN, BK, 1, 2, PERSIST, MINB>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, s);
+        default: return launch_tc<BN, BK, NH, 3, PERSIST, MINB>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, s);
+    }
+}
+
+static int run_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int B, TcArgs a, int mode, cudaStream_t s) {
+    const TcPlan pl = tc_plan(a.M, a.Cin, a.Cout, a.ks, mode);
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
-    int rc = make_im2col_map(&a_hi, x_hi, B, a.H, a.W, a.Cin, a.ks, TC_BM, a.cpitch, BK);
+    int rc = make_im2col_map(&a_hi, x_hi, B, a.H, a.W, a.Cin, a.ks, TC_BM, a.cpitch, pl.bk);
     if (rc) return rc;
-    rc = make_im2col_map(&a_lo, x_lo, B, a.H, a.W, a.Cin, a.ks, TC_BM, a.cpitch, BK);
-    if (rc) return rc;
+    a_lo = a_hi;
+    if (pl.terms & 1) {
+        rc = make_im2col_map(&a_lo, x_lo, B, a.H, a.W, a.Cin, a.ks, TC_BM, a.cpitch, pl.bk);
+        if (rc) return rc;
+    }
     const long long K = (long long)a.ks * a.ks * a.cpitch;
-    rc = make_tiled_map(&b_hi, w_hi, a.Cout, K, BN, BK);
+    rc = make_tiled_map(&b_hi, w_hi, a.Cout, K, pl.bn, pl.bk);
     if (rc) return rc;
-    rc = make_tiled_map(&b_lo, w_lo, a.Cout, K, BN, BK);
-    if (rc) return rc;
+    b_lo = b_hi;
+    if (pl.terms & 2) {
+        rc = make_tiled_map(&b_lo, w_lo, a.Cout, K, pl.bn, pl.bk);
+        if (rc) return rc;
+    }
     CUtensorMap zmap;   // fp32 output [M][ldz] (first Cout columns): 32 x 32 boxes, 128-byte swizzle
     {
         cuuint64_t dims[2] = {(cuuint64_t)a.Cout, (cuuint64_t)a.M};
         cuuint64_t strides[1] = {(cuuint64_t)a.ldz * 4};
         cuuint32_t box[2] = {32, 32};
         cuuint32_t estr[2] = {1, 1};
-        CUresult r = g_encodeTiled(&zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.z, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r = driver_fns().encodeTiled(&zmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.z, dims, strides, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("conv_tc: output tensor map failed (%d) M=%lld Cout=%d ldz=%d", (int)r, a.M, a.Cout, a.ldz);
             return -3;
         }
     }
-    if constexpr (MINB == 2) {
-        if (tc_persist_enabled()) {   // experimental: one CTA per SM walking the tile list (see conv_tc_persist_kernel)
-            constexpr int PST = BN == 64 ? 6 : 4;
-            using PCfg = TcPersistCfg<BN, BK, PST, NH>;
-            static bool pattr_done = false;
-            if (!pattr_done) {
-                cudaError_t e = cudaFuncSetAttribute(conv_tc_persist_kernel<BN, BK, PST, NH>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::SMEM_BYTES);
-                if (e != cudaSuccess) {
-                    set_error("conv_tc(persist): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-                    return (int)e;
-                }
-                pattr_done = true;
-            }
-            const int tiles_n = ceil_div(a.Cout, BN);
-            const long long total = (long long)tiles_n * ceil_div(a.M, TC_BM);
-            const int ctas = (int)(total < kNumSMs ? total : kNumSMs);
-            conv_tc_persist_kernel<BN, BK, PST, NH><<<ctas, 192, PCfg::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, zmap, a, tiles_n,
-                                                                                      (int)total);
-            return launch_status("conv_tc_persist");
+    a.tiles_n = pl.tiles_n;
+    a.tiles_total = pl.tiles_n * pl.tiles_m;
+    const int t = pl.terms;
+    if (pl.bk == 32) {
+        if (pl.persist) {
+            if (pl.bn == 128) return launch_tc_terms<128, 32, 1, true, 1>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, s);
+            return launch_tc_terms<64, 32, 1, true, 1>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, s);
         }
+        if (pl.bn == 128) return launch_tc_terms<128, 32, 1, false, 2>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, s);
+        return launch_tc_terms<64, 32, 1, false, 2>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, s);
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, STAGES_, NH, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) {
-            set_error("conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        attr_done = true;
-    }
-    dim3 grid(ceil_div(a.Cout, BN), ceil_div(a.M, TC_BM));
-    conv_tc_kernel<BN, BK, STAGES_, NH, MINB><<<grid, 192, Cfg::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, zmap, a);
-    return launch_status("conv_tc");
+    if (pl.bn == 128) return launch_tc_terms<128, 64, NHI, false, 1>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, s);
+    return launch_tc_terms<64, 64, NHI, false, 1>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, s);
 }
 
 }  // namespace fsdet
@@ -886,38 +735,42 @@ extern "C" int fsdet_conv_tc_supported(int Cin, int Cout, int ksize) {
     return (Cin % 32 == 0) && (Cout >= 8) && (Cout % 4 == 0) && (ksize == 1 || ksize == 3);
 }
 
+extern "C" int fsdet_conv_tc_stat_rows(int B, int H, int W, int Cin, int Cout, int ksize, int mode) {
+    const TcPlan pl = tc_plan((long long)B * H * W, Cin, Cout, ksize, mode);
+    return pl.persist ? pl.grid / pl.tiles_n : pl.tiles_m;
+}
+
 extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* amax_x,
                                  const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin, int cpitch, int Cout,
-                                 int ksize, int accumulate, void* stream) {
-    FSDET_CHECK_ARG(x_hi && x_lo && w_hi && w_lo && z, "conv_tc_fwd: null pointer");
+                                 int ksize, int accumulate, int mode, float* stat_partial, void* stream) {
+    const int terms = mode & 3;
+    FSDET_CHECK_ARG((mode & ~0x13) == 0, "conv_tc_fwd: unknown mode bits 0x%x", mode);
+    FSDET_CHECK_ARG(x_hi && w_hi && z && (!(terms & 1) || x_lo) && (!(terms & 2) || w_lo), "conv_tc_fwd: null pointer (mode %d)", mode);
     FSDET_CHECK_ARG(fsdet_conv_tc_supported(Cin, Cout, ksize) && cpitch >= Cin && cpitch % 8 == 0,
                     "conv_tc_fwd: unsupported Cin=%d (pitch %d) Cout=%d k=%d", Cin, cpitch, Cout, ksize);
     FSDET_CHECK_ARG(ldz % 4 == 0 && aligned16(z) && aligned16(x_hi) && aligned16(x_lo) && aligned16(w_hi) && aligned16(w_lo),
                     "conv_tc_fwd: alignment");
+    FSDET_CHECK_ARG(!(stat_partial && accumulate), "conv_tc_fwd: statistics of an accumulated output are not defined");
     int rc = load_driver_fns();
     if (rc) return rc;
     TcArgs a;
-    a.z = z; a.amax_a = amax_x; a.amax_b = amax_w; a.ldz = ldz; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ks = ksize;
-    a.pad = (ksize - 1) / 2; a.cpitch = cpitch; a.M = (long long)B * H * W; a.accumulate = accumulate;
+    a.z = z; a.amax_a = amax_x; a.amax_b = amax_w; a.stats = stat_partial; a.ldz = ldz; a.H = H; a.W = W; a.Cin = Cin;
+    a.Cout = Cout; a.ks = ksize; a.pad = (ksize - 1) / 2; a.cpitch = cpitch; a.M = (long long)B * H * W;
+    a.accumulate = accumulate; a.tiles_n = a.tiles_total = 0;
     if (a.M == 0) return 0;
-    FSDET_CHECK_ARG(a.M < (1ll << 31), "conv_tc_fwd: too many pixels");
-    cudaStream_t s = (cudaStream_t)stream;
-    const bool small_k = (Cin % 64 != 0) || (ksize * ksize * Cin <= 2304);
-    if (small_k) {   // 64-byte rows, one hi accumulator, two CTAs per SM
-        if (Cout >= 128) return launch_tc<128, 32, 3, 1, 2>(x_hi, x_lo, w_hi, w_lo, B, a, s);
-        return launch_tc<64, 32, 4, 1, 2>(x_hi, x_lo, w_hi, w_lo, B, a, s);
-    }
-    if (Cout >= 128) return launch_tc<128, 64, 3, NHI, 1>(x_hi, x_lo, w_hi, w_lo, B, a, s);
-    return launch_tc<64, 64, 4, NHI, 1>(x_hi, x_lo, w_hi, w_lo, B, a, s);
+    FSDET_CHECK_ARG(a.M < (1ll << 31) - 256, "conv_tc_fwd: too many pixels");
+    return run_tc(x_hi, x_lo, w_hi, w_lo, B, a, mode, (cudaStream_t)stream);
 }
 
-// tile shape of the weight-gradient kernel: Cin <= 64 packs two filter taps into one 128-wide N tile
-static inline int wg_cib(int Cin) { return Cin >= 128 ? 128 : 64; }
+// tile shape of the weight-gradient kernel: Cin <= 64 packs two filter taps into one 128-wide N tile; the plain
+// fp16 x fp16 mode (terms == 0) uses 256-wide N tiles where the layer has the channels (operand bytes per FLOP halve)
+static inline int wg_bn(int Cin, int terms) { return (terms == 0 && Cin >= 256) ? 256 : 128; }
+static inline int wg_cib(int Cin, int terms) { return Cin >= 128 ? wg_bn(Cin, terms) : 64; }
 static inline int wg_taps(int Cin) { return Cin >= 128 ? 1 : 2; }
 
-static int wg_splits(long long M, int Cin, int Cout, int ks, int /*bn*/) {
-    long long tiles = (long long)((Cin + wg_cib(Cin) - 1) / wg_cib(Cin)) * ((ks * ks + wg_taps(Cin) - 1) / wg_taps(Cin)) *
-                      ((Cout + 127) / 128);
+static int wg_splits(long long M, int Cin, int Cout, int ks, int terms) {
+    const int cib = wg_cib(Cin, terms), taps = wg_taps(Cin);
+    long long tiles = (long long)((Cin + cib - 1) / cib) * ((ks * ks + taps - 1) / taps) * ((Cout + 127) / 128);
     long long want = (2LL * kNumSMs + tiles - 1) / tiles;
     long long maxs = (M + 511) / 512;  // at least 512 pixels (8 stages) per split
     if (want > maxs) want = maxs;
@@ -930,42 +783,51 @@ extern "C" int fsdet_conv_tc_wgrad_supported(int Cin, int Cout, int ksize) {
     return (Cin % 64 == 0) && (Cout % 64 == 0) && (ksize == 1 || ksize == 3);
 }
 
-extern "C" size_t fsdet_conv_tc_wgrad_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize) {
-    int bn = Cin >= 128 ? 128 : 64;
-    int splits = wg_splits((long long)B * H * W, Cin, Cout, ksize, bn);
+extern "C" size_t fsdet_conv_tc_wgrad_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize, int mode) {
+    int splits = wg_splits((long long)B * H * W, Cin, Cout, ksize, mode & 3);
     return splits > 1 ? (size_t)splits * Cout * ksize * ksize * Cin : 0;
 }
 
-template <int BN, int TAPS>
+template <int BN, int TAPS, int TERMS, int NH>
 static int launch_wg(const CUtensorMap& dhi, const CUtensorMap& dlo, const CUtensorMap& xhi, const CUtensorMap& xlo,
                      const TcWgArgs& a, int splits, cudaStream_t s) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<BN>::SMEM_BYTES);
-        if (e != cudaSuccess) {
-            set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        attr_done = true;
+    using Cfg = WgCfg<BN, TERMS, NH>;
+    auto kern = wgrad_tc_kernel<BN, TAPS, TERMS, NH>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+        set_error("conv_tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return (int)e;
     }
     constexpr int CIB = BN / TAPS;
     dim3 grid(((a.Cin + CIB - 1) / CIB) * ((a.ks * a.ks + TAPS - 1) / TAPS), (a.Cout + 127) / 128, splits);
-    wgrad_tc_kernel<BN, TAPS><<<grid, 192, WgCfg<BN>::SMEM_BYTES, s>>>(dhi, dlo, xhi, xlo, a);
+    kern<<<grid, 192, Cfg::SMEM_BYTES, s>>>(dhi, dlo, xhi, xlo, a);
     return launch_status("conv_tc_wgrad");
+}
+
+template <int TAPS>
+static int launch_wg_terms(int terms, const CUtensorMap& dhi, const CUtensorMap& dlo, const CUtensorMap& xhi,
+                           const CUtensorMap& xlo, const TcWgArgs& a, int splits, cudaStream_t s) {
+    switch (terms) {
+        case 0: return launch_wg<128, TAPS, 0, 1>(dhi, dlo, xhi, xlo, a, splits, s);
+        case 1: return launch_wg<128, TAPS, 1, 1>(dhi, dlo, xhi, xlo, a, splits, s);
+        case 2: return launch_wg<128, TAPS, 2, 1>(dhi, dlo, xhi, xlo, a, splits, s);
+        default: return launch_wg<128, TAPS, 3, NHI>(dhi, dlo, xhi, xlo, a, splits, s);
+    }
 }
 
 extern "C" int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const void* dz_hi, const void* dz_lo, const float* amax_x,
                                    const float* amax_dz, float* dw, float* workspace, size_t workspace_floats, int B, int H,
-                                   int W, int Cin, int Cout, int ksize, void* stream) {
-    FSDET_CHECK_ARG(x_hi && x_lo && dz_hi && dz_lo && dw, "conv_tc_wgrad: null pointer");
+                                   int W, int Cin, int Cout, int ksize, int mode, void* stream) {
+    const int terms = mode & 3;
+    FSDET_CHECK_ARG((mode & ~3) == 0, "conv_tc_wgrad: unknown mode bits 0x%x", mode);
+    FSDET_CHECK_ARG(x_hi && dz_hi && dw && (!(terms & 1) || dz_lo) && (!(terms & 2) || x_lo), "conv_tc_wgrad: null pointer (mode %d)", mode);
     FSDET_CHECK_ARG(fsdet_conv_tc_wgrad_supported(Cin, Cout, ksize), "conv_tc_wgrad: unsupported Cin=%d Cout=%d k=%d", Cin, Cout, ksize);
     FSDET_CHECK_ARG(aligned16(dw) && aligned16(x_hi) && aligned16(x_lo) && aligned16(dz_hi) && aligned16(dz_lo), "conv_tc_wgrad: alignment");
     int rc = load_driver_fns();
     if (rc) return rc;
     const long long M = (long long)B * H * W;
-    FSDET_CHECK_ARG(M < (1ll << 31), "conv_tc_wgrad: too many pixels");
-    const int bn = Cin >= 128 ? 128 : 64;
-    const int splits = wg_splits(M, Cin, Cout, ksize, bn);
+    FSDET_CHECK_ARG(M < (1ll << 31) - 256, "conv_tc_wgrad: too many pixels");
+    const int splits = wg_splits(M, Cin, Cout, ksize, terms);
     const size_t need = splits > 1 ? (size_t)splits * Cout * ksize * ksize * Cin : 0;
     FSDET_CHECK_ARG(workspace_floats >= need && (need == 0 || (workspace && aligned16(workspace))),
                     "conv_tc_wgrad: workspace too small (%zu < %zu floats)", workspace_floats, need);
@@ -976,16 +838,18 @@ extern "C" int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const voi
     long long pps = (M + splits - 1) / splits;
     a.pix_per_split = (pps + WG_BP - 1) / WG_BP * WG_BP;
     CUtensorMap dhi, dlo, xhi, xlo;
-    // dz planes [M][Cout] bf16: 2-D tiled map, box = 64 channels x 64 pixels
+    // dz planes [M][Cout] fp16: 2-D tiled map, box = 64 channels x 64 pixels
     {
         cuuint64_t dims[2] = {(cuuint64_t)Cout, (cuuint64_t)M};
         cuuint64_t strides[1] = {(cuuint64_t)Cout * 2};
         cuuint32_t box[2] = {64, (cuuint32_t)WG_BP};
         cuuint32_t estr[2] = {1, 1};
         for (int t = 0; t < 2; ++t) {
-            CUresult r = g_encodeTiled(t ? &dlo : &dhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(t ? dz_lo : dz_hi), dims,
-                                       strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (t == 1 && !(terms & 1)) { dlo = dhi; break; }
+            CUresult r = driver_fns().encodeTiled(t ? &dlo : &dhi, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                                                  const_cast<void*>(t ? dz_lo : dz_hi), dims, strides, box, estr,
+                                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) {
                 set_error("conv_tc_wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r);
                 return -3;
@@ -994,10 +858,15 @@ extern "C" int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const voi
     }
     rc = make_im2col_map(&xhi, x_hi, B, H, W, Cin, ksize, WG_BP);
     if (rc) return rc;
-    rc = make_im2col_map(&xlo, x_lo, B, H, W, Cin, ksize, WG_BP);
-    if (rc) return rc;
+    xlo = xhi;
+    if (terms & 2) {
+        rc = make_im2col_map(&xlo, x_lo, B, H, W, Cin, ksize, WG_BP);
+        if (rc) return rc;
+    }
     cudaStream_t s = (cudaStream_t)stream;
-    rc = (bn == 128) ? launch_wg<128, 1>(dhi, dlo, xhi, xlo, a, splits, s) : launch_wg<128, 2>(dhi, dlo, xhi, xlo, a, splits, s);
+    if (Cin < 128) rc = launch_wg_terms<2>(terms, dhi, dlo, xhi, xlo, a, splits, s);
+    else if (wg_bn(Cin, terms) == 256) rc = launch_wg<256, 1, 0, 2>(dhi, dlo, xhi, xlo, a, splits, s);
+    else rc = launch_wg_terms<1>(terms, dhi, dlo, xhi, xlo, a, splits, s);
     if (rc) return rc;
     if (splits > 1) {
         long long n4 = (long long)Cout * ksize * ksize * Cin / 4;

@@ -1,0 +1,319 @@
+// The tcgen05 implicit-GEMM convolution kernel (forward and input gradient) - included by conv_tc.cu after the PTX
+// wrappers, and by tools/host_emul/conv_tc_emul.cpp after FUNCTIONAL MODELS of the same wrappers (mbarrier, TMA,
+// UMMA, TMEM, named barriers as host code), which is how its control flow - barrier phases, tile sequencing,
+// accumulator double buffering, operand-term selection, epilogue staging, the fused BatchNorm statistics - is
+// tested on the CPU (tests/test_conv_tc_host_emul.py).
+//
+//   z[p][n] = sum_{tap,ci} x[p+tap][ci] * w[n][tap][ci]      (stride 1, "same" padding, k in {1,3})
+//
+// One CTA = 192 threads:
+//   warp 0   : TMA producer.  A tiles (128 output pixels x BK channels of one filter tap, zero-filled halo) come
+//              straight from the NHWC activation planes through an im2col tensor map, B tiles (BN output channels x
+//              BK) from the [Cout][K] weight planes; both land swizzled K-major in shared memory.
+//   warp 1   : allocates TMEM, issues tcgen05.mma (one elected thread), commits to mbarriers.
+//   warps 2-5: epilogue.  tcgen05.ld (lane = pixel) -> registers -> swizzled shared-memory staging -> TMA tensor
+//              store (reduce-add when accumulating), plus - for BatchNorm layers - the per-channel
+//              sum / sum of squares / min / max of z taken from the staged tile (fsdet_bn_finalize reads them), so
+//              that no separate statistics pass over z exists.
+//
+// Operand precision (template parameter TERMS): every operand exists as two fp16 planes (hi, lo) of the tensor
+// scaled by a power of two; hi*hi is always issued, bit 0 of TERMS adds A_lo*B_hi, bit 1 adds A_hi*B_lo.  TERMS = 3
+// is fp32-grade (22 mantissa bits per operand), TERMS = 1 / 2 keep one operand exact and round the other to fp16
+// (relative rounding 2^-12 per element), TERMS = 0 is plain fp16 x fp16 -> fp32.  Only the planes that are used are
+// loaded.  With hi*hi products of successive k-blocks rotating over NH accumulators (the tensor core's fp32
+// accumulation truncates; NH > 1 only matters for TERMS = 3 and long K).
+//
+// PERSIST = false: one output tile per CTA (grid = number of tiles), the epilogue staging aliases the operand stages.
+// PERSIST = true : one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; producer and MMA issuer run
+//              ahead across tile boundaries and the accumulators are double buffered in TMEM so that the epilogue of
+//              tile i overlaps the MMAs of tile i+1 (short-K layers, where the epilogue is a large share of a tile).
+//              gridDim.x must be a multiple of tiles_n (then every CTA keeps one channel range: the statistics are
+//              carried in registers across its tiles and written once).
+#pragma once
+
+#ifdef FSDET_HOST_EMULATION
+#define FSDET_TC_DYN_SMEM(name) uint8_t* name = emul::g_dyn_smem
+#else
+#define FSDET_TC_DYN_SMEM(name) extern __shared__ uint8_t name[]
+#endif
+
+struct TcArgs {
+    float* z;
+    const float* amax_a;
+    const float* amax_b;
+    float* stats;     // optional [rows][4*Cout] = (sum | sum of squares | min | max), row = blockIdx.x / tiles_n
+    int ldz;
+    int H, W, Cin, Cout, ks, pad;
+    int cpitch;       // channel pitch of the weight planes' K axis: k = tap * cpitch + c
+    long long M;      // B*H*W
+    int accumulate;
+    int tiles_n, tiles_total;
+};
+
+constexpr int TC_BM = 128;
+
+constexpr int tmem_cols(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : (n <= 256 ? 256 : 512))); }
+constexpr int tc_max(int a, int b) { return a > b ? a : b; }
+
+template <int BN, int BK, int NH, int TERMS, bool PERSIST, int MINB>
+struct TcCfg {
+    static constexpr int ROW_BYTES = BK * 2;
+    static constexpr int A_BYTES = TC_BM * ROW_BYTES;
+    static constexpr int B_BYTES = BN * ROW_BYTES;
+    static constexpr int NA = 1 + (TERMS & 1);
+    static constexpr int NBP = 1 + ((TERMS >> 1) & 1);
+    static constexpr int STAGE_BYTES = NA * A_BYTES + NBP * B_BYTES;
+    static constexpr int OFF_ALO = A_BYTES;
+    static constexpr int OFF_BHI = NA * A_BYTES;
+    static constexpr int OFF_BLO = OFF_BHI + B_BYTES;
+    static constexpr int EPI_BYTES = 4 * 2 * 4096;                  // 4 epilogue warps x two 32x32 fp32 staging tiles
+    static constexpr int STAT_BYTES = 4 * BN * 16;                  // 4 warps x BN channels x float4
+    static constexpr int TAIL_BYTES = EPI_BYTES + STAT_BYTES;
+    static constexpr int TOTAL_BUDGET = (MINB == 2 ? 113 : 227) * 1024 - 1024 /*align*/ - 256 /*barriers*/;
+    static constexpr int STAGE_BUDGET = PERSIST ? TOTAL_BUDGET - TAIL_BYTES : TOTAL_BUDGET;
+    static constexpr int STAGES = (STAGE_BUDGET / STAGE_BYTES) > 8 ? 8 : (STAGE_BUDGET / STAGE_BYTES);
+    static constexpr int EPI_OFF = PERSIST ? STAGES * STAGE_BYTES : 0;
+    static constexpr int BAR_OFF = PERSIST ? EPI_OFF + TAIL_BYTES : tc_max(STAGES * STAGE_BYTES, TAIL_BYTES);
+    static constexpr int NACC = NH + (TERMS ? 1 : 0);
+    static constexpr int ACC_COLS = NACC * BN;                      // one accumulator set
+    static constexpr int NSETS = PERSIST ? 2 : 1;
+    static constexpr int TMEM_COLS = tmem_cols(NSETS * ACC_COLS);
+    static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256;
+    static_assert(STAGES >= 2, "at least two pipeline stages");
+    static_assert(NSETS * ACC_COLS <= 512, "accumulators must fit in TMEM");
+    static_assert(STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "swizzle atoms need 1 KB alignment");
+};
+
+// compensated fp32 accumulation (the statistics of a persistent CTA run over thousands of pixels)
+__device__ __forceinline__ void tc_kahan_add(float& s, float& e, float x) {
+    const float y = x - e;
+    const float t = s + y;
+    e = (t - s) - y;
+    s = t;
+}
+
+template <int BN, int BK, int NH, int TERMS, bool PERSIST, int MINB>
+__global__ void __launch_bounds__(192, MINB)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+               const __grid_constant__ CUtensorMap tmZ, const TcArgs p) {
+    using Cfg = TcCfg<BN, BK, NH, TERMS, PERSIST, MINB>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int NSETS = Cfg::NSETS;
+    FSDET_TC_DYN_SMEM(smem_raw);
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* epi = smem + Cfg::EPI_OFF;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* acc_full = empty_bar + STAGES;      // [NSETS] MMA issuer -> epilogue
+    uint64_t* acc_empty = acc_full + 2;           // [NSETS] epilogue (4 warps) -> MMA issuer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int kchunks = p.Cin / BK;
+    const int nk = p.ks * p.ks * kchunks;
+    const int tiles_n = p.tiles_n;
+    const int tiles_total = p.tiles_total;
+    const int tile_step = PERSIST ? (int)gridDim.x : tiles_total;   // non-persistent: exactly one tile per CTA
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmAhi);
+        if (TERMS & 1) tma_prefetch_desc(&tmAlo);
+        tma_prefetch_desc(&tmBhi);
+        if (TERMS & 2) tma_prefetch_desc(&tmBlo);
+        tma_prefetch_desc(&tmZ);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < NSETS; ++a) {
+            mbar_init(&acc_full[a], 1);
+            mbar_init(&acc_empty[a], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int HW = p.H * p.W;
+            unsigned it = 0;                                   // k-blocks issued so far (all tiles)
+            for (int tile = blockIdx.x; tile < tiles_total; tile += tile_step) {
+                const int n_tile = tile % tiles_n;
+                const long long m0 = (long long)(tile / tiles_n) * TC_BM;
+                const int img = (int)(m0 / HW);
+                const int rem = (int)(m0 - (long long)img * HW);
+                const int ph = rem / p.W, pw = rem - ph * p.W;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                    uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                    const int tap = kb / kchunks;
+                    const int c0 = (kb - tap * kchunks) * BK;
+                    const int r = tap / p.ks, sx = tap - r * p.ks;
+                    tma_load_im2col_4d(st, &tmAhi, &full_bar[s], c0, pw - p.pad, ph - p.pad, img, (uint16_t)sx, (uint16_t)r);
+                    if (TERMS & 1)
+                        tma_load_im2col_4d(st + Cfg::OFF_ALO, &tmAlo, &full_bar[s], c0, pw - p.pad, ph - p.pad, img, (uint16_t)sx,
+                                           (uint16_t)r);
+                    tma_load_2d(st + Cfg::OFF_BHI, &tmBhi, &full_bar[s], tap * p.cpitch + c0, n_tile * BN);
+                    if (TERMS & 2) tma_load_2d(st + Cfg::OFF_BLO, &tmBlo, &full_bar[s], tap * p.cpitch + c0, n_tile * BN);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=f16, both K-major, N=BN, M=128
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            unsigned it = 0;
+            unsigned t = 0;                                    // tiles done by this CTA
+            for (int tile = blockIdx.x; tile < tiles_total; tile += tile_step, ++t) {
+                const unsigned a = t % NSETS;
+                mbar_wait(&acc_empty[a], ((t / NSETS) & 1u) ^ 1u);    // the epilogue has drained this accumulator set
+                tc_fence_after();
+                const uint32_t acc = tmem_base + a * (uint32_t)Cfg::ACC_COLS;
+                uint32_t lo_started = 0;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
+                    uint64_t ahi, alo, bhi, blo;
+                    if constexpr (BK == 64) {
+                        ahi = umma_desc_k_sw128(sa); alo = umma_desc_k_sw128(sa + Cfg::OFF_ALO);
+                        bhi = umma_desc_k_sw128(sa + Cfg::OFF_BHI); blo = umma_desc_k_sw128(sa + Cfg::OFF_BLO);
+                    } else {
+                        ahi = umma_desc_k_sw64(sa); alo = umma_desc_k_sw64(sa + Cfg::OFF_ALO);
+                        bhi = umma_desc_k_sw64(sa + Cfg::OFF_BHI); blo = umma_desc_k_sw64(sa + Cfg::OFF_BLO);
+                    }
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 halves = 32 B along K inside the swizzle atom
+                        const uint32_t dhi = acc + (uint32_t)((kb % NH) * BN);
+                        const uint32_t dlo = acc + (uint32_t)(NH * BN);
+                        umma_f16(dhi, ahi + adv, bhi + adv, idesc, (kb >= NH || k > 0) ? 1u : 0u);
+                        if (TERMS & 1) { umma_f16(dlo, alo + adv, bhi + adv, idesc, lo_started); lo_started = 1u; }
+                        if (TERMS & 2) { umma_f16(dlo, ahi + adv, blo + adv, idesc, lo_started); lo_started = 1u; }
+                    }
+                    umma_commit(&empty_bar[s]);   // frees the smem slot when these MMAs have read it
+                }
+                umma_commit(&acc_full[a]);        // accumulator set complete
+            }
+        }
+    } else {
+        // epilogue warps 2..5 -> TMEM lane quarters (warp % 4); each warp owns 32 output pixels of the tile
+        const int quarter = warp & 3;
+        const float inv = 1.f / (scale_from_amax(p.amax_a ? ldg_f32(p.amax_a) : 0.f) * scale_from_amax(p.amax_b ? ldg_f32(p.amax_b) : 0.f));
+        const int nhi = nk < NH ? nk : NH;
+        uint8_t* stage_buf = epi + quarter * 8192;             // two 4 KB buffers per warp
+        const bool want_stats = p.stats != nullptr;
+        float ssum[BN / 32], esum[BN / 32], ssq[BN / 32], esq[BN / 32], smin[BN / 32], smax[BN / 32];
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) { ssum[c] = esum[c] = ssq[c] = esq[c] = 0.f; smin[c] = INFINITY; smax[c] = -INFINITY; }
+        unsigned t = 0, stores = 0;                            // tiles done, TMA stores issued by this warp
+        for (int tile = blockIdx.x; tile < tiles_total; tile += tile_step, ++t) {
+            const unsigned a = t % NSETS;
+            const int n_tile = tile % tiles_n;
+            const long long m0 = (long long)(tile / tiles_n) * TC_BM;
+            const long long mrow = m0 + quarter * 32;
+            mbar_wait(&acc_full[a], (t / NSETS) & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t r[32];
+                float acc[32];
+                const uint32_t taddr = tmem_base + a * (uint32_t)Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16) + ch * 32;
+                if constexpr (TERMS != 0) {
+                    tmem_ld32(taddr + NH * BN, r);             // lo terms first (small), then the hi*hi partial sums
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+                }
+                for (int h = nhi - 1; h >= 0; --h) {
+                    tmem_ld32(taddr + h * BN, r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+                }
+                const int n0 = n_tile * BN + ch * 32;
+                if (n0 < p.Cout && mrow < p.M) {               // warp-uniform
+                    uint8_t* buf = stage_buf + (stores & 1u) * 4096;
+                    if (stores >= 2) {                         // the store that last read this buffer must have drained
+                        if (lane == 0) tma_store_wait_read<1>();
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 v = make_float4(acc[4 * j] * inv, acc[4 * j + 1] * inv, acc[4 * j + 2] * inv, acc[4 * j + 3] * inv);
+                        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (p.accumulate) tma_reduce_add_2d(&tmZ, buf, n0, (int)mrow);
+                        else tma_store_2d(&tmZ, buf, n0, (int)mrow);
+                        tma_store_commit();
+                    }
+                    ++stores;
+                    if (want_stats) {
+                        // column `lane` of the staged 32x32 tile (conflict-free: the 16-byte chunks of a row are a
+                        // permutation), rows beyond the tensor's last pixel excluded
+                        const long long left = p.M - mrow;
+                        const int nvalid = left < 32 ? (int)left : 32;
+                        float s = 0.f, q = 0.f, mn = INFINITY, mx = -INFINITY;
+                        for (int rr = 0; rr < nvalid; ++rr) {
+                            const float v = *reinterpret_cast<const float*>(buf + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + (lane & 3) * 4);
+                            s += v; q += v * v; mn = fminf(mn, v); mx = fmaxf(mx, v);
+                        }
+                        tc_kahan_add(ssum[ch], esum[ch], s);
+                        tc_kahan_add(ssq[ch], esq[ch], q);
+                        smin[ch] = fminf(smin[ch], mn);
+                        smax[ch] = fmaxf(smax[ch], mx);
+                    }
+                }
+            }
+            // this warp's TMEM reads of set `a` are complete (tcgen05.wait::ld in tmem_ld32): hand the set back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+        }
+        if (lane == 0) tma_store_wait_read<0>();               // shared memory must outlive the bulk reads
+        __syncwarp();
+        if (want_stats) {
+            // fold the four warps (pixel quarters) in a fixed order and write this CTA's partial row
+            float4* sbuf = reinterpret_cast<float4*>(epi + Cfg::EPI_BYTES);   // [4][BN]
+#pragma unroll
+            for (int ch = 0; ch < BN / 32; ++ch)
+                sbuf[quarter * BN + ch * 32 + lane] = make_float4(ssum[ch] - esum[ch], ssq[ch] - esq[ch], smin[ch], smax[ch]);
+            named_bar_sync(1, 128);
+            const int e = (warp - 2) * 32 + lane;
+            const int n_tile = (int)(blockIdx.x % (unsigned)tiles_n);
+            const long long row = (long long)(blockIdx.x / (unsigned)tiles_n);
+            for (int c = e; c < BN; c += 128) {
+                float4 tt = sbuf[c];
+#pragma unroll
+                for (int qq = 1; qq < 4; ++qq) {
+                    const float4 o = sbuf[qq * BN + c];
+                    tt.x += o.x; tt.y += o.y; tt.z = fminf(tt.z, o.z); tt.w = fmaxf(tt.w, o.w);
+                }
+                const int n = n_tile * BN + c;
+                if (n < p.Cout) {
+                    float* dst = p.stats + row * 4 * p.Cout + n;
+                    dst[0] = tt.x; dst[p.Cout] = tt.y; dst[2 * p.Cout] = tt.z; dst[3 * p.Cout] = tt.w;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)Cfg::TMEM_COLS);
+    }
+}

@@ -21,6 +21,28 @@ import os
 USE_TC = os.environ.get('FSDET_TC', '1') != '0'
 TC_PARTS = set(os.environ.get('FSDET_TC_PARTS', 'fwd,dgrad,wgrad,head').split(','))  # debugging: which GEMMs may use it
 
+
+def _parse_terms(spec):
+    """'fwd=3,dgrad=3,wgrad=0,head=3' -> dict.  Operand-term mode of each GEMM class (include/fsdet.h,
+    fsdet_conv_tc_fwd `mode` bits 0-1): 3 = hi*hi + lo*hi + hi*lo (fp32 grade), 1 / 2 = one operand exact and the
+    other rounded to fp16, 0 = fp16 x fp16.  The defaults are the measured per-class decision."""
+    d = {'fwd': 3, 'dgrad': 3, 'wgrad': 3, 'head': 3}
+    for item in filter(None, (spec or '').split(',')):
+        k, v = item.split('=')
+        if k not in d or int(v) not in (0, 1, 2, 3):
+            raise ValueError('FSDET_TC_TERMS: bad item %r' % item)
+        d[k] = int(v)
+    return d
+
+
+TC_TERMS = _parse_terms(os.environ.get('FSDET_TC_TERMS'))
+# persistent tile loop (one CTA per SM, double-buffered TMEM accumulators) for the short-K layers
+TC_PERSIST = os.environ.get('FSDET_TC_PERSIST', '0') == '1'
+
+
+def tc_mode(name):
+    return TC_TERMS[name] | (16 if TC_PERSIST else 0)
+
 LEAKY_SLOPE = 0.1
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -321,11 +343,11 @@ class NetRunner(object):
             wh, wl, wa = self._split_tensor(ptr(w_ohwi), cin, cin, cout * k * k, x.dev, st, cpad, w_amax)
             if name == 'fwd':   # the flip-transposed copy used by the input-gradient GEMM has the same absolute maximum
                 w_ohwi._fsdet_amax = (wa, w_ohwi._version)
+            mode = tc_mode(name)
             self._timed('conv_tc', flops, 'fsdet_conv_tc_fwd', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(xa), ptr(wa), z.ptr, z.ld,
-                        x.B, x.H, x.W, _round_up(cin, 32), cpad, cout, k, acc, st)
-            if stat_rows_out is not None:
-                call('fsdet_colstats', z.ptr, z.ld, x.npix, cout, ptr(stat_rows_out), st)
-                return _lib.lib.fsdet_colstats_rows(x.npix)
+                        x.B, x.H, x.W, _round_up(cin, 32), cpad, cout, k, acc, mode, ptr(stat_rows_out), st)
+            if stat_rows_out is not None:   # BatchNorm partial rows come out of the convolution's epilogue
+                return _lib.lib.fsdet_conv_tc_stat_rows(x.B, x.H, x.W, _round_up(cin, 32), cout, k, mode)
             return 0
         self._timed('conv_igemm', flops, 'fsdet_conv_fwd', x.ptr, x.ld, ptr(w_ohwi), ptr(bias), z.ptr, z.ld,
                     ptr(stat_rows_out), x.B, x.H, x.W, cin, cout, k, acc, st)
@@ -513,7 +535,7 @@ class NetRunner(object):
             assert cout_p == s.cout, 'BatchNorm conv with Cout % 4 != 0 is unsupported'
             z = Act.new(B, H, W, s.cout, dev)
             use_batch_stats = training or not bn.track_running_stats
-            rows_cap = max(_lib.lib.fsdet_conv_stat_rows(npix), _lib.lib.fsdet_colstats_rows(npix))
+            rows_cap = max(_lib.lib.fsdet_conv_stat_rows(npix), _lib.lib.fsdet_colstats_rows(npix), (npix + 127) // 128)
             stat = _empty(rows_cap + _lib.lib.fsdet_bn_stat_scratch_rows(), 4 * s.cout, device=dev) if use_batch_stats else None
             rows = self._conv('fwd', x, wuse, None, z, stat, cin_p, s.cout, s.k, 0, st)
             vec = _empty(5, s.cout, device=dev)  # mean, invstd, scale, shift, max|xhat| (batch statistics only)
@@ -717,12 +739,13 @@ class NetRunner(object):
         if x.nchw is None and self._wgrad_tc_ok(cin_p, cout, k):
             xh, xl, xa = self._planes(x, st)
             dh, dl, da = self._planes(dz, st)
-            nws = _lib.lib.fsdet_conv_tc_wgrad_workspace_floats(x.B, x.H, x.W, ci64, co64, k)
+            mode = TC_TERMS['wgrad']
+            nws = _lib.lib.fsdet_conv_tc_wgrad_workspace_floats(x.B, x.H, x.W, ci64, co64, k, mode)
             ws = _empty(max(nws, 4), device=dev)
             padded = (ci64 != cin_p) or (co64 != cout)
             tgt = _empty(co64, k * k, ci64, device=dev) if padded else out_tensor
             self._timed('wgrad_tc', flops, 'fsdet_conv_tc_wgrad', ptr(xh), ptr(xl), ptr(dh), ptr(dl), ptr(xa), ptr(da),
-                        ptr(tgt), ptr(ws), nws, x.B, x.H, x.W, ci64, co64, k, st)
+                        ptr(tgt), ptr(ws), nws, x.B, x.H, x.W, ci64, co64, k, mode, st)
             if padded:  # crop the zero channels / rows: rows [0, cout) are contiguous, channels via pad_channels
                 call('fsdet_pad_channels', ptr(tgt), ci64, ptr(out_tensor), cin_p, cout * k * k, st)
             return

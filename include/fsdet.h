@@ -15,8 +15,9 @@
  *     CURRENT device and returns immediately;
  *   - return value: 0 = ok, <0 = invalid argument (see fsdet_last_error()),
  *     >0 = cudaError_t of the failed launch;
- *   - re-entrant: no mutable global state (one thread per GPU or one process
- *     per GPU are both fine).
+ *   - re-entrant: no mutable global state - the only process-wide data are two
+ *     driver entry points resolved once (thread-safe, immutable afterwards);
+ *     one thread per GPU or one process per GPU are both fine.
  *
  * Layouts.  Activations inside the library are NHWC fp32: a 2-D array
  * [B*H*W pixels][ld] of which `C` channels starting at the given pointer are
@@ -91,30 +92,40 @@ int fsdet_pad_channels(const float* in, int cin, float* out, int cout, size_t ro
  * (fsdet_conv_tc_supported); `cpitch` >= Cin is the channel pitch of the planes
  * (activation rows and the weights' [tap][channel] axis), so 32-channel tensors
  * stored in 64-channel-padded planes are read without touching the padding.
- * Operands are fp16 hi/lo planes produced by fsdet_amax + fsdet_split_f16:
- * the tensor is scaled by the power of two that maps its absolute maximum
- * into [512, 1024), hi = fp16(s*x), lo = fp16(s*x - hi); three MMAs per K step
- * (hi*hi + lo*hi + hi*lo) keep ~22 mantissa bits so that the fp32 reference's
- * results - including its max-pool arg-max decisions - are reproduced.
- * x_hi/x_lo dense NHWC [B*H*W][Cin] fp16, w_hi/w_lo [Cout][k*k*Cin] fp16,
+ * Operands are fp16 hi/lo planes (fsdet_amax + fsdet_split_f16, or written
+ * directly by the producing BN / weight-preparation kernels): the tensor is
+ * scaled by the power of two that maps its absolute maximum into [512, 1024),
+ * hi = fp16(s*x), lo = fp16(s*x - hi).
+ * `mode`: bits 0-1 select the operand terms added to hi*hi -
+ *     bit 0: x_lo * w_hi (x exact to 22 bits), bit 1: x_hi * w_lo (w exact);
+ *     3 = fp32-grade (reproduces the fp32 reference incl. its max-pool arg-max
+ *     decisions), 0 = plain fp16 x fp16 -> fp32.  Planes that are not used may be
+ *     NULL.  Bit 4 (16): persistent tile loop for short-K layers (one CTA per
+ *     SM, double-buffered TMEM accumulators).
+ * x_hi/x_lo dense NHWC [B*H*W][cpitch] fp16, w_hi/w_lo [Cout][k*k*cpitch] fp16,
  * amax_x / amax_w: device floats holding the tensors' absolute maxima (NULL =
  * planes are unscaled).  Output fp32 z[p][n] (+ previous z when accumulate
- * != 0).  BatchNorm partial sums are produced by fsdet_colstats in the layout
- * fsdet_bn_finalize reads. */
+ * != 0).
+ * stat_partial (optional, accumulate == 0 only): train-mode BatchNorm partial
+ * rows float [fsdet_conv_tc_stat_rows(...)][4*Cout] = (sum | sum of squares |
+ * min | max) per CTA, taken from the output tile in the epilogue (no separate
+ * pass over z); the layout fsdet_bn_finalize reads. */
 int fsdet_conv_tc_supported(int Cin, int Cout, int ksize);
+int fsdet_conv_tc_stat_rows(int B, int H, int W, int Cin, int Cout, int ksize, int mode);
 int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* amax_x,
                       const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin, int cpitch, int Cout,
-                      int ksize, int accumulate, void* stream);
+                      int ksize, int accumulate, int mode, float* stat_partial, void* stream);
 /* Weight gradient on the tensor cores (pixels are the GEMM K dimension; both
  * operands are consumed MN-major straight from the NHWC planes).  Needs
  * Cin % 64 == 0 and Cout % 64 == 0.  dw [Cout][k*k][Cin] fp32 (OHWI);
  * workspace float [fsdet_conv_tc_wgrad_workspace_floats(...)] for the split-K
- * partials (reduced in a fixed order). */
+ * partials (reduced in a fixed order).  `mode` bits 0-1 as above with
+ * bit 0: dz_lo * x_hi, bit 1: dz_hi * x_lo. */
 int fsdet_conv_tc_wgrad_supported(int Cin, int Cout, int ksize);
-size_t fsdet_conv_tc_wgrad_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize);
+size_t fsdet_conv_tc_wgrad_workspace_floats(int B, int H, int W, int Cin, int Cout, int ksize, int mode);
 int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const void* dz_hi, const void* dz_lo, const float* amax_x,
                         const float* amax_dz, float* dw, float* workspace, size_t workspace_floats, int B, int H,
-                        int W, int Cin, int Cout, int ksize, void* stream);
+                        int W, int Cin, int Cout, int ksize, int mode, void* stream);
 /* absolute maximum of fp32 [rows][ld] (first C columns) -> *amax_out (device float) */
 int fsdet_amax(const float* src, int ld, int C, size_t rows, float* amax_out, void* stream);
 /* fp32 [rows][ld] (first C columns) -> two dense fp16 planes [rows][Cpad] of the

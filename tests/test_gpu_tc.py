@@ -95,27 +95,90 @@ TC_CASES = [
 ]
 
 
+def plane_scale(P_):
+    import math
+    a = P_.amax.item()
+    return 2.0 ** (10 - math.frexp(a)[1]) if a > 0 else 1.0
+
+
+def planes_nchw(t, B, H, W, C):
+    """[B*H*W][C] fp16 plane -> float64 NCHW"""
+    return t[:, :C].double().view(B, H, W, C).permute(0, 3, 1, 2)
+
+
+# mode = operand terms (bits 0-1) | 16 for the persistent tile loop (short-K layers only; ignored by the others)
+MODES = [3, 3 | 16, 0, 0 | 16, 1, 2]
+
+
+@pytest.mark.parametrize('mode', MODES)
 @pytest.mark.parametrize('B,H,W,Cin,Cout,k', TC_CASES)
-def test_conv_tc_fwd(L, B, H, W, Cin, Cout, k):
+def test_conv_tc_fwd(L, B, H, W, Cin, Cout, k, mode):
+    """Every term mode multiplies exactly the planes it names (checked against a float64 convolution of those planes
+    to 1e-5); mode 3 additionally reproduces the float64 convolution of the fp32 inputs to 1e-5.  The BatchNorm
+    statistics that come out of the epilogue are those of the stored output."""
     g = torch.Generator(device='cuda').manual_seed(B + H + Cin + Cout)
     x = torch.randn(B, Cin, H, W, device='cuda', generator=g)
     w = torch.randn(Cout, Cin, k, k, device='cuda', generator=g) * 0.05
-    ref = F.conv2d(x.double(), w.double(), None, 1, (k - 1) // 2)
     X = split(L, nhwc(x))
     Wp = split(L, w.permute(0, 2, 3, 1).contiguous().view(Cout, -1))
+    terms = mode & 3
+    sx, sw = plane_scale(X), plane_scale(Wp)
+    xh, xl = planes_nchw(X.hi, B, H, W, Cin), planes_nchw(X.lo, B, H, W, Cin)
+    wh = Wp.hi.double().view(Cout, k, k, Cin).permute(0, 3, 1, 2)
+    wl = Wp.lo.double().view(Cout, k, k, Cin).permute(0, 3, 1, 2)
+    conv = lambda a, b: F.conv2d(a, b, None, 1, (k - 1) // 2)
+    ref = conv(xh, wh)
+    if terms & 1:
+        ref = ref + conv(xl, wh)
+    if terms & 2:
+        ref = ref + conv(xh, wl)
+    ref = ref / (sx * sw)
     assert L.lib.fsdet_conv_tc_supported(Cin, Cout, k)
     ld = Cout + 4
     z = torch.zeros(B * H * W, ld, device='cuda')
-    L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), X.lo.data_ptr(), Wp.hi.data_ptr(), Wp.lo.data_ptr(), X.a, Wp.a, z.data_ptr(), ld,
-           B, H, W, Cin, Cin, Cout, k, 0, st())
+    rows = L.lib.fsdet_conv_tc_stat_rows(B, H, W, Cin, Cout, k, mode)
+    part = torch.full((rows, 4 * Cout), 123.0, device='cuda')
+    lo_x = X.lo.data_ptr() if terms & 1 else None      # planes a mode does not use may be NULL
+    lo_w = Wp.lo.data_ptr() if terms & 2 else None
+    L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), lo_x, Wp.hi.data_ptr(), lo_w, X.a, Wp.a, z.data_ptr(), ld,
+           B, H, W, Cin, Cin, Cout, k, 0, mode, part.data_ptr(), st())
     torch.cuda.synchronize()
     got = z[:, :Cout].contiguous().view(B, H, W, Cout).permute(0, 3, 1, 2)
-    assert rel(got, ref) < TOL_TC
+    # modes < 3 keep ONE fp32 accumulator for the hi*hi products (the tensor core's accumulation truncates: 3e-5)
+    tol = TOL_TC if terms == 3 else 3e-5
+    assert rel(got, ref) < tol
+    if terms == 3:
+        assert rel(got, conv(x.double(), w.double())) < TOL_TC
     assert (z[:, Cout:] == 0).all()
-    L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), X.lo.data_ptr(), Wp.hi.data_ptr(), Wp.lo.data_ptr(), X.a, Wp.a, z.data_ptr(), ld,
-           B, H, W, Cin, Cin, Cout, k, 1, st())
+    zz = z[:, :Cout]
+    s = part.double().sum(0)
+    assert rel(s[:Cout], zz.double().sum(0)) < 1e-5 or (s[:Cout] - zz.double().sum(0)).abs().max() < 1e-3
+    assert rel(s[Cout:2 * Cout], (zz.double() ** 2).sum(0)) < 1e-5
+    assert torch.equal(part[:, 2 * Cout:3 * Cout].min(0)[0], zz.min(0)[0])
+    assert torch.equal(part[:, 3 * Cout:].max(0)[0], zz.max(0)[0])
+    L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), lo_x, Wp.hi.data_ptr(), lo_w, X.a, Wp.a, z.data_ptr(), ld,
+           B, H, W, Cin, Cin, Cout, k, 1, mode, None, st())
     got2 = z[:, :Cout].contiguous().view(B, H, W, Cout).permute(0, 3, 1, 2)
-    assert rel(got2, 2 * ref) < TOL_TC
+    assert rel(got2, 2 * ref) < tol
+
+
+def test_conv_tc_term_modes_precision(L):
+    """What each mode costs in accuracy on a long-K layer (printed; the bars are loose upper bounds)."""
+    B, H, W, Cin, Cout, k = 2, 13, 13, 1024, 1024, 3
+    g = torch.Generator(device='cuda').manual_seed(9)
+    x = torch.randn(B, Cin, H, W, device='cuda', generator=g)
+    w = torch.randn(Cout, Cin, k, k, device='cuda', generator=g) * 0.05
+    ref = F.conv2d(x.double(), w.double(), None, 1, 1)
+    X = split(L, nhwc(x))
+    Wp = split(L, w.permute(0, 2, 3, 1).contiguous().view(Cout, -1))
+    errs = {}
+    for mode, bar in ((3, 1e-5), (1, 4e-4), (2, 4e-4), (0, 6e-4)):
+        z = torch.zeros(B * H * W, Cout, device='cuda')
+        L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), X.lo.data_ptr(), Wp.hi.data_ptr(), Wp.lo.data_ptr(), X.a, Wp.a,
+               z.data_ptr(), Cout, B, H, W, Cin, Cin, Cout, k, 0, mode, None, st())
+        errs[mode] = rel(z.view(B, H, W, Cout).permute(0, 3, 1, 2), ref)
+        assert errs[mode] < bar, (mode, errs)
+    print('conv_tc relative error by term mode:', errs)
 
 
 def test_colstats(L):
@@ -140,24 +203,39 @@ WG_CASES = [
 ]
 
 
+@pytest.mark.parametrize('mode', [3, 0, 1, 2])
 @pytest.mark.parametrize('B,H,W,Cin,Cout,k', WG_CASES)
-def test_conv_tc_wgrad(L, B, H, W, Cin, Cout, k):
+def test_conv_tc_wgrad(L, B, H, W, Cin, Cout, k, mode):
     g = torch.Generator(device='cuda').manual_seed(B + H + Cin + Cout + 1)
     x = torch.randn(B, Cin, H, W, device='cuda', generator=g)
-    w0 = torch.randn(Cout, Cin, k, k, device='cuda', generator=g) * 0.05
-    w = w0.double().requires_grad_(True)
     dz = torch.randn(B, Cout, H, W, device='cuda', generator=g)
-    F.conv2d(x.double(), w, None, 1, (k - 1) // 2).backward(dz.double())   # float64 reference
     X = split(L, nhwc(x))
     D = split(L, nhwc(dz))
+    sx, sd = plane_scale(X), plane_scale(D)
+    xh, xl = planes_nchw(X.hi, B, H, W, Cin), planes_nchw(X.lo, B, H, W, Cin)
+    dh, dl = planes_nchw(D.hi, B, H, W, Cout), planes_nchw(D.lo, B, H, W, Cout)
+
+    def wgrad64(xx, dd):
+        w = torch.zeros(Cout, Cin, k, k, device='cuda', dtype=torch.float64, requires_grad=True)
+        F.conv2d(xx, w, None, 1, (k - 1) // 2).backward(dd)
+        return w.grad
+    ref = wgrad64(xh, dh)
+    if mode & 1:
+        ref = ref + wgrad64(xh, dl)
+    if mode & 2:
+        ref = ref + wgrad64(xl, dh)
+    ref = ref / (sx * sd)
     assert L.lib.fsdet_conv_tc_wgrad_supported(Cin, Cout, k)
-    nws = L.lib.fsdet_conv_tc_wgrad_workspace_floats(B, H, W, Cin, Cout, k)
+    nws = L.lib.fsdet_conv_tc_wgrad_workspace_floats(B, H, W, Cin, Cout, k, mode)
     ws = torch.empty(max(nws, 4), device='cuda')
     dw = torch.full((Cout, k * k, Cin), 7.0, device='cuda')
-    L.call('fsdet_conv_tc_wgrad', X.hi.data_ptr(), X.lo.data_ptr(), D.hi.data_ptr(), D.lo.data_ptr(), X.a, D.a, dw.data_ptr(),
-           ws.data_ptr(), nws, B, H, W, Cin, Cout, k, st())
+    L.call('fsdet_conv_tc_wgrad', X.hi.data_ptr(), X.lo.data_ptr() if mode & 2 else None, D.hi.data_ptr(),
+           D.lo.data_ptr() if mode & 1 else None, X.a, D.a, dw.data_ptr(), ws.data_ptr(), nws, B, H, W, Cin, Cout, k, mode, st())
     torch.cuda.synchronize()
-    assert rel(dw.view(Cout, k, k, Cin).permute(0, 3, 1, 2), w.grad) < TOL_TC
+    got = dw.view(Cout, k, k, Cin).permute(0, 3, 1, 2)
+    assert rel(got, ref) < (TOL_TC if mode == 3 else 3e-5)
+    if mode == 3:
+        assert rel(got, wgrad64(x.double(), dz.double())) < TOL_TC
 
 
 def test_conv_tc_padded_channels_and_small_cout(L):
@@ -173,7 +251,7 @@ def test_conv_tc_padded_channels_and_small_cout(L):
     Wp = split(L, w.detach().permute(0, 2, 3, 1).contiguous().view(Cout * k * k, Cin), 64)
     z = torch.zeros(B * H * W, Cout, device='cuda')
     L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), X.lo.data_ptr(), Wp.hi.data_ptr(), Wp.lo.data_ptr(), X.a, Wp.a, z.data_ptr(), Cout,
-           B, H, W, 32, 64, Cout, k, 0, st())
+           B, H, W, 32, 64, Cout, k, 0, 3, None, st())
     assert rel(z.view(B, H, W, Cout).permute(0, 3, 1, 2), ref) < TOL_TC
     # dgrad: GEMM Cin = 64 (dz channels), Cout = 32
     wt = torch.empty(Cin, k * k, Cout, device='cuda')
@@ -182,13 +260,13 @@ def test_conv_tc_padded_channels_and_small_cout(L):
     D = split(L, nhwc(dz))
     dx = torch.zeros(B * H * W, Cin, device='cuda')
     L.call('fsdet_conv_tc_fwd', D.hi.data_ptr(), D.lo.data_ptr(), T.hi.data_ptr(), T.lo.data_ptr(), D.a, T.a, dx.data_ptr(), Cin,
-           B, H, W, Cout, Cout, Cin, k, 0, st())
+           B, H, W, Cout, Cout, Cin, k, 0, 3, None, st())
     assert rel(dx.view(B, H, W, Cin).permute(0, 3, 1, 2), x.grad) < TOL_TC
     # wgrad with padded input channels: result [Cout][9][64], first 32 channels valid, rest zero
-    nws = L.lib.fsdet_conv_tc_wgrad_workspace_floats(B, H, W, 64, Cout, k)
+    nws = L.lib.fsdet_conv_tc_wgrad_workspace_floats(B, H, W, 64, Cout, k, 3)
     ws = torch.empty(max(nws, 4), device='cuda')
     dw = torch.full((Cout, k * k, 64), 7.0, device='cuda')
     L.call('fsdet_conv_tc_wgrad', X.hi.data_ptr(), X.lo.data_ptr(), D.hi.data_ptr(), D.lo.data_ptr(), X.a, D.a, dw.data_ptr(),
-           ws.data_ptr(), nws, B, H, W, 64, Cout, k, st())
+           ws.data_ptr(), nws, B, H, W, 64, Cout, k, 3, st())
     assert rel(dw[:, :, :32].reshape(Cout, k, k, Cin).permute(0, 3, 1, 2), w.grad) < TOL_TC
     assert (dw[:, :, 32:] == 0).all()

@@ -1,4 +1,4 @@
-// Host build of csrc/conv_tc_persist.cuh against FUNCTIONAL MODELS of the PTX wrappers it uses (see
+// Host build of csrc/conv_tc_kernels.cuh against FUNCTIONAL MODELS of the PTX wrappers it uses (see
 // cuda_host_emul.h for the thread model).  What is modelled: mbarriers (arrival counts, transaction bytes, phase
 // parity), the im2col / tiled TMA loads (tiles land unswizzled), tcgen05.mma (fp16 x fp16 -> fp32 into a TMEM array),
 // tcgen05.commit, tcgen05.ld, the swizzled 32x32 TMA store / reduce-add.  What this validates: the kernel's CONTROL
@@ -24,19 +24,8 @@ unsigned char* g_dyn_smem = nullptr;
 namespace fsdet {
 void set_error(const char*, ...) {}
 
-// ---- declarations shared with conv_tc.cu (kept in sync by hand: only the fields the kernel reads matter)
-struct TcArgs {
-    float* z;
-    const float* amax_a;
-    const float* amax_b;
-    int ldz;
-    int H, W, Cin, Cout, ks, pad;
-    int cpitch;
-    long long M;
-    int accumulate;
-};
-constexpr int TC_BM = 128;
-constexpr int tmem_cols(int n) { return n <= 32 ? 32 : (n <= 64 ? 64 : (n <= 128 ? 128 : (n <= 256 ? 256 : 512))); }
+// ---- helpers conv_tc.cu defines before including the kernel header
+constexpr int EMUL_BM = 128;   // == TC_BM (checked below)
 static inline float scale_from_amax(float a) {   // conv_tc.cu: power of two mapping amax into [512, 1024)
     if (!(a > 0.f) || !std::isfinite(a)) return 1.f;
     int ex = (int)((__float_as_uint(a) >> 23) & 0xff) - 126;
@@ -119,7 +108,7 @@ static inline void tma_load_im2col_4d(void* dst, const CUtensorMap* map, uint64_
     uint16_t* d = reinterpret_cast<uint16_t*>(dst);
     long long pix0 = ((long long)n * m->H + (h + m->pad)) * m->W + (w + m->pad);
     const long long total = (long long)m->B * m->H * m->W;
-    for (int i = 0; i < TC_BM; ++i) {
+    for (int i = 0; i < EMUL_BM; ++i) {
         const long long pi = pix0 + i;
         uint16_t* row = d + (size_t)i * m->bk;
         bool ok = pi < total;
@@ -136,7 +125,7 @@ static inline void tma_load_im2col_4d(void* dst, const CUtensorMap* map, uint64_
             row[k] = (ok && ch < m->C) ? m->base[(((size_t)img * m->H + y) * m->W + x) * m->cpitch + ch] : (uint16_t)0;
         }
     }
-    bar_complete_tx(bar, (uint32_t)(TC_BM * m->bk * 2));
+    bar_complete_tx(bar, (uint32_t)(EMUL_BM * m->bk * 2));
 }
 static inline void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     const MapModel* m = model(map);
@@ -193,51 +182,105 @@ static inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     for (int j = 0; j < 32; ++j) memcpy(&r[j], &g_tmem[row][col + j], 4);
 }
 
-#include "../../fewshot_detection_b200/csrc/conv_tc_persist.cuh"
+// barrier over a subset of the block's threads (bar.sync id, n): generation counter per id
+struct NamedBar { int waiting = 0; long long gen = 0; };
+static NamedBar g_named[16];
+static inline void named_bar_sync(int id, int nthreads) {
+    long long my;
+    {
+        std::lock_guard<std::mutex> l(g_mu);
+        NamedBar& b = g_named[id];
+        my = b.gen;
+        if (++b.waiting == nthreads) { b.waiting = 0; ++b.gen; return; }
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        {
+            std::lock_guard<std::mutex> l(g_mu);
+            if (g_named[id].gen != my) return;
+        }
+        if (g_deadlock.load()) return;
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) { g_deadlock.store(true); return; }
+        std::this_thread::yield();
+    }
+}
+
+#include "../../fewshot_detection_b200/csrc/conv_tc_kernels.cuh"
+static_assert(EMUL_BM == TC_BM, "tile height of the models");
 
 }  // namespace fsdet
 
 using namespace fsdet;
 
-template <int BN, int PST>
-static int run(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo, const TcArgs& a, int B,
+template <int BN, int BK, int NH, int TERMS, bool PERSIST, int MINB>
+static int run(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo, TcArgs a, int B,
                int ctas) {
-    using Cfg = TcPersistCfg<BN, 32, PST, 1>;
+    using Cfg = TcCfg<BN, BK, NH, TERMS, PERSIST, MINB>;
     CUtensorMap mAh, mAl, mBh, mBl, mZ;
     const long long K = (long long)a.ks * a.ks * a.cpitch;
     auto act = [&](CUtensorMap* m, const uint16_t* base) {
         MapModel mm{}; mm.kind = 0; mm.base = base; mm.B = B; mm.H = a.H; mm.W = a.W; mm.C = a.Cin; mm.cpitch = a.cpitch;
-        mm.ks = a.ks; mm.pad = a.pad; mm.bk = 32;
+        mm.ks = a.ks; mm.pad = a.pad; mm.bk = BK;
         memset(m, 0, sizeof(*m)); memcpy(m, &mm, sizeof(mm));
     };
     auto wgt = [&](CUtensorMap* m, const uint16_t* base) {
-        MapModel mm{}; mm.kind = 1; mm.base = base; mm.rows = a.Cout; mm.K = K; mm.bk = 32; mm.box_rows = BN;
+        MapModel mm{}; mm.kind = 1; mm.base = base; mm.rows = a.Cout; mm.K = K; mm.bk = BK; mm.box_rows = BN;
         memset(m, 0, sizeof(*m)); memcpy(m, &mm, sizeof(mm));
     };
     static_assert(sizeof(MapModel) <= sizeof(CUtensorMap), "model must fit in the tensor map");
-    act(&mAh, x_hi); act(&mAl, x_lo); wgt(&mBh, w_hi); wgt(&mBl, w_lo);
+    // planes a term does not use must never be touched: their maps get a null base (a load would crash)
+    act(&mAh, x_hi); act(&mAl, (TERMS & 1) ? x_lo : nullptr); wgt(&mBh, w_hi); wgt(&mBl, (TERMS & 2) ? w_lo : nullptr);
     { MapModel mm{}; mm.kind = 2; mm.z = a.z; mm.rows = a.Cout; mm.M = a.M; mm.ldz = a.ldz; memset(&mZ, 0, sizeof(mZ)); memcpy(&mZ, &mm, sizeof(mm)); }
-    const int tiles_n = ceil_div(a.Cout, BN);
-    const long long total = (long long)tiles_n * ceil_div(a.M, TC_BM);
+    a.tiles_n = ceil_div(a.Cout, BN);
+    a.tiles_total = a.tiles_n * ceil_div(a.M, TC_BM);
+    const int grid = PERSIST ? ctas : a.tiles_total;
     g_deadlock.store(false);
-    emul::launch(dim3(ctas), dim3(192), Cfg::SMEM_BYTES, [&]() {
-        if (threadIdx.x == 0) { memset(g_tmem, 0, sizeof(g_tmem)); std::lock_guard<std::mutex> l(g_mu); g_bars.clear(); }
+    emul::launch(dim3(grid), dim3(192), Cfg::SMEM_BYTES, [&]() {
+        if (threadIdx.x == 0) {
+            memset(g_tmem, 0, sizeof(g_tmem));
+            std::lock_guard<std::mutex> l(g_mu);
+            g_bars.clear();
+            for (auto& nb : g_named) nb = NamedBar{};
+        }
         pthread_barrier_wait(&emul::g_block.bar);
-        conv_tc_persist_kernel<BN, 32, PST, 1>(mAh, mAl, mBh, mBl, mZ, a, tiles_n, (int)total);
+        conv_tc_kernel<BN, BK, NH, TERMS, PERSIST, MINB>(mAh, mAl, mBh, mBl, mZ, a);
     });
     return g_deadlock.load() ? -100 : 0;
 }
 
-// returns 0, or -100 when a barrier wait timed out (deadlock: wrong phase / arrival count)
-extern "C" int emul_conv_tc_persist(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
-                                    const float* amax_x, const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin,
-                                    int cpitch, int Cout, int ks, int accumulate, int bn, int stages, int ctas) {
+template <int BN, int BK, int NH, bool PERSIST, int MINB>
+static int run_terms(int terms, const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
+                     const TcArgs& a, int B, int ctas) {
+    switch (terms) {
+        case 0: return run<BN, BK, 1, 0, PERSIST, MINB>(x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+        case 1: return run<BN, BK, 1, 1, PERSIST, MINB>(x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+        case 2: return run<BN, BK, 1, 2, PERSIST, MINB>(x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+        default: return run<BN, BK, NH, 3, PERSIST, MINB>(x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+    }
+}
+
+// returns 0, or -100 when a barrier wait timed out (deadlock: wrong phase / arrival count).
+//   bk = 32: short-K flavour (persist = 0: one tile per CTA, `ctas` ignored; persist = 1: `ctas` CTAs walk the tiles,
+//            ctas must be a multiple of ceil(Cout / bn));  bk = 64: long-K flavour (3 rotating hi accumulators for terms = 3)
+//   stats: optional [rows][4*Cout] partial rows (rows = persist ? ctas / tiles_n : number of 128-pixel tiles)
+extern "C" int emul_conv_tc(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
+                            const float* amax_x, const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin,
+                            int cpitch, int Cout, int ks, int accumulate, int bn, int bk, int terms, int persist, int ctas,
+                            float* stats) {
     TcArgs a;
-    a.z = z; a.amax_a = amax_x; a.amax_b = amax_w; a.ldz = ldz; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ks = ks;
-    a.pad = (ks - 1) / 2; a.cpitch = cpitch; a.M = (long long)B * H * W; a.accumulate = accumulate;
-    if (bn == 64 && stages == 6) return run<64, 6>(x_hi, x_lo, w_hi, w_lo, a, B, ctas);
-    if (bn == 64 && stages == 2) return run<64, 2>(x_hi, x_lo, w_hi, w_lo, a, B, ctas);
-    if (bn == 128 && stages == 4) return run<128, 4>(x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+    a.z = z; a.amax_a = amax_x; a.amax_b = amax_w; a.stats = stats; a.ldz = ldz; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
+    a.ks = ks; a.pad = (ks - 1) / 2; a.cpitch = cpitch; a.M = (long long)B * H * W; a.accumulate = accumulate;
+    a.tiles_n = a.tiles_total = 0;
+    if (bk == 32 && persist) {
+        if (bn == 64) return run_terms<64, 32, 1, true, 1>(terms, x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+        if (bn == 128) return run_terms<128, 32, 1, true, 1>(terms, x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+    } else if (bk == 32) {
+        if (bn == 64) return run_terms<64, 32, 1, false, 2>(terms, x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+        if (bn == 128) return run_terms<128, 32, 1, false, 2>(terms, x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+    } else if (bk == 64 && !persist) {
+        if (bn == 64) return run_terms<64, 64, 3, false, 1>(terms, x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+        if (bn == 128) return run_terms<128, 64, 3, false, 1>(terms, x_hi, x_lo, w_hi, w_lo, a, B, ctas);
+    }
     return -1;
 }
 

@@ -31,7 +31,7 @@ for (B, H, W, Cin, Cout, k) in [(2, 13, 13, 64, 128, 3), (2, 13, 13, 1280, 1024,
         xn = nhwc(x); wn = w.permute(0, 2, 3, 1).contiguous()
         xh, xl, xa = split(xn); wh, wl, wa = split(wn.view(Cout, -1))
         z = torch.zeros(B * H * W, Cout, device='cuda')
-        L.call('fsdet_conv_tc_fwd', xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), xa.data_ptr(), wa.data_ptr(), z.data_ptr(), Cout, B, H, W, Cin, Cin, Cout, k, 0, st())
+        L.call('fsdet_conv_tc_fwd', xh.data_ptr(), xl.data_ptr(), wh.data_ptr(), wl.data_ptr(), xa.data_ptr(), wa.data_ptr(), z.data_ptr(), Cout, B, H, W, Cin, Cin, Cout, k, 0, 3, None, st())
         got = z.view(B, H, W, Cout).permute(0, 3, 1, 2)
         z2 = torch.zeros(B * H * W, Cout, device='cuda')
         L.call('fsdet_conv_fwd', xn.data_ptr(), Cin, wn.data_ptr(), None, z2.data_ptr(), Cout, None, B, H, W, Cin, Cout, k, 0, st())
