@@ -60,8 +60,8 @@ SIGNATURES = {
     'fsdet_head_param_grads': ('pppppiiip', 'i'),
     'fsdet_head_bias_grad': ('pippziip', 'i'),
     'fsdet_head_bias_grad_workspace_floats': ('zii', 'z'),
-    'fsdet_region_decode': ('ppiiiiippp', 'i'),
-    'fsdet_build_targets': ('pppiiiiifffqppppppppppp', 'i'),
+    'fsdet_region_decode': ('ppipiiiippp', 'i'),
+    'fsdet_build_targets': ('pppiiiiifffqppppppppppppp', 'i'),
     'fsdet_region_loss_grad': ('ppppp iiiiiiii ppppppppp ff ii p p'.replace(' ', ''), 'i'),
     'fsdet_sgd_step': ('ppppppiiffffipp', 'i'),
     'fsdet_fill': ('pfzp', 'i'),

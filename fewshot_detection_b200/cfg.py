@@ -25,6 +25,17 @@ class _Options(dict):
         self[k] = v
 
 
+COCO_NAMES = [
+    'person', 'bicycle', 'car', 'motorbike', 'aeroplane', 'bus', 'train', 'truck', 'boat', 'traffic light', 'fire hydrant',
+    'stop sign', 'parking meter', 'bench', 'bird', 'cat', 'dog', 'horse', 'sheep', 'cow', 'elephant', 'bear', 'zebra',
+    'giraffe', 'backpack', 'umbrella', 'handbag', 'tie', 'suitcase', 'frisbee', 'skis', 'snowboard', 'sports ball', 'kite',
+    'baseball bat', 'baseball glove', 'skateboard', 'surfboard', 'tennis racket', 'bottle', 'wine glass', 'cup', 'fork',
+    'knife', 'spoon', 'bowl', 'banana', 'apple', 'sandwich', 'orange', 'broccoli', 'carrot', 'hot dog', 'pizza', 'donut',
+    'cake', 'chair', 'sofa', 'pottedplant', 'bed', 'diningtable', 'toilet', 'tvmonitor', 'laptop', 'mouse', 'remote',
+    'keyboard', 'cell phone', 'microwave', 'oven', 'toaster', 'sink', 'refrigerator', 'book', 'clock', 'vase', 'scissors',
+    'teddy bear', 'hair drier', 'toothbrush']
+
+
 cfg = _Options()
 cfg.voc_classes = ["aeroplane", "bicycle", "bird", "boat", "bottle", "bus", "car", "cat", "chair", "cow",
                    "diningtable", "dog", "horse", "motorbike", "person", "pottedplant", "sheep", "sofa", "train",
@@ -39,6 +50,10 @@ cfg.multiscale = True
 cfg.metain_type = 2       # 2 = support image + mask channel (cfg.py:37-38)
 # defaults of the few-shot bookkeeping that image.fill_truth_detection(_meta) reads (cfg.py:103-145): all 20 VOC
 # classes are base classes until a .data file says otherwise
+cfg.coco_classes = COCO_NAMES      # data/coco.names of the reference (cfg.py:25-27), VOC spellings for the shared classes
+cfg.vocids_in_coco = [COCO_NAMES.index(c) for c in cfg.voc_classes]
+cfg.cocoonly_ids = [i for i in range(len(COCO_NAMES)) if i not in cfg.vocids_in_coco]
+cfg.randmeta = False
 cfg.classes = cfg.voc_classes
 cfg.base_classes = list(cfg.voc_classes)
 cfg.base_ids = list(range(len(cfg.voc_classes)))
@@ -72,27 +87,117 @@ def _configure_meta(metaopt):
     metaopt['channels'] = chans[cfg.metain_type]
 
 
+def read_names(path):
+    """One class name per line (data/voc.names, data/coco.names; cfg.py:11-17)."""
+    with open(path) as f:
+        return [l.strip() for l in f.readlines()]
+
+
+def novel_classes_of(spec, novelid):
+    """cfg.py:55-63: `novel` is either a comma-separated class list or a .txt file whose line `novelid` is one;
+    novelid 'None' selects no novel classes."""
+    if not spec.endswith('txt'):
+        return spec.split(',')
+    if novelid == 'None':
+        return []
+    with open(spec) as f:
+        return f.readlines()[int(novelid)].strip().split(',')
+
+
+def fewshot_image_ids(metafile, base_classes):
+    """cfg.py:41-53: image ids listed by the per-class files of a few-shot dict (`<class> <listfile>` lines), base
+    classes only, sorted and de-duplicated."""
+    with open(metafile) as f:
+        rows = [l.rstrip().split() for l in f.readlines()]
+    lines = []
+    for row in rows:
+        if row and row[0] in base_classes:
+            with open(row[-1]) as g:
+                lines.extend(g.readlines())
+    return [l.split('/')[-1].split('.')[0] for l in sorted(set(lines))]
+
+
+def _save_interval_for(max_epoch, repeat, data):
+    """cfg.py:88-98: fine-tuning saves more often the fewer (epoch / repeat) passes it makes."""
+    passes = max_epoch / repeat
+    interval = 10
+    for limit, every in ((20, 1), (50, 2), (100, 5)):
+        if passes <= limit:
+            interval = every
+            break
+    return 2 if data == 'coco' else interval
+
+
+def _backup_dir(dataopt, novelid):
+    """cfg.py:133-145: the backup directory name encodes the run's switches."""
+    name = dataopt['backup']
+    if not cfg.multiscale:
+        name += 'fix'
+    if cfg.metain_type != 2:
+        head, _, tail = name.partition('_')
+        name = head + 'in{}'.format(cfg.metain_type) + (('_' + tail) if tail else '')
+    name += '_novel{}'.format(novelid)
+    if cfg.metayolo:
+        name += '_neg{}'.format(cfg.neg_ratio)
+    if cfg.randmeta:
+        name += '_rand'
+    return name
+
+
 def _configure_data(dataopt):
-    """The subset of cfg.py:70-147 that feeds the hot path (class lists, neg
-    ratio, metayolo / metain_type switches).  Dataset bookkeeping (few-shot id
-    lists, backup dir naming) belongs to the out-of-scope input pipeline."""
-    cfg.data = dataopt.get('data', 'voc')
-    if 'scale' in dataopt:
-        cfg.multiscale = int(dataopt['scale'])
-    if 'metain_type' in dataopt:
-        cfg.metain_type = int(dataopt['metain_type'])
+    """The `.data` file -> process-global options (cfg.py:70-147): class lists and the base / novel split that the
+    few-shot protocol rests on (base training must NOT see the novel classes), negative-row ratio, fine-tuning
+    schedule, backup directory name.  Keys the file does not have keep their defaults."""
+    data = dataopt.get('data', 'voc')
+    cfg.data = data
+    if data == 'voc':
+        cfg.classes = cfg.voc_classes
+    elif data == 'coco':
+        cfg.classes = cfg.coco_classes
+        cfg.save_interval = 2
+    else:
+        raise NotImplementedError('Data type {} not found'.format(data))
+    for key, conv, dst in (('scale', int, 'multiscale'), ('metain_type', int, 'metain_type')):
+        if key in dataopt:
+            cfg[dst] = conv(dataopt[key])
     if 'tuning' in dataopt:
         cfg.tuning = bool(int(dataopt['tuning']))
+        cfg.max_epoch = int(dataopt.get('max_epoch', 500))
+        cfg.repeat = int(dataopt.get('repeat', 100))
+        cfg.save_interval = _save_interval_for(cfg.max_epoch, cfg.repeat, data)
+        if 'meta' in dataopt:
+            cfg.shot = int(dataopt['meta'].split('.')[0].split('_')[-1].replace('shot', ''))
+    novelid = dataopt.get('novelid', 'None')
+    cfg.novelid = novelid
+    cfg.novel_classes = novel_classes_of(dataopt['novel'], novelid) if 'novel' in dataopt else []
+    unknown = [c for c in cfg.novel_classes if c not in cfg.classes]
+    if unknown:
+        raise ValueError('novel classes %r are not classes of the %s data set' % (unknown, data))
+    if cfg.tuning:
+        cfg.base_classes = list(cfg.classes)          # fine-tuning sees every class (cfg.py:105-113)
+    else:
+        cfg.base_classes = [c for c in cfg.classes if c not in cfg.novel_classes]
+    cfg.base_ids = [cfg.classes.index(c) for c in cfg.base_classes]
+    cfg.novel_ids = [cfg.classes.index(c) for c in cfg.novel_classes]
+    cfg._real_base_ids = [i for i in range(len(cfg.classes)) if i not in cfg.novel_ids]
+    if 'gpus' in dataopt:
+        cfg.num_gpus = len(dataopt['gpus'].split(','))
     neg = dataopt['neg'] if 'neg' in dataopt else cfg.neg_ratio
     if isinstance(neg, str) and neg.isdigit():
         neg = float(neg)
         if neg.is_integer():
             neg = int(neg)
     cfg.neg_ratio = neg
+    cfg.randmeta = bool(int(dataopt['rand'])) if 'rand' in dataopt else False
     if 'metayolo' in dataopt:
         cfg.metayolo = bool(int(dataopt['metayolo']))
-    if 'gpus' in dataopt:
-        cfg.num_gpus = len(dataopt['gpus'].split(','))
+    if 'backup' in dataopt:
+        cfg.backup = _backup_dir(dataopt, novelid)
+    cfg.yolo_joint = int(dataopt['joint']) if 'joint' in dataopt else False
+    if cfg.yolo_joint:
+        cfg.metaids = fewshot_image_ids(dataopt['meta'], cfg.base_classes)
+        cfg.backup = cfg.get('backup', '') + '_joint{}'.format(
+            int(dataopt['meta'].split('.')[0].split('_')[-1].replace('shot', '')))
 
 
 cfg.config_data = _configure_data

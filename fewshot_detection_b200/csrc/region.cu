@@ -16,7 +16,10 @@ namespace fsdet {
 __device__ __forceinline__ float sigmoidf_acc(float v) { return 1.f / (1.f + expf(-v)); }
 
 // ------------------------------------------------------------------- decode
-__global__ void region_decode_kernel(const float* __restrict__ out, const int32_t* __restrict__ inds, int nB, int A, int nC,
+// `nB` rows are launched; when `nB_dev` is given (CUDA-graph replay: the number of rows kept by neg_filter changes from
+// step to step but the launch is frozen at its capacity) only slots < *nB_dev are live.
+__global__ void region_decode_kernel(const float* __restrict__ out, const int32_t* __restrict__ inds, int nB,
+                                     const int32_t* __restrict__ nB_dev, int A, int nC,
                                      int H, int W, const float* __restrict__ anchors, float* __restrict__ pb) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int HW = H * W;
@@ -26,6 +29,7 @@ __global__ void region_decode_kernel(const float* __restrict__ out, const int32_
     long long t = i / HW;
     int a = (int)(t % A);
     int slot = (int)(t / A);
+    if (nB_dev && slot >= *nB_dev) return;
     int r = inds ? inds[slot] : slot;
     const float* o = out + ((long long)r * A * (5 + nC) + (long long)a * (5 + nC)) * HW + cell;
     float x = sigmoidf_acc(o[0]);
@@ -84,6 +88,8 @@ struct BTArgs {
     const float* pb;
     const double* target;
     const double* anchors;
+    const int32_t* inds;     // optional: `target` is the FULL label matrix and slot b reads row inds[b]
+    const int32_t* nB_dev;   // optional: live slots (CUDA-graph replay at fixed capacity)
     int nB, A, H, W, max_boxes;
     float noobj, obj, thresh;
     long long seen;
@@ -96,9 +102,10 @@ __global__ void __launch_bounds__(256) build_targets_kernel(const BTArgs a) {
     __shared__ float gt[kMaxGT][4];
     __shared__ int s_nt;
     const int b = blockIdx.x;
+    if (a.nB_dev && b >= *a.nB_dev) return;          // block-uniform
     const int HW = a.H * a.W;
     const int nAnch = a.A * HW;
-    const double* trow = a.target + (long long)b * 250;
+    const double* trow = a.target + (long long)(a.inds ? a.inds[b] : b) * 250;
 
     if (threadIdx.x == 0) {
         int nt = 0;
@@ -190,6 +197,7 @@ struct LossArgs {
     const float* out;
     float* grad;
     const int32_t* inds;
+    const int32_t* nB_dev;   // optional: live slots (CUDA-graph replay at fixed capacity)
     const int32_t* img_start;
     int rows_total, nB, bs, cs, A, nC, H, W;
     const float *coord_mask, *conf_mask, *cls_mask, *tx, *ty, *tw, *th, *tconf, *tcls;
@@ -228,7 +236,7 @@ __global__ void __launch_bounds__(256) region_box_loss_kernel(const LossArgs a) 
     long long n = (long long)a.nB * a.A * HW;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};  // x y w h conf cls proposals
-    if (i < n) {
+    if (i < n && (!a.nB_dev || (int)(i / ((long long)a.A * HW)) < *a.nB_dev)) {
         int cell = (int)(i % HW);
         long long t = i / HW;
         int an = (int)(t % a.A);
@@ -325,12 +333,12 @@ __global__ void loss_total_kernel(double* losses) {
 #ifndef FSDET_HOST_EMULATION  // tools/host_emul compiles the kernels above with g++ for CPU logic tests
 using namespace fsdet;
 
-extern "C" int fsdet_region_decode(const float* output, const int32_t* inds, int nB, int A, int nC, int H, int W,
-                                   const float* anchors_f32, float* pred_boxes, void* stream) {
+extern "C" int fsdet_region_decode(const float* output, const int32_t* inds, int nB, const int32_t* nB_dev, int A, int nC,
+                                   int H, int W, const float* anchors_f32, float* pred_boxes, void* stream) {
     FSDET_CHECK_ARG(output && anchors_f32 && pred_boxes && aligned16(pred_boxes), "region_decode: bad args");
     long long n = (long long)nB * A * H * W;
     if (n == 0) return 0;
-    region_decode_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(output, inds, nB, A, nC, H, W, anchors_f32,
+    region_decode_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(output, inds, nB, nB_dev, A, nC, H, W, anchors_f32,
                                                                              pred_boxes);
     return launch_status("region_decode");
 }
@@ -339,7 +347,7 @@ extern "C" int fsdet_build_targets(const float* pred_boxes, const double* target
                                    int H, int W, int max_boxes, float noobject_scale, float object_scale, float sil_thresh,
                                    long long seen, float* coord_mask, float* conf_mask, float* cls_mask, float* tx,
                                    float* ty, float* tw, float* th, float* tconf, float* tcls, int32_t* counters,
-                                   void* stream) {
+                                   const int32_t* inds, const int32_t* nB_dev, void* stream) {
     FSDET_CHECK_ARG(pred_boxes && target && anchors_f64 && counters && coord_mask && conf_mask && cls_mask && tx && ty &&
                         tw && th && tconf && tcls,
                     "build_targets: null pointer");
@@ -350,7 +358,8 @@ extern "C" int fsdet_build_targets(const float* pred_boxes, const double* target
     if (e != cudaSuccess) { set_error("build_targets: memset: %s", cudaGetErrorString(e)); return (int)e; }
     if (nB == 0) return 0;
     BTArgs a;
-    a.pb = pred_boxes; a.target = target; a.anchors = anchors_f64; a.nB = nB; a.A = A; a.H = H; a.W = W;
+    a.pb = pred_boxes; a.target = target; a.anchors = anchors_f64; a.inds = inds; a.nB_dev = nB_dev; a.nB = nB; a.A = A;
+    a.H = H; a.W = W;
     a.max_boxes = max_boxes; a.noobj = noobject_scale; a.obj = object_scale; a.thresh = sil_thresh; a.seen = seen;
     a.coord_mask = coord_mask; a.conf_mask = conf_mask; a.cls_mask = cls_mask; a.tx = tx; a.ty = ty; a.tw = tw; a.th = th;
     a.tconf = tconf; a.tcls = tcls; a.counters = counters;
@@ -358,13 +367,12 @@ extern "C" int fsdet_build_targets(const float* pred_boxes, const double* target
     return launch_status("build_targets");
 }
 
-extern "C" int fsdet_region_loss_grad(const float* output, float* grad_output, const int32_t* inds, const int32_t* row_of,
+extern "C" int fsdet_region_loss_grad(const float* output, float* grad_output, const int32_t* inds, const int32_t* nB_dev,
                                       const int32_t* img_start, int rows_total, int nB, int bs, int cs, int A, int nC,
                                       int H, int W, const float* coord_mask, const float* conf_mask,
                                       const float* cls_mask, const float* tx, const float* ty, const float* tw,
                                       const float* th, const float* tconf, const float* tcls, float coord_scale,
                                       float class_scale, int mode, int metayolo, double* losses, void* stream) {
-    (void)row_of;
     FSDET_CHECK_ARG(output && grad_output && losses, "region_loss_grad: null pointer");
     FSDET_CHECK_ARG(mode == 1 || (nC == 1 && img_start && bs * cs == rows_total),
                     "region_loss_grad: RegionLossV2 needs classes=1 and rows = bs*cs");
@@ -374,7 +382,7 @@ extern "C" int fsdet_region_loss_grad(const float* output, float* grad_output, c
     if (e == cudaSuccess) e = cudaMemsetAsync(losses, 0, 8 * sizeof(double), s);
     if (e != cudaSuccess) { set_error("region_loss_grad: memset: %s", cudaGetErrorString(e)); return (int)e; }
     LossArgs a;
-    a.out = output; a.grad = grad_output; a.inds = inds; a.img_start = img_start; a.rows_total = rows_total; a.nB = nB;
+    a.out = output; a.grad = grad_output; a.inds = inds; a.nB_dev = nB_dev; a.img_start = img_start; a.rows_total = rows_total; a.nB = nB;
     a.bs = bs; a.cs = cs; a.A = A; a.nC = nC; a.H = H; a.W = W; a.coord_mask = coord_mask; a.conf_mask = conf_mask;
     a.cls_mask = cls_mask; a.tx = tx; a.ty = ty; a.tw = tw; a.th = th; a.tconf = tconf; a.tcls = tcls;
     a.coord_scale = coord_scale; a.class_scale = class_scale; a.mode = mode; a.metayolo = metayolo; a.losses = losses;

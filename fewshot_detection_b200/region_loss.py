@@ -29,23 +29,29 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
-def neg_filter(pred_boxes, target, withids=False):
-    """region_loss.py:15-34. `target` is the CPU float64 [rows, 250] label
-    matrix. Returns the kept row indices (python list, ascending); the rows
-    themselves are gathered on the device by the caller."""
-    assert pred_boxes.size(0) == target.size(0)
+def kept_rows(target):
+    """The row selection of region_loss.py:15-34 on the [rows, 250] label matrix: every row with a label is kept,
+    every empty row with probability neg_ratio * #labelled / #empty, one Python `random()` draw per empty row in row
+    order (the reference's RNG consumption).  Returns the kept row indices (ascending list)."""
+    n = target.size(0)
     if cfg.neg_ratio == 'full':
-        inds = list(range(pred_boxes.size(0)))
-    elif isinstance(cfg.neg_ratio, Number):
+        return list(range(n))
+    if isinstance(cfg.neg_ratio, Number):
         flags = (torch.sum(target, 1) != 0).cpu().tolist()
         ratio = cfg.neg_ratio * sum(flags) * 1. / (len(flags) - sum(flags))
         if ratio >= 1:
-            inds = list(range(pred_boxes.size(0)))
-        else:
-            flags = [0 if f == 0 and random() > ratio else 1 for f in flags]
-            inds = [i for i, f in enumerate(flags) if f]
-    else:
-        raise NotImplementedError('neg_ratio not recognized')
+            return list(range(n))
+        flags = [0 if f == 0 and random() > ratio else 1 for f in flags]
+        return [i for i, f in enumerate(flags) if f]
+    raise NotImplementedError('neg_ratio not recognized')
+
+
+def neg_filter(pred_boxes, target, withids=False):
+    """region_loss.py:15-34 with the reference's signature. `target` is the float64 [rows, 250] label
+    matrix. Returns the kept row indices (python list, ascending); the rows
+    themselves are gathered on the device by the caller."""
+    assert pred_boxes.size(0) == target.size(0)
+    inds = kept_rows(target)
     if withids:
         return pred_boxes, target, inds
     return pred_boxes, target
@@ -85,7 +91,7 @@ def build_targets(pred_boxes, target, anchors, num_anchors, num_classes, nH, nW,
     pb = pred_boxes.contiguous()
     call('fsdet_build_targets', ptr(pb), ptr(tgt), ptr(anc), nB, nA, nH, nW, int(cfg.max_boxes),
          float(noobject_scale), float(object_scale), float(sil_thresh), int(seen),
-         *[ptr(out[i]) for i in range(9)], ptr(counters), _st())
+         *[ptr(out[i]) for i in range(9)], ptr(counters), None, None, _st())
     if not sync:
         return (counters,) + tuple(out[i] for i in range(9))
     c = counters.tolist()
@@ -121,6 +127,76 @@ class _RegionBase(nn.Module):
         self.seen = 0
         self.verbose = True   # print the reference's per-step log line (forces a host sync)
         self.last = None      # dict with the logged scalars of the last call (device tensors when not verbose)
+        self.static = None    # fixed-capacity device buffers of a CUDA-graph-captured step (graph.GraphedTrainStep)
+        self._pending = None  # (pinned counters, event) of the last non-verbose call, checked one call late
+
+    # -- degenerate ground truth (the reference raises `math domain error` from math.log, region_loss.py:114) -----
+    def _note_counters(self, counters):
+        """Non-verbose calls do not synchronise: the kernel's degenerate-box counter is copied to pinned memory behind
+        the step and examined at the NEXT call (or by poll()), so a zero-size / out-of-grid label is still reported,
+        one step late, instead of silently training on garbage."""
+        if torch.cuda.is_current_stream_capturing():
+            return
+        if self._pending is None:
+            self._pending = [torch.zeros(4, dtype=torch.int32).pin_memory(), torch.cuda.Event(), False]
+        host, ev, armed = self._pending
+        if armed:
+            ev.synchronize()
+            self._raise_if_degenerate(host)
+        host.copy_(counters, non_blocking=True)
+        ev.record()
+        self._pending[2] = True
+
+    @staticmethod
+    def _raise_if_degenerate(host):
+        if int(host[2]):
+            raise ValueError('math domain error: %d ground-truth boxes with zero width/height or outside the grid '
+                             '(reported one step late: verbose=False)' % int(host[2]))
+
+    def poll(self):
+        """Check the degenerate-label counter of the last non-verbose call (blocks until that step has finished)."""
+        if self._pending is not None and self._pending[2]:
+            self._pending[1].synchronize()
+            self._pending[2] = False
+            self._raise_if_degenerate(self._pending[0])
+
+    # -- CUDA-graph form -------------------------------------------------------------------------------------------
+    def make_static(self, rows_total, bs, device):
+        """Allocate the fixed-capacity buffers a captured step reads: [0] = number of live rows, [1 : bs+2] = per-image
+        prefix of the kept rows (V2), [bs+2 :] = kept row indices.  The kernels are launched for `rows_total` slots and
+        skip the dead ones, so ONE graph serves every outcome of neg_filter."""
+        n = 1 + (bs + 1) + rows_total
+        return {'rows_total': rows_total, 'bs': bs, 'dev': torch.zeros(n, dtype=torch.int32, device=device),
+                'ring': [[torch.zeros(n, dtype=torch.int32).pin_memory(), torch.cuda.Event(), False] for _ in range(3)],
+                'turn': 0}
+
+    @staticmethod
+    def stage_filter(st, target):
+        """Host half of a captured step: neg_filter on the CPU label tensor (the reference's `random()` draws) and one
+        asynchronous upload of (live rows, img_start, inds) into the static buffers `st` (from make_static); call
+        before every replay.  While `self.static = st` is set, forward() takes the fixed-capacity form."""
+        t2 = target.view(-1, target.size(-1))
+        if t2.is_cuda:
+            raise TypeError('stage_filter needs the CPU label tensor (the reference keeps `target` on the host)')
+        if t2.size(0) != st['rows_total']:
+            raise ValueError('label rows %d != captured capacity %d' % (t2.size(0), st['rows_total']))
+        inds = kept_rows(t2)
+        host, ev, armed = st['ring'][st['turn']]
+        if armed:
+            ev.synchronize()
+        host[0] = len(inds)
+        bs = st['bs']
+        if bs:
+            cs = st['rows_total'] // bs
+            counts, _ = np.histogram(inds, bins=bs, range=(0, bs * cs))
+            host[1:bs + 2] = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32))
+        if inds:
+            host[bs + 2:bs + 2 + len(inds)] = torch.tensor(inds, dtype=torch.int32)
+        st['dev'].copy_(host, non_blocking=True)
+        ev.record()
+        st['ring'][st['turn']][2] = True
+        st['turn'] = (st['turn'] + 1) % len(st['ring'])
+        return inds
 
     def _run(self, output, target2d, inds, mode, bs, cs, img_start):
         if not output.is_cuda:
@@ -132,39 +208,53 @@ class _RegionBase(nn.Module):
         nA, nC = int(self.num_anchors), int(self.num_classes)
         nH, nW = out_c.size(2), out_c.size(3)
         assert out_c.size(1) == nA * (5 + nC)
-        nB = len(inds)
-        full = nB == rows_total
-        inds_t = None
-        if not full:
-            inds_t = torch.tensor(inds, dtype=torch.int32).to(dev, non_blocking=True)
-        if full:
-            tgt_rows = target2d
-        elif target2d.is_cuda:
-            tgt_rows = target2d[inds_t.long()]
+        static = self.static if inds is None else None
+        nb_dev = bt_inds = None
+        if static is not None:
+            # captured step: launches at full capacity, live-row count / indices / image prefix read from device memory
+            if static['rows_total'] != rows_total or (mode == 0 and static['bs'] != bs):
+                raise ValueError('static loss buffers were made for another shape')
+            nB = rows_total
+            sb = static['dev']
+            nb_dev = sb[0:1]
+            inds_t = bt_inds = sb[static['bs'] + 2:]
+            tgt = _to_device_f64(target2d, dev)          # the FULL label matrix, rows gathered by the kernel
         else:
-            tgt_rows = target2d[torch.as_tensor(inds, dtype=torch.long)]
-        tgt = _to_device_f64(tgt_rows, dev)
+            nB = len(inds)
+            full = nB == rows_total
+            inds_t = None
+            if not full:
+                inds_t = torch.tensor(inds, dtype=torch.int32).to(dev, non_blocking=True)
+            if full:
+                tgt_rows = target2d
+            elif target2d.is_cuda:
+                tgt_rows = target2d[inds_t.long()]
+            else:
+                tgt_rows = target2d[torch.as_tensor(inds, dtype=torch.long)]
+            tgt = _to_device_f64(tgt_rows, dev)
         key = (str(dev), tuple(float(a) for a in self.anchors))
         if getattr(self, '_anchor_cache', (None,))[0] != key:   # small constants are uploaded once (CUDA-graph friendly)
             self._anchor_cache = (key, torch.tensor(key[1], dtype=torch.float32).to(dev),
                                   torch.tensor(key[1], dtype=torch.float64).to(dev))
         anc32, anc64 = self._anchor_cache[1], self._anchor_cache[2]
         pred = torch.empty(max(nB, 1) * nA * nH * nW, 4, device=dev)
-        call('fsdet_region_decode', ptr(out_c), ptr(inds_t), nB, nA, nC, nH, nW, ptr(anc32), ptr(pred), st)
+        call('fsdet_region_decode', ptr(out_c), ptr(inds_t), nB, ptr(nb_dev), nA, nC, nH, nW, ptr(anc32), ptr(pred), st)
         tg = torch.empty(9, max(nB, 1), nA, nH, nW, device=dev)
         counters = torch.empty(4, dtype=torch.int32, device=dev)
         call('fsdet_build_targets', ptr(pred), ptr(tgt), ptr(anc64), nB, nA, nH, nW, int(cfg.max_boxes),
              float(self.noobject_scale), float(self.object_scale), float(self.thresh), int(self.seen),
-             *[ptr(tg[i]) for i in range(9)], ptr(counters), st)
+             *[ptr(tg[i]) for i in range(9)], ptr(counters), ptr(bt_inds), ptr(nb_dev), st)
         grad = torch.empty_like(out_c)
         losses = torch.empty(8, dtype=torch.float64, device=dev)
         imgs_t = None
-        if mode == 0:
+        if mode == 0 and static is not None:
+            imgs_t = static['dev'][1:static['bs'] + 2]
+        elif mode == 0:
             ikey = (str(dev), tuple(img_start))
             if getattr(self, '_img_cache', (None,))[0] != ikey:
                 self._img_cache = (ikey, torch.tensor(img_start, dtype=torch.int32).to(dev))
             imgs_t = self._img_cache[1]
-        call('fsdet_region_loss_grad', ptr(out_c), ptr(grad), ptr(inds_t), None, ptr(imgs_t), rows_total, nB, bs, cs, nA,
+        call('fsdet_region_loss_grad', ptr(out_c), ptr(grad), ptr(inds_t), ptr(nb_dev), ptr(imgs_t), rows_total, nB, bs, cs, nA,
              nC, nH, nW, *[ptr(tg[i]) for i in range(9)], float(self.coord_scale), float(self.class_scale), mode,
              1 if cfg.metayolo else 0, ptr(losses), st)
         loss = losses[6].to(torch.float32)
@@ -179,6 +269,8 @@ class _RegionBase(nn.Module):
                 self.seen, c[0], c[1], int(host[7]), host[0], host[1], host[2], host[3], host[4], host[5], host[6]))
             self.last.update(nGT=c[0], nCorrect=c[1], nProposals=int(host[7]), loss_x=host[0], loss_y=host[1],
                              loss_w=host[2], loss_h=host[3], loss_conf=host[4], loss_cls=host[5], loss=host[6])
+        else:
+            self._note_counters(counters)
         if output.requires_grad and torch.is_grad_enabled():
             return _LossFn.apply(output, loss, grad)
         return loss
@@ -190,6 +282,8 @@ class RegionLoss(_RegionBase):
     def forward(self, output, target):
         if target.dim() == 3:
             target = target.view(-1, target.size(-1))
+        if self.static is not None:       # captured step: the row selection was staged by stage_filter()
+            return self._run(output, target, None, 1, 0, 0, None)
         _, _, inds = neg_filter(output, target, withids=True)
         return self._run(output, target, inds, 1, 0, 0, None)
 
@@ -206,6 +300,8 @@ class RegionLossV2(_RegionBase):
         bs = target.size(0)
         cs = target.size(1)
         target2d = target.view(-1, target.size(-1))
+        if self.static is not None:       # captured step: the row selection was staged by stage_filter()
+            return self._run(output, target2d, None, 0, bs, cs, None)
         _, _, inds = neg_filter(output, target2d, withids=True)
         counts, _ = np.histogram(inds, bins=bs, range=(0, bs * cs))
         img_start = [0] + [int(v) for v in np.cumsum(counts)]

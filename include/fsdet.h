@@ -233,14 +233,15 @@ int fsdet_head_bias_grad(const float* d, int ld, float* dbias, float* workspace 
 size_t fsdet_head_bias_grad_workspace_floats(size_t npix, int n_cls, int O);
 
 /* ---- region loss (region_loss.py) -------------------------------------- */
-/* RegionLoss(V2).forward prologue, region_loss.py:276-298: for the kept rows
- * `inds` of output [rows_total, A*(5+nC), H, W] computes pred_boxes
- * float32 [nB*A*H*W][4] = (sigmoid(tx)+col, sigmoid(ty)+row, exp(tw)*aw,
- * exp(th)*ah) in grid units, with torch's float32 op order. */
-int fsdet_region_decode(const float* output, const int32_t* inds, int nB, int A, int nC, int H, int W,
-                        const float* anchors_f32 /* [2A] */, float* pred_boxes, void* stream);
+/* RegionLoss(V2).forward prologue, region_loss.py:256-298: sigmoid / exp decode of the kept rows into
+ * pred_boxes float32 [nB*A*H*W][4] in grid units.  inds (optional) = kept output rows (neg_filter).
+ * nB_dev (optional, also below): device int32 holding the number of LIVE slots when the launch is frozen at a
+ * capacity of nB rows (CUDA-graph replay: neg_filter keeps a different number of rows every step). */
+int fsdet_region_decode(const float* output, const int32_t* inds, int nB, const int32_t* nB_dev, int A, int nC, int H,
+                        int W, const float* anchors_f32 /* [2A] */, float* pred_boxes, void* stream);
 /* build_targets, region_loss.py:37-132 (+ utils.bbox_ious / bbox_iou,
- * utils.py:21-83).  target: float64 [nB][250] rows already filtered.  Outputs:
+ * utils.py:21-83).  target: float64 [nB][250] rows already filtered, or - when
+ * `inds` is given - the FULL label matrix, of which slot b reads row inds[b].  Outputs:
  * nine float32 [nB][A][H][W] tensors and counters int32[4] = {nGT, nCorrect,
  * n_degenerate (GT with w or h == 0: the reference raises there), 0}.
  * Index/mask outputs are bit-exact w.r.t. the reference; phase-1 IoUs are
@@ -250,14 +251,14 @@ int fsdet_build_targets(const float* pred_boxes, const double* target, const dou
                         int nB, int A, int H, int W, int max_boxes, float noobject_scale, float object_scale,
                         float sil_thresh, long long seen, float* coord_mask, float* conf_mask, float* cls_mask,
                         float* tx, float* ty, float* tw, float* th, float* tconf, float* tcls, int32_t* counters,
-                        void* stream);
+                        const int32_t* inds, const int32_t* nB_dev, void* stream);
 /* Loss terms + gradient w.r.t. the raw head output (region_loss.py:303-345).
  * mode 0 = RegionLossV2 (softmax across the cs class rows of each image),
  * mode 1 = RegionLoss (softmax across nC channels; tcls zeroed if metayolo).
- * row_of[r] = kept-row slot of output row r or -1; img_start[bs+1] = prefix of
- * kept rows per image (V2).  losses: double[8] = {x,y,w,h,conf,cls,total,nProposals}
+ * img_start[bs+1] = prefix of kept rows per image (V2).
+ * losses: double[8] = {x,y,w,h,conf,cls,total,nProposals}
  * accumulated with atomics in double (zeroed by this call's first kernel). */
-int fsdet_region_loss_grad(const float* output, float* grad_output, const int32_t* inds, const int32_t* row_of,
+int fsdet_region_loss_grad(const float* output, float* grad_output, const int32_t* inds, const int32_t* nB_dev,
                            const int32_t* img_start, int rows_total, int nB, int bs, int cs, int A, int nC, int H,
                            int W, const float* coord_mask, const float* conf_mask, const float* cls_mask,
                            const float* tx, const float* ty, const float* tw, const float* th, const float* tconf,

@@ -23,15 +23,18 @@ def P(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
-def run_build_targets(emul, pred, target, anchors, A, H, W, seen, max_boxes=50):
-    nB = target.shape[0]
+def run_build_targets(emul, pred, target, anchors, A, H, W, seen, max_boxes=50, inds=None, live=None, cap=None):
+    """inds / live / cap: the CUDA-graph form - `cap` slots are launched, `live` of them (device scalar) are real, slot
+    b reads row inds[b] of the FULL label matrix."""
+    nB = target.shape[0] if cap is None else cap
     outs = [np.full((nB, A, H, W), 7.0, dtype=np.float32) for _ in NAMES]
     counters = np.full(4, -1, dtype=np.int32)
     pred = np.ascontiguousarray(pred, dtype=np.float32)
     target = np.ascontiguousarray(target, dtype=np.float64)
     anchors = np.ascontiguousarray(anchors, dtype=np.float64)
     emul.emul_build_targets(P(pred), P(target), P(anchors), nB, A, H, W, max_boxes, ctypes.c_float(1.0), ctypes.c_float(5.0),
-                            ctypes.c_float(0.6), ctypes.c_longlong(seen), *[P(o) for o in outs], P(counters))
+                            ctypes.c_float(0.6), ctypes.c_longlong(seen), *[P(o) for o in outs], P(counters),
+                            P(inds) if inds is not None else None, P(live) if live is not None else None)
     return outs, counters
 
 
@@ -72,7 +75,7 @@ def test_region_decode_kernel_vs_numpy(emul):
     out = rs.randn(nB, A * (5 + nC), H, W).astype(np.float32)
     anchors = np.array([1.3221, 1.73145, 3.19275, 4.00944, 5.05587, 8.09892, 9.47112, 4.84053, 11.2364, 10.0071], dtype=np.float32)
     pb = np.zeros((nB * A * H * W, 4), dtype=np.float32)
-    emul.emul_region_decode(P(out), None, nB, A, nC, H, W, P(anchors), P(pb))
+    emul.emul_region_decode(P(out), None, nB, None, A, nC, H, W, P(anchors), P(pb))
     o = out.reshape(nB, A, 5 + nC, H * W)
     sig = lambda v: 1.0 / (1.0 + np.exp(-v.astype(np.float64)))
     col = np.tile(np.arange(W), H)
@@ -80,3 +83,40 @@ def test_region_decode_kernel_vs_numpy(emul):
     want = np.stack([sig(o[:, :, 0]) + col, sig(o[:, :, 1]) + row, np.exp(o[:, :, 2].astype(np.float64)) * anchors[0::2][None, :, None],
                      np.exp(o[:, :, 3].astype(np.float64)) * anchors[1::2][None, :, None]], -1).reshape(-1, 4)
     np.testing.assert_allclose(pb, want, rtol=2e-6, atol=1e-6)
+
+
+def test_fixed_capacity_form_equals_compacted_rows(emul):
+    """GraphedTrainStep with neg_filter: the launches are frozen at the capacity of all rows; only `live` slots are
+    processed and slot b gathers row inds[b] of the full label matrix.  Result == the eager form on the gathered rows;
+    slots beyond `live` are not touched."""
+    d = np.load(os.path.join(G, 'build_targets_g13_seen20000.npz'))
+    H, W = int(d['nH']), int(d['nW'])
+    target = d['target']
+    nB = target.shape[0]
+    keep = np.array([i for i in range(nB) if i % 3 != 1], dtype=np.int32)
+    per = 5 * H * W
+    pred_all = d['pred_boxes'].reshape(nB, per, 4)
+    pred_kept = np.ascontiguousarray(pred_all[keep])
+    want, cw = run_build_targets(emul, pred_kept.reshape(-1, 4), target[keep], d['anchors'], 5, H, W, int(d['seen']))
+    # capacity form: pred_boxes compacted in slot order (what region_decode writes), padded to the capacity
+    pred_cap = np.zeros((nB, per, 4), dtype=np.float32)
+    pred_cap[:len(keep)] = pred_kept
+    inds = np.zeros(nB, dtype=np.int32)
+    inds[:len(keep)] = keep
+    live = np.array([len(keep)], dtype=np.int32)
+    got, cg = run_build_targets(emul, pred_cap.reshape(-1, 4), target, d['anchors'], 5, H, W, int(d['seen']), inds=inds, live=live,
+                                cap=nB)
+    assert cg.tolist() == cw.tolist()
+    for name, g, w_ in zip(NAMES, got, want):
+        assert np.array_equal(g[:len(keep)].view(np.uint32), w_.view(np.uint32)), name
+        assert np.all(g[len(keep):] == 7.0), name
+    # decode with a live count: slots beyond it are not written
+    rs = np.random.RandomState(3)
+    out = rs.randn(nB, 5 * 6, H, W).astype(np.float32)
+    anchors32 = d['anchors'].astype(np.float32)
+    pb_full = np.full((nB * per, 4), -1.0, dtype=np.float32)
+    emul.emul_region_decode(P(out), P(inds), nB, P(live), 5, 1, H, W, P(anchors32), P(pb_full))
+    pb_ref = np.full((len(keep) * per, 4), -1.0, dtype=np.float32)
+    emul.emul_region_decode(P(out), P(keep), len(keep), None, 5, 1, H, W, P(anchors32), P(pb_ref))
+    assert np.array_equal(pb_full[:len(keep) * per], pb_ref)
+    assert np.all(pb_full[len(keep) * per:] == -1.0)
