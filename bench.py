@@ -27,7 +27,7 @@ import torch  # noqa: E402
 
 METRIC = 'images/sec (416x416, 20-cls) meta-training step; build_targets ms/batch'
 # kernels launched per C-ABI call (lower bounds, for the gpu_launches claim)
-LAUNCHES = {'fsdet_conv_wgrad': 2, 'fsdet_bn_finalize': 2, 'fsdet_bn_bwd_finalize': 2, 'fsdet_head_bias_grad': 2,
+LAUNCHES = {'fsdet_weight_prep': 2, 'fsdet_conv_wgrad': 2, 'fsdet_bn_finalize': 2, 'fsdet_bn_bwd_finalize': 2, 'fsdet_head_bias_grad': 2,
             'fsdet_region_loss_grad': 3}
 
 
@@ -54,6 +54,49 @@ def synth_batch(B, ncls, side, seed):
     mask = torch.from_numpy(synth_masks(ncls, 416, seed + 1))
     target = torch.from_numpy(synth_targets(B, ncls, seed + 2, max_gt=5))
     return x, metax, mask, target
+
+
+def arch_costs(blocks, side, n_cls=1):
+    """(forward FLOPs, fused activation elements read + written) per image of a cfg network at input `side`, by
+    SURVEY.md 8d's rule: every convolution reads its input once and writes its output once, pooling / BN / leaky /
+    reorg / concat are fused into producers or consumers, the dynamic convolution + head count as ONE layer that reads
+    its input once and writes n_cls * 30 channels."""
+    C, H = int(blocks[0]['channels']), side
+    flops = elems = 0
+    hist = []
+    body = blocks[1:]
+    for idx, b in enumerate(body):
+        t = b['type']
+        if t == 'convolutional':
+            if 'dynamic' in b and int(b['dynamic']) == 1:
+                hist.append((C, H))
+                continue
+            k, f = int(b['size']), int(b['filters'])
+            rep = n_cls if (idx > 0 and 'dynamic' in body[idx - 1] and int(body[idx - 1]['dynamic']) == 1) else 1
+            flops += 2 * H * H * f * k * k * C * rep
+            elems += H * H * C + H * H * f * rep
+            C = f
+        elif t == 'maxpool' and int(b['stride']) == 2:
+            H //= 2
+        elif t == 'reorg':
+            C, H = C * 4, H // 2
+        elif t == 'route':
+            ls = [int(x) for x in b['layers'].split(',')]
+            ls = [l if l > 0 else l + idx for l in ls]
+            C, H = sum(hist[l][0] for l in ls), hist[ls[0]][1]
+        elif t == 'globalmax':
+            H = 1
+        hist.append((C, H))
+    return flops, elems
+
+
+def step_costs(B, ncls, side):
+    """Algorithmic FLOPs and HBM bytes of one training step per GPU: 3x the forward of B query and n_cls
+    support images (fp32 activations), weights read twice + written once + 5 SGD passes."""
+    from fewshot_detection_b200 import netcfg
+    fq, eq = arch_costs(netcfg.darknet_dynamic_blocks(side, side), side, ncls)
+    fs, es = arch_costs(netcfg.reweighting_net_blocks(), 416)
+    return 3.0 * (B * fq + ncls * fs), 3.0 * 4 * (B * eq + ncls * es) + 8 * 265.2e6
 
 
 class ClockSampler(object):
@@ -137,7 +180,22 @@ def cpu_step_factory(ncls, side, B, threads):
         loss.backward()
         opt.step()
         return float(loss.item())
+
+    def support_only():
+        """forward + backward of the support branch alone (its cost is per STEP, not per query image)"""
+        opt.zero_grad()
+        dw = m.meta_forward(metax, mask)
+        dw[0].sum().backward()
+    state['support_only'] = support_only
     return step, state
+
+
+def fair_cpu_rate(B_ref, B_full, t_step, t_support):
+    """images/s of the CPU arm at the GPU arm's query:support ratio.  The CPU step is a bounded sample of B_ref query
+    images but pays the whole support branch (n_cls images) every step, which the GPU arm amortises over B_full query
+    images: time per full step = (t_step - t_support) * B_full / B_ref + t_support."""
+    t_full = (t_step - t_support) * B_full / B_ref + t_support
+    return B_full / t_full
 
 
 def cpu_build_targets_ms(B, ncls, G=13):
@@ -169,16 +227,24 @@ def run_reference(args):
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    val = B * args.steps / dt
-    sample = '%d query + %d support images per step (the full step is 64 query + %d support per GPU), oracle port, ' \
-             'torch %s CPU, %d threads' % (B, args.ncls, args.ncls, torch.__version__, threads)
+    state['support_only']()
+    t1 = time.perf_counter()
+    for _ in range(2):
+        state['support_only']()
+    t_sup = (time.perf_counter() - t1) / 2
+    raw = B * args.steps / dt
+    val = fair_cpu_rate(B, args.batch, dt / args.steps, t_sup)
+    sample = '%d query + %d support images per step, oracle port, torch %s CPU, %d threads; value = images/s at the GPU ' \
+             "arm's ratio of %d query : %d support images per step, i.e. the support branch (%.2f s of the %.2f s sample step) " \
+             'charged once per %d query images (raw sample rate %.3f img/s)' % (
+                 B, args.ncls, torch.__version__, threads, args.batch, args.ncls, t_sup, dt / args.steps, args.batch, raw)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'configs[1]: darknet_dynamic + reweighting_net base-train step, %dx%d, %d classes, 5 anchors'
                                % (args.side, args.side, args.ncls), 'batch_per_step': B, 'n_cls': args.ncls,
-                   'neg': 'full', 'host': 'cpu'},
+                   'neg': 'full', 'host': 'cpu', 'support_branch': 'pro-rated to %d query images per step' % args.batch},
         'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -205,7 +271,8 @@ def main():
         __graft_entry__.build()
     if world > 1:
         dist.barrier()
-    from fewshot_detection_b200 import netcfg, _lib
+    from fewshot_detection_b200 import netcfg, _lib, engine as _engine
+    engine_terms = dict(_engine.TC_TERMS, persist=_engine.TC_PERSIST)
     from fewshot_detection_b200.cfg import cfg
     from fewshot_detection_b200.darknet_meta import Darknet
     from fewshot_detection_b200.optim import FusedSGD
@@ -330,7 +397,7 @@ def main():
     dom = max(kern, key=lambda k: kern[k]['ms_per_step']) if kern else None
     traffic = None
     try:
-        rj = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_r01.json')))
+        rj = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_r02.json' if os.path.exists(os.path.join(ROOT, 'profiles', 'roofline_r02.json')) else 'roofline_r01.json')))
         if rj.get('kernel') == dom:
             traffic = rj['traffic_bytes_per_launch']
     except Exception:
@@ -341,8 +408,8 @@ def main():
         roofline = {'kernel': dom, 'bound': 'tensor', 'achieved': a, 'peak': peak_tf, 'unit': 'TFLOP/s',
                     'frac': a / peak_tf, 'traffic': traffic, 'peak_source': peak_src,
                     'share_of_step': kern[dom]['ms_per_step'] / (ms / args.steps), 'kernels': kern,
-                    'note': 'tcgen05 implicit GEMM with fp16 hi/lo operand splitting: 3 tensor-core MMAs per fp32-equivalent '
-                            'MAC, i.e. the tensor pipe does 3x the algorithmic FLOPs; measured against the bf16 peak. '
+                    'note': 'tcgen05 implicit GEMM (forward + input gradient) with fp16 hi/lo operand splitting: 3 tensor-core MMAs '
+                            'per fp32-equivalent MAC, i.e. the tensor pipe does 3x the algorithmic FLOPs; measured against the bf16 peak. '
                             'Per-kernel times are CUDA-event timed eager launches in this run (the timed region '
                             'replays the same kernels from a CUDA graph)'}
 
@@ -350,18 +417,24 @@ def main():
     # (fused algorithmic bytes: every layer reads its input and writes its output once, x3 for a training step, + 8
     # passes over the 265 MB of parameters) next to the tensor-pipe figure of the MMA layers.
     step_rooflines = None
+    hbm_gbs = float(peaks.get('hbm_gbs', 6577.7))
+
+    def whole_step(Bq, nc, sd, ms_step):
+        alg_flops, alg_bytes = step_costs(Bq, nc, sd)
+        t = ms_step / 1e3
+        return {'hbm_frac': alg_bytes / t / 1e9 / hbm_gbs, 'tensor_frac': alg_flops / t / 1e12 / peak_tf,
+                'algorithmic_GB': alg_bytes / 1e9, 'algorithmic_TFLOP': alg_flops / 1e12}
     try:
-        if side == 416:
-            hbm_gbs = float(peaks.get('hbm_gbs', 6577.7))
-            alg_bytes = 3.0 * (B * 100.7e6 + ncls * 57.4e6) + 8 * 265.2e6
-            alg_flops = 3.0 * (B * 29.48e9 + ncls * 9.05e9)
+        if True:
+            alg_flops, alg_bytes = step_costs(B, ncls, side)
             t = ms / args.steps / 1e3
             step_rooflines = {
                 'hbm': {'algorithmic_bytes_per_step_per_gpu': alg_bytes, 'achieved_GBps': alg_bytes / t / 1e9,
                         'peak_GBps': hbm_gbs, 'frac': alg_bytes / t / 1e9 / hbm_gbs, 'floor_ms': alg_bytes / hbm_gbs / 1e6},
                 'tensor': {'algorithmic_flops_per_step_per_gpu': alg_flops, 'achieved_TFLOPs': alg_flops / t / 1e12,
                            'peak_TFLOPs': peak_tf, 'frac': alg_flops / t / 1e12 / peak_tf,
-                           'note': 'fp32-equivalent arithmetic = 3 tensor-core MACs per MAC: the reachable fraction is 1/3'}}
+                           'note': 'forward / input-gradient GEMMs: fp32-equivalent arithmetic = 3 tensor-core MACs per MAC; '
+                                   'weight-gradient GEMMs: 1 (engine.TC_TERMS, profiles/precision_budget_r02.log)'}}
             if roofline is not None:
                 roofline['whole_step'] = step_rooflines
     except Exception as e:  # never lose the bench line over a derived figure
@@ -395,6 +468,42 @@ def main():
     ms_e2e = timed(e2e_step, args.steps, flush=lambda: e2e_losses.extend(reader.drain()))
     assert len(e2e_losses) == args.steps + 3 and all(np.isfinite(v) for v in e2e_losses)
     e2e_value = global_batch * args.steps / (ms_e2e / 1e3)
+
+    # ---- the reference's real training regimes and the other BASELINE configs, same model / optimizer / graph cache
+    # (extra keys; each is a device-resident CUDA-graph replay loop like `value`, inputs larger than L2):
+    #   neg1     configs[1] with cfg.neg_ratio = 1 (cfg/metayolo.data: base training; rows sampled on the host per step)
+    #   eager    configs[1] with every kernel launched eagerly through ctypes (--no-graph path, host-bound)
+    #   configs3 fine-tuning regime: 20 classes, cfg.neg_ratio = 0 (cfg/metatune.data)
+    #   configs4 608x608, 80 classes (largest single-GPU variant: B = 64 per GPU)
+    extras = {}
+
+    def extra_line(tag, Bq, nc, sd, neg, nsteps, graph=True):
+        try:
+            hb = [synth_batch(Bq, nc, sd, 7000 + 1000 * rank + 10 * i) for i in range(2)]
+            rb = [tuple(t.to(dev) for t in b[:3]) + (b[3],) for b in hb]       # labels stay on the host (neg_filter)
+            cfg.neg_ratio = neg
+            fn = (lambda i: step(*rb[i % 2])) if graph else (lambda i: eager_step(*rb[i % 2]))
+            for i in range(3):
+                fn(i)
+            m_ = timed(fn, nsteps)
+            v = Bq * world * nsteps / (m_ / 1e3)
+            extras[tag] = {'value': v, 'unit': 'images/s', 'ms_per_step': m_ / nsteps, 'steps': nsteps,
+                           'config': {'batch_per_gpu': Bq, 'n_cls': nc, 'side': sd, 'neg': str(neg),
+                                      'launch': 'cuda-graph replay' if graph else 'eager'},
+                           'roofline_whole_step': whole_step(Bq, nc, sd, m_ / nsteps)}
+            del hb, rb
+        except Exception as e:      # an extra line must never cost the headline
+            extras[tag] = {'error': repr(e)}
+            sys.stderr.write('extra line %s failed: %r\n' % (tag, e))
+        finally:
+            cfg.neg_ratio = 'full'
+            torch.cuda.empty_cache()
+
+    if graphed is not None and not os.environ.get('FSDET_BENCH_NO_EXTRAS'):
+        extra_line('neg1', B, ncls, side, 1, max(4, args.steps // 2))
+        extra_line('eager', B, ncls, side, 'full', 3, graph=False)
+        extra_line('configs3', B, 20, 416, 0, max(4, args.steps // 2))
+        extra_line('configs4', B, 80, 608, 'full', 4)
 
     # ---- build_targets ms/batch (decode output -> 9 target tensors + counters, device resident)
     nB = B * ncls
@@ -495,10 +604,17 @@ def main():
         cstep()
         cstep()
         dt = (time.perf_counter() - t0) / 2
-        cpu_baseline = {'value': args.ref_batch / dt, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+        cstate['support_only']()
+        t0 = time.perf_counter()
+        cstate['support_only']()
+        t_sup = time.perf_counter() - t0
+        cpu_baseline = {'value': fair_cpu_rate(args.ref_batch, B, dt, t_sup), 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                        'raw_sample_rate': args.ref_batch / dt, 'support_branch_s': t_sup, 'sample_step_s': dt,
                         'sample': '2 full training steps (after 1 warm-up) of %d query + %d support images at %dx%d (oracle '
-                                  'port: torch-CPU ops + Python build_targets); %d of %d host cores used, see cpu_threads()'
-                                  % (args.ref_batch, ncls, side, side, threads, os.cpu_count() or 1)}
+                                  'port: torch-CPU ops + Python build_targets); %d of %d host cores used, see cpu_threads(); '
+                                  'value = images/s with the support branch charged once per %d query images, the GPU '
+                                  "arm's query:support ratio (fair_cpu_rate)"
+                                  % (args.ref_batch, ncls, side, side, threads, os.cpu_count() or 1, B)}
         bt_cpu_ms = cpu_build_targets_ms(B, ncls, G)
         # decode + NMS of ONE image's n_cls rows with the oracle port (Python loops, as the reference's)
         from oracle import utils as OU
@@ -529,6 +645,8 @@ def main():
         'cpu_baseline': cpu_baseline,
         'build_targets_ms': {'gpu': bt_gpu_ms, 'cpu_oracle': bt_cpu_ms, 'rows': nB, 'grid': G},
         'augment': aug,
+        'extras': extras,
+        'precision_policy': dict(engine_terms),
         'detect_nms_ms': {'gpu': det_gpu_ms, 'rows': nB, 'survivors': det_kept, 'cpu_oracle_one_image': det_cpu_ms,
                           'cpu_rows': ncls, 'note': 'decode + threshold 0.005 + NMS 0.45 of all (image, class) rows; the CPU '
                                                     'figure is the oracle port on the first image only (n_cls rows)'},

@@ -37,6 +37,7 @@ SIGNATURES = {
     'fsdet_conv_tc_wgrad_supported': ('iii', 'i'),
     'fsdet_conv_tc_wgrad_workspace_floats': ('iiiiiii', 'z'),
     'fsdet_conv_tc_wgrad': ('ppppppppziiiiiiip', 'i'),
+    'fsdet_weight_prep': ('ppipip', 'i'),
     'fsdet_amax': ('piizpp', 'i'),
     'fsdet_split_f16': ('piiizpppp', 'i'),
     'fsdet_colstats': ('pizipp', 'i'),

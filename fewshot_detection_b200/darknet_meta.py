@@ -26,87 +26,102 @@ from .pooling import GlobalMaxPool2d, MaxPoolStride1, MaxPool2x2, Reorg, EmptyMo
 from .region_loss import RegionLossV2, RegionLoss
 
 
+class _Build(object):
+    """Running state while a block list is turned into modules: channel count of the current feature map, channel
+    counts of every module built so far (routes look them up), convolution and dynamic-convolution counters."""
+
+    def __init__(self, owner, loss_cls):
+        self.owner, self.loss_cls = owner, loss_cls
+        self.channels = 3
+        self.history = []
+        self.n_conv = 0
+        self.n_dynamic = 0
+
+
+def _make_convolutional(ctx, block):
+    """nn.Sequential(conv{i}[, bn{i}][, leaky{i}]) - the names are the state_dict keys of the reference
+    (darknet_meta.py:219-259).  Bias only without BatchNorm; pad = (k-1)//2 when `pad=1`."""
+    ctx.n_conv += 1
+    tag = str(ctx.n_conv)
+    k, filters = int(block['size']), int(block['filters'])
+    pad = (k - 1) // 2 if int(block['pad']) else 0
+    has_bn = bool(int(block['batch_normalize']))
+    if 'groups' in block and int(block['groups']) != 1:
+        raise NotImplementedError('grouped convolution')
+    if ctx.owner.is_dynamic(block):
+        conv_cls = dynamic_conv2d(ctx.n_dynamic == 0, partial=int(block['partial']) if 'partial' in block else None)
+        ctx.n_dynamic += 1
+    else:
+        conv_cls = nn.Conv2d
+    use_bias = (not has_bn) and (bool(int(block['bias'])) if 'bias' in block else True)
+    seq = nn.Sequential()
+    seq.add_module('conv' + tag, conv_cls(ctx.channels, filters, k, int(block['stride']), pad, bias=use_bias))
+    if has_bn:
+        seq.add_module('bn' + tag, nn.BatchNorm2d(filters))
+    if block['activation'] == 'leaky':
+        seq.add_module('leaky' + tag, nn.LeakyReLU(0.1, inplace=True))
+    elif block['activation'] == 'relu':
+        raise NotImplementedError('relu activation')
+    ctx.channels = filters
+    return seq
+
+
+def _make_maxpool(ctx, block):
+    size, stride = int(block['size']), int(block['stride'])
+    return MaxPool2x2(size, stride) if stride > 1 else MaxPoolStride1()
+
+
+def _make_reorg(ctx, block):
+    stride = int(block['stride'])
+    ctx.channels = stride * stride * ctx.channels
+    return Reorg(stride)
+
+
+def _make_route(ctx, block):
+    here = len(ctx.history)
+    sources = [int(i) if int(i) > 0 else int(i) + here for i in block['layers'].split(',')]
+    if len(sources) == 2:
+        assert sources[0] == here - 1
+    if len(sources) in (1, 2):
+        ctx.channels = sum(ctx.history[i] for i in sources)
+    return EmptyModule()
+
+
+def _make_region(ctx, block):
+    loss = ctx.loss_cls()
+    loss.anchors = [float(i) for i in block['anchors'].split(',')]
+    loss.num_classes = int(block['classes'])
+    loss.num_anchors = int(block['num'])
+    loss.anchor_step = len(loss.anchors) // loss.num_anchors
+    for key in ('object_scale', 'noobject_scale', 'class_scale', 'coord_scale'):
+        setattr(loss, key, float(block[key]))
+    return loss
+
+
+_BUILDERS = {
+    'convolutional': _make_convolutional,
+    'maxpool': _make_maxpool,
+    'reorg': _make_reorg,
+    'route': _make_route,
+    'region': _make_region,
+    'globalmax': lambda ctx, block: GlobalMaxPool2d(),
+}
+
+
 def create_network(owner, blocks, loss_cls):
-    """Block list -> nn.ModuleList (darknet_meta.py:208-353 / darknet.py:134-245)."""
+    """Block list -> nn.ModuleList with one module per non-header block (darknet_meta.py:208-353 /
+    darknet.py:134-245), through a table from block type to builder."""
+    ctx = _Build(owner, loss_cls)
     models = nn.ModuleList()
-    prev_filters = 3
-    out_filters = []
-    conv_id = 0
-    dynamic_count = 0
     for block in blocks:
-        t = block['type']
-        if t == 'net' or t == 'learnet':
-            prev_filters = int(block['channels'])
+        kind = block['type']
+        if kind in ('net', 'learnet'):
+            ctx.channels = int(block['channels'])
             continue
-        elif t == 'convolutional':
-            conv_id = conv_id + 1
-            batch_normalize = int(block['batch_normalize'])
-            filters = int(block['filters'])
-            kernel_size = int(block['size'])
-            stride = int(block['stride'])
-            pad = (kernel_size - 1) // 2 if int(block['pad']) else 0
-            activation = block['activation']
-            bias = bool(int(block['bias'])) if 'bias' in block else True
-            if owner.is_dynamic(block):
-                partial = int(block['partial']) if 'partial' in block else None
-                Conv2d = dynamic_conv2d(dynamic_count == 0, partial=partial)
-                dynamic_count += 1
-            else:
-                Conv2d = nn.Conv2d
-            if 'groups' in block and int(block['groups']) != 1:
-                raise NotImplementedError('grouped convolution')
-            model = nn.Sequential()
-            if batch_normalize:
-                model.add_module('conv{0}'.format(conv_id), Conv2d(prev_filters, filters, kernel_size, stride, pad, bias=False))
-                model.add_module('bn{0}'.format(conv_id), nn.BatchNorm2d(filters))
-            else:
-                model.add_module('conv{0}'.format(conv_id), Conv2d(prev_filters, filters, kernel_size, stride, pad, bias=bias))
-            if activation == 'leaky':
-                model.add_module('leaky{0}'.format(conv_id), nn.LeakyReLU(0.1, inplace=True))
-            elif activation == 'relu':
-                raise NotImplementedError('relu activation')
-            prev_filters = filters
-            out_filters.append(prev_filters)
-            models.append(model)
-        elif t == 'maxpool':
-            pool_size = int(block['size'])
-            stride = int(block['stride'])
-            models.append(MaxPool2x2(pool_size, stride) if stride > 1 else MaxPoolStride1())
-            out_filters.append(prev_filters)
-        elif t == 'reorg':
-            stride = int(block['stride'])
-            prev_filters = stride * stride * prev_filters
-            out_filters.append(prev_filters)
-            models.append(Reorg(stride))
-        elif t == 'route':
-            layers = block['layers'].split(',')
-            ind = len(models)
-            layers = [int(i) if int(i) > 0 else int(i) + ind for i in layers]
-            if len(layers) == 1:
-                prev_filters = out_filters[layers[0]]
-            elif len(layers) == 2:
-                assert layers[0] == ind - 1
-                prev_filters = out_filters[layers[0]] + out_filters[layers[1]]
-            out_filters.append(prev_filters)
-            models.append(EmptyModule())
-        elif t == 'region':
-            loss = loss_cls()
-            anchors = block['anchors'].split(',')
-            loss.anchors = [float(i) for i in anchors]
-            loss.num_classes = int(block['classes'])
-            loss.num_anchors = int(block['num'])
-            loss.anchor_step = len(loss.anchors) // loss.num_anchors
-            loss.object_scale = float(block['object_scale'])
-            loss.noobject_scale = float(block['noobject_scale'])
-            loss.class_scale = float(block['class_scale'])
-            loss.coord_scale = float(block['coord_scale'])
-            out_filters.append(prev_filters)
-            models.append(loss)
-        elif t == 'globalmax':
-            out_filters.append(prev_filters)
-            models.append(GlobalMaxPool2d())
-        else:
-            raise NotImplementedError('block type %s is not on the supported hot path' % t)
+        if kind not in _BUILDERS:
+            raise NotImplementedError('block type %s is not on the supported hot path' % kind)
+        models.append(_BUILDERS[kind](ctx, block))
+        ctx.history.append(ctx.channels)
     return models
 
 
@@ -172,54 +187,45 @@ class Darknet(nn.Module):
         return 'dynamic' in block and int(block['dynamic']) == 1
 
     # --------------------------------------------------------------- weight IO
+    def _weight_stream(self):
+        """The Darknet weight stream's order (darknet_meta.py:355-479): every convolution that owns weights as
+        (position, conv, bn-or-None) - detector blocks first, then the reweighting net.  `position` is the 1-based
+        block counter `save_weights(cutoff=)` counts in: detector block i sits at i, learnet block j at
+        len(self.blocks) + j (the learnet header occupies a position of its own)."""
+        for offset, blocks, models in ((0, self.blocks, self.models), (len(self.blocks), self.learnet_blocks, self.learnet_models)):
+            for i, block in enumerate(blocks):
+                if i == 0 or block['type'] != 'convolutional':
+                    continue
+                seq = models[i - 1]
+                if self.is_dynamic(block) and seq[0].weight is None:
+                    continue                                    # the dynamic convolution's weights are its input
+                yield offset + i, seq[0], (seq[1] if int(block['batch_normalize']) else None)
+
     def load_weights(self, weightfile):
-        """Darknet weight stream (darknet_meta.py:355-411): detector blocks first,
-        then the reweighting net; loading stops silently when the buffer is
-        exhausted (that is how darknet19_448.conv.23 initialises only the trunk)."""
+        """header int32[4] (its last entry is `seen`) + float32 stream.  Loading stops silently where the stream
+        ends - that is how darknet19_448.conv.23 initialises only the trunk (darknet_meta.py:367-368)."""
         with open(weightfile, 'rb') as fp:
             header = np.fromfile(fp, count=4, dtype=np.int32)
-            self.header = torch.from_numpy(header)
-            self.seen = int(self.header[3])
             buf = np.fromfile(fp, dtype=np.float32)
+        self.header = torch.from_numpy(header)
+        self.seen = int(self.header[3])
         start = 0
-        for blocks, models in [(self.blocks, self.models), (self.learnet_blocks, self.learnet_models)]:
-            ind = -2
-            for block in blocks:
-                if start >= buf.size:
-                    break
-                ind = ind + 1
-                if block['type'] == 'convolutional':
-                    model = models[ind]
-                    if self.is_dynamic(block) and model[0].weight is None:
-                        continue
-                    if int(block['batch_normalize']):
-                        start = load_conv_bn(buf, start, model[0], model[1])
-                    else:
-                        start = load_conv(buf, start, model[0])
+        for _, conv, bn in self._weight_stream():
+            if start >= buf.size:
+                break
+            start = load_conv_bn(buf, start, conv, bn) if bn is not None else load_conv(buf, start, conv)
 
     def save_weights(self, outfile, cutoff=0):
-        """darknet_meta.py:413-479."""
+        """Writes the stream up to block position `cutoff` (0 = everything), darknet_meta.py:413-479."""
         if cutoff <= 0:
             cutoff = len(self.blocks) - 1 + len(self.learnet_blocks)
         with open(outfile, 'wb') as fp:
             self.header[3] = int(self.seen)
             self.header.numpy().tofile(fp)
-            ind = -1
-            for blockId in range(1, cutoff + 1):
-                if blockId >= len(self.blocks):
-                    if blockId == len(self.blocks):
-                        ind = -2
-                    blockId = blockId - len(self.blocks)
-                    blocks, models = self.learnet_blocks, self.learnet_models
+            for position, conv, bn in self._weight_stream():
+                if position > cutoff:
+                    break
+                if bn is not None:
+                    save_conv_bn(fp, conv, bn)
                 else:
-                    blocks, models = self.blocks, self.models
-                ind = ind + 1
-                block = blocks[blockId]
-                if block['type'] == 'convolutional':
-                    model = models[ind]
-                    if self.is_dynamic(block) and model[0].weight is None:
-                        continue
-                    if int(block['batch_normalize']):
-                        save_conv_bn(fp, model[0], model[1])
-                    else:
-                        save_conv(fp, model[0])
+                    save_conv(fp, conv)

@@ -12,8 +12,8 @@ work of the WHOLE batch is one `fsdet_augment_batch` launch (+ one `fsdet_box_ma
   MetaBatcher        support images + masks: get_metain (dataset.py:423-445) incl. its re-draw loop, get_img_mask
                      (dataset.py:378-398) for metain_type 1/2
 
-What is NOT mirrored: the few-shot list construction (build_dataset / load_metadict / build_fewset, dataset.py:57-180:
-file bookkeeping with a pdb.set_trace() left in it) - both classes take already-built lists.  Entries may be image
+The few-shot list construction (build_dataset / load_metadict / build_fewset, MetaDataset's index) lives in lists.py;
+both classes here take already-built lists.  Entries may be image
 paths (decoded on the host with PIL, label path derived like listDataset.get_labpath) or in-memory
 (uint8 array, label array) pairs.
 """
@@ -89,13 +89,21 @@ class DetectionBatcher(object):
     lines: image paths, or (uint8 [h, w, 3] array, label array [k, 5]) pairs.  `batch(indices)` returns
     (data float32 CUDA [B, 3, H, W], target float64 CPU [B, n_cls, 250] (cfg.metayolo) or [B, 250])."""
 
-    def __init__(self, lines, shape=None, shuffle=True, train=False, seen=0, batch_size=64, num_workers=4, filter=None):
+    def __init__(self, lines, shape=None, shuffle=True, train=False, seen=0, batch_size=64, num_workers=4, filter=None,
+                 seen_step=None):
+        """seen_step: by how much `seen` (the GLOBAL sample count that drives the multi-scale schedule) advances per
+        sample of THIS batcher.  The reference adds `num_workers` per sample inside every DataLoader worker's private
+        dataset copy, each of which sees 1/num_workers of the samples (dataset.py:262) - i.e. its copies track the
+        global count.  One batcher that sees every sample must add 1 (single process) or the world size (one process
+        per GPU, each batcher seeing 1/world of the global batch).  `num_workers` is kept for signature compatibility
+        and only used as the step when seen_step is None and a legacy caller relies on it (tests pass 1)."""
         self.lines = list(lines)
         if shuffle:
             random.shuffle(self.lines)
         self.nSamples = len(self.lines)
         self.shape, self.train, self.seen = shape, train, seen
         self.batch_size, self.num_workers, self.filter = batch_size, num_workers, filter
+        self.seen_step = num_workers if seen_step is None else seen_step
         self.first_batch = False
 
     def __len__(self):
@@ -122,7 +130,7 @@ class DetectionBatcher(object):
             p['shape'] = self.shape
             entries.append(e)
             params.append(p)
-            self.seen = self.seen + self.num_workers
+            self.seen = self.seen + self.seen_step
         shapes = set(p['shape'] for p in params)
         if len(shapes) != 1:
             raise ValueError('a batch must not straddle a multi-scale boundary (indices %r)' % (list(indices),))

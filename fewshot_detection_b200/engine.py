@@ -328,9 +328,10 @@ class NetRunner(object):
         return self._tc_ok(cin, c.cout, c.k) and c.cout >= 32 and bool(
             _lib.lib.fsdet_conv_tc_wgrad_supported(_round_up(cin, 64), _round_up(c.cout, 64), c.k))
 
-    def _conv(self, name, x, w_ohwi, bias, z, stat_rows_out, cin, cout, k, acc, st, w_amax=None):
+    def _conv(self, name, x, w_ohwi, bias, z, stat_rows_out, cin, cout, k, acc, st, w_amax=None, wplanes=None):
         """z = conv(x, w) through the tensor-core kernel when the shape allows, else SIMT.
-        Returns the number of BN partial rows written to `stat_rows_out` (a float tensor or None)."""
+        Returns the number of BN partial rows written to `stat_rows_out` (a float tensor or None).
+        wplanes: (hi, lo, amax) of the weight operand when fsdet_weight_prep already produced them."""
         flops = 2.0 * x.npix * cout * k * k * cin
         if x.nchw is not None:
             in0, c0, in1, c1 = x.nchw
@@ -344,9 +345,12 @@ class NetRunner(object):
         if bias is None and name in TC_PARTS and self._tc_ok(cin, cout, k):
             cpad = _round_up(cin, 64)
             xh, xl, xa = self._planes(x, st)
-            wh, wl, wa = self._split_tensor(ptr(w_ohwi), cin, cin, cout * k * k, x.dev, st, cpad, w_amax)
-            if name == 'fwd':   # the flip-transposed copy used by the input-gradient GEMM has the same absolute maximum
-                w_ohwi._fsdet_amax = (wa, w_ohwi._version)
+            if wplanes is not None:
+                wh, wl, wa = wplanes
+            else:
+                wh, wl, wa = self._split_tensor(ptr(w_ohwi), cin, cin, cout * k * k, x.dev, st, cpad, w_amax)
+                if name == 'fwd':   # the flip-transposed copy used by the input-gradient GEMM has the same absolute maximum
+                    w_ohwi._fsdet_amax = (wa, w_ohwi._version)
             mode = tc_mode(name)
             self._timed('conv_tc', flops, 'fsdet_conv_tc_fwd', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(xa), ptr(wa), z.ptr, z.ld,
                         x.B, x.H, x.W, _round_up(cin, 32), cpad, cout, k, acc, mode, ptr(stat_rows_out), st)
@@ -390,6 +394,74 @@ class NetRunner(object):
         tmp = torch.empty_like(p)
         return tmp, (lambda: p.grad.add_(tmp))
 
+    # -- weight operands of all tensor-core layers, two launches per step ----------------------------------------
+    def _weight_plan(self, dev):
+        """Device tables for fsdet_weight_prep (built once; rebuilt when a weight tensor moved): one descriptor per
+        BatchNorm convolution that runs on the tensor cores, persistent zero-initialised fp16 planes for its forward
+        GEMM and - when its input needs a gradient - for its input-gradient GEMM."""
+        import struct
+        import numpy as np
+        layers = []
+        prev = self.in_cpad
+        first = True
+        for s in self.specs:
+            if s.kind == 'conv' and not s.head:
+                conv, bn = self._conv_modules(self.models[s.idx])
+                cin_p = _round_up(s.cin, 4)
+                if bn is not None and not first and self._tc_ok(cin_p, s.cout, s.k) and cin_p == s.cin:
+                    layers.append((s, self._ohwi(conv.weight), cin_p))
+            first = False if s.kind == 'conv' else first
+        key = (str(dev), USE_TC, tuple(sorted(TC_PARTS)), tuple(w.data_ptr() for _, w, _ in layers))
+        plan = getattr(self, '_wplan', None)
+        if plan is not None and plan['key'] == key:
+            return plan
+        plan = {'key': key, 'by_id': {}, 'n': len(layers)}
+        if not layers:
+            self._wplan = plan
+            return plan
+        amax_all = torch.zeros(len(layers), dtype=torch.float32, device=dev)
+        descs = b''
+        tiles = []
+        for li, (s, w, cin_p) in enumerate(layers):
+            kk = s.k * s.k
+            fp, bp = _round_up(cin_p, 64), _round_up(s.cout, 64)
+            want_fwd = 'fwd' in TC_PARTS
+            want_bwd = 'dgrad' in TC_PARTS and self._tc_ok(s.cout, cin_p, s.k)
+            fh = fl = bh = bl = None
+            if want_fwd:
+                fh = torch.zeros(s.cout, kk * fp, dtype=torch.float16, device=dev)
+                fl = torch.zeros(s.cout, kk * fp, dtype=torch.float16, device=dev)
+            if want_bwd:
+                bh = torch.zeros(cin_p, kk * bp, dtype=torch.float16, device=dev)
+                bl = torch.zeros(cin_p, kk * bp, dtype=torch.float16, device=dev)
+            tci, tco = (cin_p + 31) // 32, (s.cout + 31) // 32
+            am = amax_all[li:li + 1]
+            descs += struct.pack('<6Q8i', w.data_ptr(), ptr(fh) or 0, ptr(fl) or 0, ptr(bh) or 0, ptr(bl) or 0, am.data_ptr(),
+                                 s.cout, kk, cin_p, fp, bp, tci, tco, 0)
+            n_t = kk * tci * tco
+            t = np.empty((n_t, 2), dtype=np.int32)
+            t[:, 0] = li
+            t[:, 1] = np.arange(n_t, dtype=np.int32)
+            tiles.append(t)
+            plan['by_id'][id(w)] = {'fwd': (fh, fl, am) if want_fwd else None, 'bwd': (bh, bl, am) if want_bwd else None}
+        tiles = np.concatenate(tiles, 0)
+        plan['descs'] = torch.frombuffer(bytearray(descs), dtype=torch.uint8).to(dev)
+        plan['tiles'] = torch.from_numpy(tiles).to(dev)
+        plan['n_tiles'] = int(tiles.shape[0])
+        plan['amax'] = amax_all
+        self._wplan = plan
+        return plan
+
+    def _prepare_weights(self, dev, st):
+        """Planes of every tensor-core layer's weights for this step (the weights change once per step)."""
+        self._wp = {}
+        if not USE_TC:
+            return
+        plan = self._weight_plan(dev)
+        if plan['n']:
+            call('fsdet_weight_prep', ptr(plan['descs']), ptr(plan['tiles']), plan['n_tiles'], ptr(plan['amax']), plan['n'], st)
+            self._wp = plan['by_id']
+
     # -- forward -----------------------------------------------------------
     def forward(self, inputs, extra=None, training=True, record=True):
         """inputs: list of NCHW tensors concatenated along channels (image[, mask]).
@@ -407,6 +479,7 @@ class NetRunner(object):
         for t in inputs:
             if t.dtype != torch.float32 or not t.is_cuda:
                 raise TypeError('inputs must be float32 CUDA tensors (no CPU fallback)')
+        self._prepare_weights(dev, st)
         first = self.specs[0] if self.specs else None
         in0 = inputs[0].contiguous()
         in1 = inputs[1].contiguous() if c1 else None
@@ -541,7 +614,8 @@ class NetRunner(object):
             use_batch_stats = training or not bn.track_running_stats
             rows_cap = max(_lib.lib.fsdet_conv_stat_rows(npix), _lib.lib.fsdet_colstats_rows(npix), (npix + 127) // 128)
             stat = _empty(rows_cap + _lib.lib.fsdet_bn_stat_scratch_rows(), 4 * s.cout, device=dev) if use_batch_stats else None
-            rows = self._conv('fwd', x, wuse, None, z, stat, cin_p, s.cout, s.k, 0, st)
+            wp = getattr(self, '_wp', {}).get(id(wuse))
+            rows = self._conv('fwd', x, wuse, None, z, stat, cin_p, s.cout, s.k, 0, st, wplanes=wp['fwd'] if wp else None)
             vec = _empty(5, s.cout, device=dev)  # mean, invstd, scale, shift, max|xhat| (batch statistics only)
             vec.xh_ok = bool(use_batch_stats)
             amax_y = _empty(1, device=dev) if use_batch_stats else None
@@ -724,9 +798,14 @@ class NetRunner(object):
             return
         dev = x.dev
         kk = k * k
+        g, acc = x.grad_for_write()
+        wp = getattr(self, '_wp', {}).get(id(w_ohwi))
+        if wp is not None and wp['bwd'] is not None and dz.planes is not None:
+            # flip-transposed planes prepared at the start of the step; `w_ohwi` only names the layer here
+            self._conv('dgrad', dz, w_ohwi, None, g, None, cout, cin_p, k, acc, st, wplanes=wp['bwd'])
+            return
         wt = _empty(cin_p, kk, cout, device=dev)
         call('fsdet_weight_flip_transpose', ptr(w_ohwi), ptr(wt), cout, kk, cin_p, st)
-        g, acc = x.grad_for_write()
         known = getattr(w_ohwi, '_fsdet_amax', None)
         w_amax = known[0] if (known is not None and known[1] == w_ohwi._version) else None
         self._conv('dgrad', dz, wt, None, g, None, cout, cin_p, k, acc, st, w_amax)

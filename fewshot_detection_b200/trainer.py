@@ -61,9 +61,11 @@ def epoch_plan(model_seen, nsamples, batch_size, max_batches, tuning=False, max_
 
 class MetaTrainer(object):
     def __init__(self, model, optimizer, learning_rate, batch_size, steps, scales, make_train_batcher, make_meta_batcher,
-                 backupdir=None, save_interval=10, reducer=None, world=1, processed_batches=0, log=print):
+                 backupdir=None, save_interval=10, reducer=None, world=1, processed_batches=0, log=print, use_graph=None):
         """learning_rate: the cfg rate already divided by `lr_factor` (what the driver calls `learning_rate` after
-        :136); batch_size: GLOBAL batch; make_train_batcher(seen) / make_meta_batcher(): the epoch's data streams."""
+        :136); batch_size: GLOBAL batch; make_train_batcher(seen) / make_meta_batcher(): the epoch's data streams.
+        use_graph: replay the step from CUDA graphs (graph.GraphedTrainStep: one graph per input shape, neg_filter
+        staged from the host) - the default whenever the model's parameters live on a CUDA device."""
         self.model, self.optimizer = model, optimizer
         self.region_loss = model.loss
         self.learning_rate, self.batch_size = learning_rate, batch_size
@@ -75,6 +77,15 @@ class MetaTrainer(object):
         self.region_loss.seen = model.seen           # train_meta.py:93
         self.log = log
         self.losses = collections.deque(maxlen=100)   # detached loss tensors of the most recent steps (no host sync)
+        if use_graph is None:
+            use_graph = any(p.is_cuda for p in model.parameters())
+        self.graphed = None
+        if use_graph:
+            from .distributed import GradAllReducer
+            from .graph import GraphedTrainStep
+            if self.reducer is None:
+                self.reducer = GradAllReducer(model)      # flat gradient buffer: in-place all-reduce and fused SGD
+            self.graphed = GraphedTrainStep(model, self.region_loss, optimizer, self.reducer)
 
     def adjust_learning_rate(self, batch):
         lr = learning_rate_at(batch, self.learning_rate, self.steps, self.scales)
@@ -83,9 +94,16 @@ class MetaTrainer(object):
         return lr
 
     def train_step(self, data, metax, mask, target):
+        """One optimisation step (train_meta.py:214-225).  No `zero_grad()`: the engine OVERWRITES every parameter
+        gradient each step (and with a GradAllReducer the gradients are views into its flat buffer, which
+        `zero_grad(set_to_none=True)` would silently detach - the all-reduce would then run over stale zeros)."""
+        if self.graphed is not None:
+            self.region_loss.seen = self.region_loss.seen + data.size(0) * self.world
+            return self.graphed(data, metax, mask, target)
         if self.reducer is not None:
             self.reducer.begin_step()
-        self.optimizer.zero_grad()
+        elif not getattr(self.model, '_fsdet_overwrites_grads', False):
+            self.optimizer.zero_grad()            # plain torch modules (the CPU tests' stub model) accumulate
         output = self.model(data, metax, mask)
         self.region_loss.seen = self.region_loss.seen + data.size(0) * self.world
         loss = self.region_loss(output, target)

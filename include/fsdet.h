@@ -126,6 +126,24 @@ size_t fsdet_conv_tc_wgrad_workspace_floats(int B, int H, int W, int Cin, int Co
 int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const void* dz_hi, const void* dz_lo, const float* amax_x,
                         const float* amax_dz, float* dw, float* workspace, size_t workspace_floats, int B, int H,
                         int W, int Cin, int Cout, int ksize, int mode, void* stream);
+/* All weight operands of a network for the tensor-core convolutions in two launches (csrc/weights.cu): absolute
+ * maxima, then the scaled fp16 (hi, lo) planes of every layer in the forward order [Cout][tap*fwd_pitch + ci] and -
+ * when bwd_hi != NULL - flip-transposed for the input-gradient GEMM [Cin][(kk-1-tap)*bwd_pitch + co].
+ * descs_dev: device array of n_layers descriptors; tiles_dev: device int32 pairs (layer, tile) with tile in
+ * [0, kk*tiles_co*tiles_ci) enumerating the 32x32 (Cout x Cin) tiles of every filter tap; amax_all: device float
+ * [n_layers] (desc.amax points into it).  The planes' channel padding (pitch > channels) is never written: allocate
+ * them zeroed once.  Replaces fsdet_amax + fsdet_split_f16 + fsdet_weight_flip_transpose + fsdet_split_f16 per layer. */
+typedef struct fsdet_weight_desc {
+    const float* w;      /* OHWI fp32 [Cout][kk][Cin] (torch channels_last storage of nn.Conv2d.weight) */
+    void* fwd_hi;        /* fp16 [Cout][kk*fwd_pitch] or NULL */
+    void* fwd_lo;
+    void* bwd_hi;        /* fp16 [Cin][kk*bwd_pitch] or NULL */
+    void* bwd_lo;
+    float* amax;         /* device scalar, written by the first pass */
+    int32_t Cout, kk, Cin, fwd_pitch, bwd_pitch, tiles_ci, tiles_co, reserved;
+} fsdet_weight_desc;
+int fsdet_weight_prep(const fsdet_weight_desc* descs_dev, const int32_t* tiles_dev, int n_tiles, float* amax_all,
+                      int n_layers, void* stream);
 /* absolute maximum of fp32 [rows][ld] (first C columns) -> *amax_out (device float) */
 int fsdet_amax(const float* src, int ld, int C, size_t rows, float* amax_out, void* stream);
 /* fp32 [rows][ld] (first C columns) -> two dense fp16 planes [rows][Cpad] of the

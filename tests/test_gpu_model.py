@@ -10,13 +10,15 @@ pytestmark = pytest.mark.gpu
 
 # Two arithmetic paths are tested (engine.USE_TC):
 #   'fp32' : exact-fp32 SIMT kernels (per-op rounding ~1e-7)  -> the strict bars below
-#   'tc'   : tcgen05 tensor-core kernels with scaled fp16 hi/lo operand splitting (measured per-op rounding
-#            1e-7..4e-6 vs 2e-7..2e-6 for the fp32 FMA kernels, tools/tc_precision.py).  Forward outputs and
-#            losses meet the same 1e-3 bar.  Gradients of these tiny synthetic problems are ill-conditioned
-#            (DESIGN.md "Parity"): every implementation's distance from a float64 evaluation is
-#            (condition number) x (its per-op rounding) + arg-max flips, so the tensor-core path is held to
-#            TC_GRAD_FACTOR x the distance of the float32 references instead of 2 x.
-TC_GRAD_FACTOR = 4.0
+#   'tc'   : tcgen05 tensor-core kernels, the shipped precision policy (engine.TC_TERMS): forward and input-gradient
+#            GEMMs with scaled fp16 hi/lo operand splitting (per-op rounding 1e-7..4e-6, like fp32 FMA kernels),
+#            weight-gradient GEMMs in plain fp16 x fp16 (measured 2e-4..6e-4 per tensor against the 3-term value at
+#            the real layer shapes, profiles/precision_budget_r02.log; it feeds SGD only and does not compound).
+#            Every mini-model tensor - output, loss, all 60 parameter gradients - meets the north star's 1e-3 on
+#            both paths.  Gradients of the FULL architecture on tiny batches are ill-conditioned in float32
+#            (DESIGN.md "Parity": torch's own cuDNN fp32 sits 1e-2 from float64), so there both paths are held to
+#            the same bar: max(1e-3, 3 x the distance of the float32 references).
+TC_GRAD_FACTOR = 3.0
 
 
 @pytest.fixture(params=['fp32', 'tc'])
@@ -76,7 +78,7 @@ def test_meta_mini_all_tensors_vs_reference(path):
         assert p.grad is not None, name
         e = rel(p.grad.detach().cpu().contiguous().numpy(), d['grad/' + name])
         worst = max(worst, e)
-        assert e < (TOL if path == 'fp32' else TC_GRAD_FACTOR * TOL), (name, e)
+        assert e < TOL, (name, e)
     with torch.no_grad():
         dw = m.meta_forward(metax, mask)
     assert rel(dw[0].cpu().numpy(), d['dynamic_weights_2nd_pass']) < TOL

@@ -4,14 +4,13 @@
     python tools/train_meta_b200.py datacfg darknetcfg learnetcfg weightfile            # one GPU
     torchrun --nproc-per-node 8 tools/train_meta_b200.py datacfg darknetcfg learnetcfg weightfile
 
-Base training from plain image-list files (`train = <list>` in the .data file, one image path per line; labels
-are found like listDataset.get_labpath) and a support dictionary (`meta = <file>` with `class list-file` lines).
-What the reference's script does beyond that - few-shot list construction for fine-tuning (dataset.build_dataset /
-build_fewset), the in-training test() pass - is not wired here; `fewshot_detection_b200.evaluate` / `valid` /
-`voc_eval` are the evaluation entry points.
-
-STATUS: written against tests/test_trainer_cpu.py (loop logic with a stub model) and the batcher tests; it has not
-been run end to end (no dataset in the build container, no GPU minutes left in round 1).
+The `.data` file drives everything as in the reference: `train` (image list or class dict), `meta` (support dict),
+`novel` / `novelid` (base / novel split), `neg`, `tuning` (+ `max_epoch`, `repeat`, `dynamic`) - the image list comes
+from lists.build_dataset, the support index from lists.support_index, the step from trainer.MetaTrainer (CUDA-graph
+replay, one graph per multi-scale input size).  Under torchrun every rank builds the same lists with the same seeds,
+takes its slice of each global batch, and rank 0's parameters are broadcast once before the first step.
+What the reference's script does beyond that - the in-training test() pass - is not wired here;
+`fewshot_detection_b200.evaluate` / `valid` / `voc_eval` are the evaluation entry points.
 """
 import os
 import sys
@@ -28,21 +27,19 @@ def read_list(path):
         return [l.rstrip() for l in f.readlines() if l.strip()]
 
 
-def read_metadict(path, classes):
-    """`class list-file` lines (MetaDataset.__init__, dataset.py:316-336) -> per-class image lists."""
-    pairs = {}
-    for line in read_list(path):
-        p = line.split()
-        if len(p) == 4:
-            p = [p[0] + ' ' + p[1], p[2] + ' ' + p[3]]
-        pairs[p[0]] = p[1]
-    return [read_list(pairs[c]) for c in classes]
-
-
-def meta_inds(metalines, nbatch):
-    """MetaDataset.inds for training (dataset.py:331-340): per class `nbatch` random picks, interleaved class by class."""
-    per_class = [list(zip([i] * nbatch, np.random.choice(range(len(lines)), nbatch).tolist())) for i, lines in enumerate(metalines)]
-    return sum(list(zip(*per_class)), ())
+def broadcast_parameters(model, src=0):
+    """Identical replicas: the gradient all-reduce keeps replicas in sync only if they START in sync.  A weight file
+    may initialise just the trunk (darknet19_448.conv.23 stops after 23 layers, darknet_meta.py:367-368), every other
+    tensor is per-process random - so rank `src`'s parameters and BN buffers are broadcast once."""
+    import torch.distributed as dist
+    with torch.no_grad():
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src)
+        chk = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+        ref = chk.clone()
+        dist.broadcast(ref, src)
+        if not torch.equal(chk, ref):
+            raise RuntimeError('replicas differ after the parameter broadcast')
 
 
 def main():
@@ -56,7 +53,7 @@ def main():
     from fewshot_detection_b200.optim import FusedSGD
     from fewshot_detection_b200.distributed import GradAllReducer
     from fewshot_detection_b200.dataset import DetectionBatcher, MetaBatcher
-    from fewshot_detection_b200 import trainer as T
+    from fewshot_detection_b200 import trainer as T, lists as LS
     import torch.distributed as dist
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -78,8 +75,13 @@ def main():
     scales = [float(s) for s in net_options['scales'].split(',')]
 
     model = Darknet(darknetcfg, learnetcfg)
-    model.load_weights(sys.argv[4])
+    if os.path.exists(sys.argv[4]):
+        model.load_weights(sys.argv[4])
+    else:
+        logging('weight file %s not found: training from the random initialisation' % sys.argv[4])
     model = model.cuda()
+    if world > 1:
+        broadcast_parameters(model)
     classes = cfg.base_classes
     factor = T.lr_factor(cfg.neg_ratio, len(classes))
     hp = T.sgd_hyper_parameters(float(net_options['learning_rate']), float(net_options['momentum']), float(net_options['decay']),
@@ -87,12 +89,15 @@ def main():
     optimizer = FusedSGD(model.parameters(), **hp)
     reducer = GradAllReducer(model) if world > 1 else None
 
-    trainlist = read_list(data_options['train'])
+    seed = int(os.environ.get('FSDET_SEED', str(int.from_bytes(os.urandom(4), 'little')) if world == 1 else '0'))
+    import random
+    random.seed(seed)                 # every rank must build the same lists and draw the same sizes
+    np.random.seed(seed % (2 ** 32))
+    trainlist = LS.build_dataset(data_options)
     nsamples = len(trainlist)
-    metalines = read_metadict(data_options['meta'], classes)
     processed, init_epoch, max_epochs = T.epoch_plan(model.seen, nsamples, batch_size, int(net_options['max_batches']),
                                                      cfg.tuning, cfg.get('max_epoch'), cfg.repeat)
-    backupdir = data_options.get('backup', 'backup')
+    backupdir = cfg.get('backup') or data_options.get('backup', 'backup')     # cfg.py:133-145 names it after the run's switches
     if rank == 0 and not os.path.exists(backupdir):
         os.makedirs(backupdir)
 
@@ -101,11 +106,13 @@ def main():
         lines = trainlist if world == 1 else \
             [trainlist[i] for b in range(0, nsamples - batch_size + 1, batch_size) for i in range(b + rank * per_rank, b + (rank + 1) * per_rank)]
         return DetectionBatcher(lines, shape=(model.width, model.height), shuffle=False, train=True, seen=seen,
-                                batch_size=per_rank, num_workers=int(data_options['num_workers']))
+                                batch_size=per_rank, seen_step=world)
 
     def make_meta_batcher():
-        nbatch = 500 * 64 // batch_size * (4 if cfg.get('data') == 'coco' else 1)
-        return MetaBatcher(metalines, meta_inds(metalines, nbatch), classes=classes, train=True)
+        cfg.num_gpus = 1              # one process per GPU: each rank draws its own n_cls support images per step
+        metalines, inds = LS.support_index(data_options['meta'], classes, LS.support_batches_per_epoch(train=True),
+                                           shuffle=cfg.randmeta)
+        return MetaBatcher(metalines, inds, classes=classes, train=True)
 
     tr = T.MetaTrainer(model, optimizer, float(net_options['learning_rate']) / factor, batch_size, steps, scales,
                        make_train_batcher, make_meta_batcher, backupdir=backupdir if rank == 0 else None,
