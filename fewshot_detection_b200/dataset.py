@@ -117,6 +117,11 @@ class DetectionBatcher(object):
         return _Entry(line[0], line[1])
 
     def batch(self, indices):
+        return self.finish(self.prepare(indices))
+
+    def prepare(self, indices):
+        """Host half of a batch (may run in a background thread while the GPU trains on the previous batch): the
+        random draws in the reference's order, file decode, label transforms.  Returns what finish() needs."""
         entries, params = [], []
         for index in indices:
             assert index <= len(self), 'index range error'
@@ -135,14 +140,22 @@ class DetectionBatcher(object):
         if len(shapes) != 1:
             raise ValueError('a batch must not straddle a multi-scale boundary (indices %r)' % (list(indices),))
         W, H = params[0]['shape']
-        data = I.augment_batch([e.pixels() for e in entries], (W, H), params, filter=self.filter)
+        pixels = [e.pixels() for e in entries]
         fill = I.fill_truth_detection_meta if cfg.metayolo else I.fill_truth_detection
         labels = [fill(e.label, W, H, p['flip'], p['dx'], p['dy'], 1. / p['sx'], 1. / p['sy']) for e, p in zip(entries, params)]
-        return data, torch.from_numpy(np.stack(labels))
+        return pixels, (W, H), params, torch.from_numpy(np.stack(labels))
+
+    def finish(self, prepared):
+        """Device half: one augmentation launch for the whole batch."""
+        pixels, shape, params, target = prepared
+        return I.augment_batch(pixels, shape, params, filter=self.filter), target
+
+    def batch_ranges(self):
+        return [range(start, start + self.batch_size) for start in range(0, self.nSamples - self.batch_size + 1, self.batch_size)]
 
     def __iter__(self):
-        for start in range(0, self.nSamples - self.batch_size + 1, self.batch_size):
-            yield self.batch(range(start, start + self.batch_size))
+        for r in self.batch_ranges():
+            yield self.batch(r)
 
 
 class MetaBatcher(object):
@@ -205,6 +218,10 @@ class MetaBatcher(object):
         return None
 
     def batch(self, indices):
+        return self.finish(self.prepare(indices))
+
+    def prepare(self, indices):
+        """Host half (draws, decode, label transforms); see DetectionBatcher.prepare."""
         chosen, clsids = [], []
         for index in indices:
             clsid, metaind = self.inds[index]
@@ -213,9 +230,13 @@ class MetaBatcher(object):
                 raise ValueError('support image (%d, %r) has no usable box (the reference returns (None, None))' % (clsid, metaind))
             chosen.append(r)
             clsids.append(clsid)
-        metax = I.augment_batch([e.pixels() for e, _, _ in chosen], self.meta_shape, [p for _, p, _ in chosen], filter=self.filter)
-        n = len(chosen)
-        rects = np.array([r for _, _, r in chosen], dtype=np.int32).reshape(n, 4)
+        return [e.pixels() for e, _, _ in chosen], [p for _, p, _ in chosen], [r for _, _, r in chosen], clsids
+
+    def finish(self, prepared):
+        pixels, params, rect_list, clsids = prepared
+        metax = I.augment_batch(pixels, self.meta_shape, params, filter=self.filter)
+        n = len(pixels)
+        rects = np.array(rect_list, dtype=np.int32).reshape(n, 4)
         w, h = self.mask_shape
         mask = torch.empty(n, 1, h, w, dtype=torch.float32, device=metax.device)
         I.call('fsdet_box_masks', I.ptr(torch.from_numpy(rects).to(metax.device)), n, h, w, I.ptr(mask), I._st())

@@ -72,6 +72,10 @@ class GraphedTrainStep(object):
         self.opt.sync_hyper()
         self.opt.prepare()
         sampled = cfg.neg_ratio != 'full'
+        if target.dim() == 3:
+            self.loss_mod.warm_caches(dev, target.size(0), target.size(1))
+        else:
+            self.loss_mod.warm_caches(dev)
         if sampled:
             rows = target.view(-1, target.size(-1)).size(0)
             bs = target.size(0) if target.dim() == 3 else 0

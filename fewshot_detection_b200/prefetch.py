@@ -120,3 +120,38 @@ class AsyncLossReader(object):
         while self.count:
             out.append(self.pop())
         return out
+
+
+class BackgroundPrep(object):
+    """Runs the HOST half of the input pipeline one batch ahead in a worker thread (what the reference's DataLoader
+    worker processes do, train_meta.py:173-193): `thunks` is an iterable of zero-argument callables, each returning one
+    prepared batch; iteration yields their results in order.  Exceptions of the worker surface at the consumer.  The
+    random draws happen inside the thunks, i.e. in one thread and in order - a seeded run stays reproducible."""
+
+    def __init__(self, thunks, depth=2):
+        import queue
+        import threading
+        self._q = queue.Queue(maxsize=depth)
+        self._done = object()
+
+        def work():
+            try:
+                for t in thunks:
+                    self._q.put((True, t()))
+                self._q.put((True, self._done))
+            except BaseException as e:      # hand the failure to the consumer instead of dying silently
+                self._q.put((False, e))
+        self._thread = threading.Thread(target=work, daemon=True)
+        self._thread.start()
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        ok, item = self._q.get()
+        if not ok:
+            raise item
+        if item is self._done:
+            self._q.put((True, self._done))
+            raise StopIteration
+        return item

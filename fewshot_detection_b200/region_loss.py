@@ -161,6 +161,18 @@ class _RegionBase(nn.Module):
             self._raise_if_degenerate(self._pending[0])
 
     # -- CUDA-graph form -------------------------------------------------------------------------------------------
+    def warm_caches(self, device, bs=0, cs=0):
+        """Upload the small constants a call needs (anchors, the per-image row prefix of the unsampled loss) NOW: a
+        host -> device copy of pageable memory is not allowed inside a CUDA-graph capture."""
+        key = (str(device), tuple(float(a) for a in self.anchors))
+        if getattr(self, '_anchor_cache', (None,))[0] != key:
+            self._anchor_cache = (key, torch.tensor(key[1], dtype=torch.float32).to(device),
+                                  torch.tensor(key[1], dtype=torch.float64).to(device))
+        if bs:
+            ikey = (str(device), tuple(range(0, bs * cs + 1, cs)))
+            if getattr(self, '_img_cache', (None,))[0] != ikey:
+                self._img_cache = (ikey, torch.tensor(ikey[1], dtype=torch.int32).to(device))
+
     def make_static(self, rows_total, bs, device):
         """Allocate the fixed-capacity buffers a captured step reads: [0] = number of live rows, [1 : bs+2] = per-image
         prefix of the kept rows (V2), [bs+2 :] = kept row indices.  The kernels are launched for `rows_total` slots and
@@ -232,10 +244,7 @@ class _RegionBase(nn.Module):
             else:
                 tgt_rows = target2d[torch.as_tensor(inds, dtype=torch.long)]
             tgt = _to_device_f64(tgt_rows, dev)
-        key = (str(dev), tuple(float(a) for a in self.anchors))
-        if getattr(self, '_anchor_cache', (None,))[0] != key:   # small constants are uploaded once (CUDA-graph friendly)
-            self._anchor_cache = (key, torch.tensor(key[1], dtype=torch.float32).to(dev),
-                                  torch.tensor(key[1], dtype=torch.float64).to(dev))
+        self.warm_caches(dev)                 # small constants are uploaded once (CUDA-graph friendly)
         anc32, anc64 = self._anchor_cache[1], self._anchor_cache[2]
         pred = torch.empty(max(nB, 1) * nA * nH * nW, 4, device=dev)
         call('fsdet_region_decode', ptr(out_c), ptr(inds_t), nB, ptr(nb_dev), nA, nC, nH, nW, ptr(anc32), ptr(pred), st)

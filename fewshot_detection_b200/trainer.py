@@ -122,8 +122,17 @@ class MetaTrainer(object):
         self.model.train()
         n_meta = meta.batch_size
         nb = 0
-        for nb, (data, target) in enumerate(batcher, 1):
-            metax, mask = meta.batch(range((nb - 1) * n_meta, nb * n_meta))[:2]
+        if hasattr(batcher, 'prepare') and hasattr(meta, 'prepare'):
+            # host half (draws, file decode, labels) of batch i+1 in a worker thread while the GPU runs step i
+            from .prefetch import BackgroundPrep
+            ranges = batcher.batch_ranges()
+            prep = BackgroundPrep((lambda i=i, r=r: (batcher.prepare(r), meta.prepare(range(i * n_meta, (i + 1) * n_meta))))
+                                  for i, r in enumerate(ranges))
+            stream = ((batcher.finish(q), meta.finish(s)) for q, s in prep)
+        else:
+            stream = (((data, target), meta.batch(range(i * n_meta, (i + 1) * n_meta))) for i, (data, target) in enumerate(batcher))
+        for nb, ((data, target), support) in enumerate(stream, 1):
+            metax, mask = support[:2]
             self.adjust_learning_rate(self.processed_batches)
             self.processed_batches = self.processed_batches + 1
             loss = self.train_step(data, metax, mask, target)
