@@ -78,7 +78,8 @@ class MetaTrainer(object):
         self.log = log
         self.losses = collections.deque(maxlen=100)   # detached loss tensors of the most recent steps (no host sync)
         if use_graph is None:
-            use_graph = any(p.is_cuda for p in model.parameters())
+            import os
+            use_graph = any(p.is_cuda for p in model.parameters()) and os.environ.get('FSDET_NO_GRAPH', '0') != '1'
         self.graphed = None
         if use_graph:
             from .distributed import GradAllReducer

@@ -235,14 +235,18 @@ def test_tiny_mini_train_step_vs_oracle(path):
 
 def test_train_steps_match_oracle_sgd(path):
     """Three full meta-training steps (forward, RegionLossV2, backward, FusedSGD) against the oracle +
-    torch.optim.SGD on the CPU. Parameters are compared with a float64 run of the oracle as ground truth
-    (bar: 1e-3, or twice the float32 oracle's own distance where float32 cannot do better)."""
+    torch.optim.SGD on the CPU, float64 run of the oracle as ground truth.  The learning rate is the driver's
+    order of magnitude for this batch (train_meta.py:143-147 divides by batch size and lr factor): at 1e-3 on a
+    summed loss of ~200 every step moves the weights by O(1) and the trajectory is chaotic - a 5e-4 gradient
+    difference becomes a 5 % loss difference two steps later, whatever the arithmetic.  Compared: the losses
+    (1e-3) and the parameter UPDATE p - p0 (relative L2 per tensor; p itself would match trivially)."""
     from fewshot_detection_b200 import netcfg
     from fewshot_detection_b200.optim import FusedSGD
     from oracle import darknet as ODK, region_loss as ORL
     from seeding import seeded_init, synth_targets, synth_masks
     det, ler = netcfg.mini_dynamic_blocks(128, 4), netcfg.mini_reweighting_blocks(64, 4, 128)
     bs, cs = 4, 3
+    LR = 2e-5
 
     def batch(it):
         g = torch.Generator().manual_seed(100 + it)
@@ -254,7 +258,8 @@ def test_train_steps_match_oracle_sgd(path):
         om = ODK.MetaDarknet([dict(b) for b in det], [dict(b) for b in ler])
         seeded_init(om, 11)
         om = om.to(dtype).train()
-        oo = torch.optim.SGD(om.parameters(), lr=1e-3, momentum=0.9, dampening=0, weight_decay=5e-4)
+        p0 = {n: p.detach().double().clone() for n, p in om.named_parameters()}
+        oo = torch.optim.SGD(om.parameters(), lr=LR, momentum=0.9, dampening=0, weight_decay=5e-4)
         losses = []
         for it in range(3):
             x, metax, mask, tgt = batch(it)
@@ -266,12 +271,13 @@ def test_train_steps_match_oracle_sgd(path):
             out.backward(o32.grad.to(dtype))
             oo.step()
             losses.append(lo.item())
-        return losses, {n: p.detach().double() for n, p in om.named_parameters()}
+        return losses, {n: p.detach().double() - p0[n] for n, p in om.named_parameters()}
 
-    l64, p64 = run_oracle(torch.float64)
-    l32, p32 = run_oracle(torch.float32)
+    l64, d64 = run_oracle(torch.float64)
+    l32, d32 = run_oracle(torch.float32)
     m = _meta(det, ler, 11)
-    og = FusedSGD(m.parameters(), lr=1e-3, momentum=0.9, dampening=0, weight_decay=5e-4)
+    p0 = {n: p.detach().double().cpu().contiguous().clone() for n, p in m.named_parameters()}
+    og = FusedSGD(m.parameters(), lr=LR, momentum=0.9, dampening=0, weight_decay=5e-4)
     L = m.models[len(m.models) - 1]
     L.verbose = False
     for it in range(3):
@@ -282,11 +288,15 @@ def test_train_steps_match_oracle_sgd(path):
         lg.backward()
         og.step()
         assert abs(lg.item() - l64[it]) < TOL * abs(l64[it]), it
+    worst = 0.0
     for n, p in m.named_parameters():
-        # compare the parameter *update* (p - p0 is what training computes); p itself trivially matches
-        e_ours = relt(p.detach().cpu().contiguous(), p64[n])
-        e_ref = relt(p32[n], p64[n])
-        assert e_ours < max(TOL, (2 if path == 'fp32' else TC_GRAD_FACTOR) * e_ref), (n, e_ours, e_ref)
+        upd = p.detach().double().cpu().contiguous() - p0[n]
+        e_ours = relt(upd, d64[n])
+        e_ref = relt(d32[n], d64[n])
+        worst = max(worst, e_ours)
+        # fp32 kernels: like the float32 oracle; shipped policy: + the fp16 x fp16 weight gradient (<= 6e-4 per step)
+        assert e_ours < max(TOL if path == 'fp32' else 2 * TOL, 3 * e_ref), (n, e_ours, e_ref)
+    print('worst update error', worst)
 
 
 def test_weight_file_roundtrip(tmp_path):

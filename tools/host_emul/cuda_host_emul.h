@@ -133,8 +133,8 @@ inline void launch(dim3 grid, dim3 block, size_t dyn_smem, const std::function<v
         const int n = (w + 1) * 32 <= nthreads ? 32 : nthreads - w * 32;
         pthread_barrier_init(&g_block.warp_bar[w], nullptr, n);
     }
-    std::vector<unsigned char> smem(dyn_smem + 64);
-    g_dyn_smem = (unsigned char*)(((uintptr_t)smem.data() + 63) & ~(uintptr_t)63);
+    std::vector<unsigned char> smem(dyn_smem + 1024);     // 1 KB aligned like the device's swizzled operand tiles want
+    g_dyn_smem = (unsigned char*)(((uintptr_t)smem.data() + 1023) & ~(uintptr_t)1023);
     std::vector<std::thread> ts;
     for (int t = 0; t < nthreads; ++t)
         ts.emplace_back([&, t]() {
