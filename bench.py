@@ -265,6 +265,9 @@ def main():
     dev = torch.device('cuda', local)
     import torch.distributed as dist
     if world > 1:
+        if rank == 0:      # communicator / algorithm lines (NVLS, rings, trees) of rank 0 on stderr
+            os.environ.setdefault('NCCL_DEBUG', 'INFO')
+            os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT,GRAPH,TUNING')
         dist.init_process_group('nccl', device_id=dev)
     import __graft_entry__
     if rank == 0:

@@ -327,7 +327,7 @@ __device__ __forceinline__ void bwd_block_reduce(const double* red, double* dst,
 // REDUCE writes per CTA row [sum(du) | sum(du*xhat) | max|du|] (3C doubles).
 // APPLY writes dz as fp32 and/or directly as the scaled fp16 (hi, lo) planes the tensor-core GEMMs read.
 template <bool APPLY>
-__global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_kernel(const BwdArgs a) {
     const int H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1, Hp = a.H >> 1, Wp = a.W >> 1;
     const int C4 = a.C >> 2;
     const int TC = blockDim.x;          // channel-vector lanes
@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_kernel(const Bw
 // touches one element per window and channel, and the apply pass needs the activation derivative only there.
 // Same arithmetic as the general kernel (the zero terms are dropped), a fraction of the instructions.
 template <bool APPLY>
-__global__ void __launch_bounds__(256, APPLY ? 2 : 3) bn_act_bwd_pool_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_pool_kernel(const BwdArgs a) {
     const int H2 = (a.H + 1) >> 1, W2 = (a.W + 1) >> 1, Hp = a.H >> 1, Wp = a.W >> 1;
     const int C4 = a.C >> 2;
     const int TC = blockDim.x;          // channel-vector lanes
@@ -665,7 +665,10 @@ extern "C" int fsdet_bn_act_fwd(const float* z, int ldz, const float* scale, con
     } else {
         long long nwin = (long long)B * ((H + 1) / 2) * ((W + 1) / 2);
         if (nwin == 0) return 0;
-        const int TC = CP4 >= 32 ? 32 : (CP4 >= 16 ? 16 : (CP4 >= 8 ? 8 : (CP4 >= 4 ? 4 : (CP4 >= 2 ? 2 : 1))));
+        // channel-vector lanes sized by the REAL channels: the zero padding of the planes (pitch > C) is written by the
+        // same threads in a second trip of their channel loop instead of by threads that never load anything
+        const int C4 = C / 4;
+        const int TC = C4 >= 32 ? 32 : (C4 >= 16 ? 16 : (C4 >= 8 ? 8 : (C4 >= 4 ? 4 : (C4 >= 2 ? 2 : 1))));
         const int TY = 256 / TC;
         dim3 block(TC, TY), grid((unsigned)ceil_div(nwin, TY));
         if (a.yf || a.fh) bn_act_pool_kernel<true><<<grid, block, 0, s>>>(a);

@@ -88,7 +88,7 @@ extern "C" int fsdet_conv_first_tc_apply(const float* in0, int C0, const float* 
     FSDET_CHECK_ARG(scale && shift && (y_pool || pool_hi), "conv_first_tc_apply: null pointer");
     FSDET_CHECK_ARG(!pool_hi || (pool_lo && amax_y && cpad >= 32 && cpad % 32 == 0 && aligned16(pool_hi) && aligned16(pool_lo)),
                     "conv_first_tc_apply: planes need lo, amax and a pitch that is a multiple of 32 (got %d)", cpad);
-    FSDET_CHECK_ARG(!y_pool || (ld_pool % 4 == 0 && ld_pool >= 32 && aligned16(y_pool)), "conv_first_tc_apply: fp32 output ld=%d", ld_pool);
+    FSDET_CHECK_ARG(!y_pool || (ld_pool % 4 == 0 && ld_pool >= Cout && aligned16(y_pool)), "conv_first_tc_apply: fp32 output ld=%d", ld_pool);
     if (a.tiles == 0) return 0;
     a.scale = scale; a.shift = shift; a.slope = slope; a.yp = y_pool; a.ldp = ld_pool; a.ph = pool_hi; a.pl = pool_lo; a.cpad = cpad;
     a.amax_y = amax_y;

@@ -315,19 +315,17 @@ __global__ void __launch_bounds__(FT_THREADS, 2) conv_first_tc_kernel(const FtAr
                     for (int c = 0; c < 32; ++c)                      // select with constant indices (no local memory)
                         if ((c >> 3) == wq) o[c & 7] = z[c];
                     const int c0 = 8 * wq;
-                    if (p.yp && c0 < p.Cout) {
+                    if (p.yp && c0 < p.Cout) {          // Cout % 4 == 0
                         *reinterpret_cast<float4*>(p.yp + pp * p.ldp + c0) = make_float4(o[0], o[1], o[2], o[3]);
-                        *reinterpret_cast<float4*>(p.yp + pp * p.ldp + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                        if (c0 + 4 < p.Cout) *reinterpret_cast<float4*>(p.yp + pp * p.ldp + c0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
                     }
                     if (p.ph) {
                         uint4 hi, lo;
                         ft_split8(o, psc, hi, lo);
                         __half* ph = reinterpret_cast<__half*>(p.ph) + pp * p.cpad;
                         __half* pl = reinterpret_cast<__half*>(p.pl) + pp * p.cpad;
-                        if (c0 < p.Cout) {
-                            *reinterpret_cast<uint4*>(ph + c0) = hi;
-                            *reinterpret_cast<uint4*>(pl + c0) = lo;
-                        }
+                        *reinterpret_cast<uint4*>(ph + c0) = hi;      // channels >= Cout are exact zeros (zero weights / scale)
+                        *reinterpret_cast<uint4*>(pl + c0) = lo;
                         for (int cz = 32 + c0; cz < p.cpad; cz += 32) {   // zero padding channels of the planes
                             *reinterpret_cast<uint4*>(ph + cz) = make_uint4(0, 0, 0, 0);
                             *reinterpret_cast<uint4*>(pl + cz) = make_uint4(0, 0, 0, 0);

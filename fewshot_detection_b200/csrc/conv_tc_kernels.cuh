@@ -92,7 +92,12 @@ __device__ __forceinline__ void tc_kahan_add(float& s, float& e, float x) {
     s = t;
 }
 
-template <int BN, int BK, int NH, int TERMS, bool PERSIST, int MINB>
+// CLUSTER = 2 (one-tile-per-CTA flavours only): two CTAs of a thread-block cluster work on two M tiles of the SAME
+// channel range; each loads its own activation tiles and only HALF of the weight tile, multicast into both CTAs'
+// shared memory - the weight operand crosses the L2 -> SM fabric once per pair instead of once per CTA (the 128 x 128
+// tiles of the 3-term scheme run at the L2 bandwidth limit on the mid-resolution layers).  A stage may be refilled
+// once BOTH CTAs' MMAs have consumed it (its empty barrier counts the two multicast commits).
+template <int BN, int BK, int NH, int TERMS, bool PERSIST, int MINB, int CLUSTER = 1>
 __global__ void __launch_bounds__(192, MINB)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
@@ -113,9 +118,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int kchunks = p.Cin / BK;
     const int nk = p.ks * p.ks * kchunks;
+    static_assert(CLUSTER == 1 || (CLUSTER == 2 && !PERSIST), "the cluster flavour is one tile per CTA");
     const int tiles_n = p.tiles_n;
     const int tiles_total = p.tiles_total;
     const int tile_step = PERSIST ? (int)gridDim.x : tiles_total;   // non-persistent: exactly one tile per CTA
+    // CLUSTER == 2: CTAs 2c and 2c+1 take M tiles 2m and 2m+1 of channel range n (gridDim.x = 2 * tiles_n * ceil(tiles_m / 2))
+    const uint32_t crank = CLUSTER == 2 ? cluster_ctarank() : 0u;
+    const int first_tile = CLUSTER == 2 ? (((int)(blockIdx.x >> 1) / tiles_n) * 2 + (int)crank) * tiles_n + (int)(blockIdx.x >> 1) % tiles_n
+                                        : (int)blockIdx.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmAhi);
@@ -125,7 +135,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         tma_prefetch_desc(&tmZ);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CLUSTER);
         }
         for (int a = 0; a < NSETS; ++a) {
             mbar_init(&acc_full[a], 1);
@@ -136,6 +146,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)Cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER == 2) cluster_sync_all();                      // the peer's barriers exist before anything remote touches them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -143,7 +154,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         if (lane == 0) {
             const int HW = p.H * p.W;
             unsigned it = 0;                                   // k-blocks issued so far (all tiles)
-            for (int tile = blockIdx.x; tile < tiles_total; tile += tile_step) {
+            for (int tile = first_tile; tile < tiles_total; tile += tile_step) {
                 const int n_tile = tile % tiles_n;
                 const long long m0 = (long long)(tile / tiles_n) * TC_BM;
                 const int img = (int)(m0 / HW);
@@ -161,8 +172,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                     if (TERMS & 1)
                         tma_load_im2col_4d(st + Cfg::OFF_ALO, &tmAlo, &full_bar[s], c0, pw - p.pad, ph - p.pad, img, (uint16_t)sx,
                                            (uint16_t)r);
-                    tma_load_2d(st + Cfg::OFF_BHI, &tmBhi, &full_bar[s], tap * p.cpitch + c0, n_tile * BN);
-                    if (TERMS & 2) tma_load_2d(st + Cfg::OFF_BLO, &tmBlo, &full_bar[s], tap * p.cpitch + c0, n_tile * BN);
+                    if (CLUSTER == 2) {       // my half of the weight rows, delivered to both CTAs of the pair
+                        const int half = (int)crank * (BN / 2);
+                        tma_load_2d_mc(st + Cfg::OFF_BHI + half * Cfg::ROW_BYTES, &tmBhi, &full_bar[s], tap * p.cpitch + c0,
+                                       n_tile * BN + half, (uint16_t)3);
+                        if (TERMS & 2)
+                            tma_load_2d_mc(st + Cfg::OFF_BLO + half * Cfg::ROW_BYTES, &tmBlo, &full_bar[s], tap * p.cpitch + c0,
+                                           n_tile * BN + half, (uint16_t)3);
+                    } else {
+                        tma_load_2d(st + Cfg::OFF_BHI, &tmBhi, &full_bar[s], tap * p.cpitch + c0, n_tile * BN);
+                        if (TERMS & 2) tma_load_2d(st + Cfg::OFF_BLO, &tmBlo, &full_bar[s], tap * p.cpitch + c0, n_tile * BN);
+                    }
                 }
             }
         }
@@ -172,7 +192,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             unsigned it = 0;
             unsigned t = 0;                                    // tiles done by this CTA
-            for (int tile = blockIdx.x; tile < tiles_total; tile += tile_step, ++t) {
+            for (int tile = first_tile; tile < tiles_total; tile += tile_step, ++t) {
                 const unsigned a = t % NSETS;
                 mbar_wait(&acc_empty[a], ((t / NSETS) & 1u) ^ 1u);    // the epilogue has drained this accumulator set
                 tc_fence_after();
@@ -200,7 +220,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                         if (TERMS & 1) { umma_f16(dlo, alo + adv, bhi + adv, idesc, lo_started); lo_started = 1u; }
                         if (TERMS & 2) { umma_f16(dlo, ahi + adv, blo + adv, idesc, lo_started); lo_started = 1u; }
                     }
-                    umma_commit(&empty_bar[s]);   // frees the smem slot when these MMAs have read it
+                    if (CLUSTER == 2) umma_commit_mc(&empty_bar[s], (uint16_t)3);   // both producers write into this CTA's slot
+                    else umma_commit(&empty_bar[s]);   // frees the smem slot when these MMAs have read it
                 }
                 umma_commit(&acc_full[a]);        // accumulator set complete
             }
@@ -216,7 +237,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) { ssum[c] = esum[c] = ssq[c] = esq[c] = 0.f; smin[c] = INFINITY; smax[c] = -INFINITY; }
         unsigned t = 0, stores = 0;                            // tiles done, TMA stores issued by this warp
-        for (int tile = blockIdx.x; tile < tiles_total; tile += tile_step, ++t) {
+        for (int tile = first_tile; tile < tiles_total; tile += tile_step, ++t) {
             const unsigned a = t % NSETS;
             const int n_tile = tile % tiles_n;
             const long long m0 = (long long)(tile / tiles_n) * TC_BM;
@@ -293,8 +314,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 sbuf[quarter * BN + ch * 32 + lane] = make_float4(ssum[ch] - esum[ch], ssq[ch] - esq[ch], smin[ch], smax[ch]);
             named_bar_sync(1, 128);
             const int e = (warp - 2) * 32 + lane;
-            const int n_tile = (int)(blockIdx.x % (unsigned)tiles_n);
-            const long long row = (long long)(blockIdx.x / (unsigned)tiles_n);
+            const int n_tile = CLUSTER == 2 ? first_tile % tiles_n : (int)(blockIdx.x % (unsigned)tiles_n);
+            const long long row = CLUSTER == 2 ? (long long)(first_tile / tiles_n) : (long long)(blockIdx.x / (unsigned)tiles_n);
             for (int c = e; c < BN; c += 128) {
                 float4 tt = sbuf[c];
 #pragma unroll
@@ -312,6 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER == 2) cluster_sync_all();                      // no CTA leaves while its peer may still signal its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)Cfg::TMEM_COLS);

@@ -19,7 +19,9 @@ import os
 
 # tensor-core (tcgen05) convolution path for layers with Cin % 64 == 0; FSDET_TC=0 selects the exact-fp32 SIMT kernels
 USE_TC = os.environ.get('FSDET_TC', '1') != '0'
-TC_PARTS = set(os.environ.get('FSDET_TC_PARTS', 'fwd,dgrad,wgrad,head,first').split(','))  # debugging: which GEMMs may use it
+# 'first' = the recomputing first-block kernels (csrc/conv_first_tc.cuh): correct but, as measured on a B200, slower than the
+# store-z path they were meant to replace (instruction-bound epilogues) - opt-in only
+TC_PARTS = set(os.environ.get('FSDET_TC_PARTS', 'fwd,dgrad,wgrad,head').split(','))  # debugging: which GEMMs may use it
 
 
 def _parse_terms(spec):

@@ -38,7 +38,7 @@ class _Entry(object):
 
 
 class GraphedTrainStep(object):
-    def __init__(self, model, region_loss, optimizer, reducer=None, max_graphs=12):
+    def __init__(self, model, region_loss, optimizer, reducer=None, max_graphs=12, strict=True):
         self.model, self.loss_mod, self.opt = model, region_loss, optimizer
         self.reducer = reducer if reducer is not None else GradAllReducer(model)
         self.entries = collections.OrderedDict()       # key -> _Entry (LRU)
@@ -48,6 +48,12 @@ class GraphedTrainStep(object):
         self.captures = 0
         self._chk = None                               # (pinned counters, event, armed): degenerate-label check, one step late
         self.in_graph_allreduce = None                 # None = try to capture the collective, False = known not to work
+        # 'thread_local': other host threads (the input pipeline's background preparation, pinned-memory bookkeeping)
+        # may keep calling CUDA while this thread captures - the default 'global' mode turns any such call into a
+        # capture error
+        self.capture_error_mode = 'thread_local'
+        self.strict = strict                           # False: fall back to eager launches if a capture fails
+        self.capture_failed = None
 
     # ------------------------------------------------------------------ eager (very first step)
     def _eager(self, x, metax, mask, target):
@@ -107,13 +113,13 @@ class GraphedTrainStep(object):
         pool = self.pool
         try:
             try:
-                with torch.cuda.graph(e.graph_fb, pool=pool):
+                with torch.cuda.graph(e.graph_fb, pool=pool, capture_error_mode=self.capture_error_mode):
                     body(with_opt=not two_graphs, overlap=multi and not two_graphs)
                 if two_graphs:
                     if self.pool is None:
                         self.pool = e.graph_fb.pool()
                     e.graph_opt = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(e.graph_opt, pool=self.pool):
+                    with torch.cuda.graph(e.graph_opt, pool=self.pool, capture_error_mode=self.capture_error_mode):
                         self.opt.step()
             except Exception as err:      # NCCL not capturable here: one exposed all-reduce between two graphs
                 if not multi or self.in_graph_allreduce is False:
@@ -123,12 +129,12 @@ class GraphedTrainStep(object):
                 self.in_graph_allreduce = False
                 torch.cuda.synchronize()
                 e.graph_fb = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(e.graph_fb, pool=pool):
+                with torch.cuda.graph(e.graph_fb, pool=pool, capture_error_mode=self.capture_error_mode):
                     body(with_opt=False, overlap=False)
                 if self.pool is None:
                     self.pool = e.graph_fb.pool()
                 e.graph_opt = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(e.graph_opt, pool=self.pool):
+                with torch.cuda.graph(e.graph_opt, pool=self.pool, capture_error_mode=self.capture_error_mode):
                     self.opt.step()
         finally:
             self.loss_mod.static = None
@@ -176,10 +182,24 @@ class GraphedTrainStep(object):
         the row sampling - pass it as `target_host` when `target` is a device tensor."""
         if not any('momentum_buffer' in self.opt.state[p] for g in self.opt.param_groups for p in g['params']):
             return self._eager(x, metax, mask, target)      # the very first step runs eagerly
+        if self.capture_failed is not None:
+            return self._eager(x, metax, mask, target)
         key = self._key(x, metax, target)
         e = self.entries.get(key)
         if e is None:
-            e = self._capture(key, x, metax, mask, target)
+            try:
+                e = self._capture(key, x, metax, mask, target)
+            except Exception as err:
+                if self.strict:
+                    raise
+                # a failed capture must not take the training run down: report it once and launch eagerly from now on
+                import sys
+                import traceback
+                self.capture_failed = err
+                sys.stderr.write('GraphedTrainStep: CUDA-graph capture failed, continuing with eager launches:\n%s\n'
+                                 % ''.join(traceback.format_exception_only(type(err), err)))
+                torch.cuda.synchronize()
+                return self._eager(x, metax, mask, target)
         else:
             self.entries.move_to_end(key)
         for s, t in zip(e.static, (x, metax, mask, target)):

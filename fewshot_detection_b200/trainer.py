@@ -86,7 +86,7 @@ class MetaTrainer(object):
             from .graph import GraphedTrainStep
             if self.reducer is None:
                 self.reducer = GradAllReducer(model)      # flat gradient buffer: in-place all-reduce and fused SGD
-            self.graphed = GraphedTrainStep(model, self.region_loss, optimizer, self.reducer)
+            self.graphed = GraphedTrainStep(model, self.region_loss, optimizer, self.reducer, strict=False)
 
     def adjust_learning_rate(self, batch):
         lr = learning_rate_at(batch, self.learning_rate, self.steps, self.scales)
@@ -123,7 +123,8 @@ class MetaTrainer(object):
         self.model.train()
         n_meta = meta.batch_size
         nb = 0
-        if hasattr(batcher, 'prepare') and hasattr(meta, 'prepare'):
+        import os
+        if hasattr(batcher, 'prepare') and hasattr(meta, 'prepare') and os.environ.get('FSDET_NO_BG_PREP', '0') != '1':
             # host half (draws, file decode, labels) of batch i+1 in a worker thread while the GPU runs step i
             from .prefetch import BackgroundPrep
             ranges = batcher.batch_ranges()

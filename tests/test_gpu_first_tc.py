@@ -99,3 +99,44 @@ def test_first_block_passes_vs_torch(B, C0, C1, H, W, Cout):
     if C < 4:
         assert dw4[:, :, C:].abs().max().item() < 1e-3 * ref_w.abs().max().item()
     print('first block: dW rel err %.2e' % e)
+
+
+def test_model_with_recomputing_first_block_matches_default_path():
+    """The opt-in first-block path ('first' in engine.TC_PARTS) through the public API: same output, loss and
+    parameter gradients as the default path (which stores the first layer's pre-BN tensor)."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden'))
+    from fewshot_detection_b200 import netcfg, engine
+    from fewshot_detection_b200.darknet_meta import Darknet
+    from seeding import seeded_init, synth_targets, synth_masks
+    det, ler = netcfg.mini_dynamic_blocks(128, 8), netcfg.mini_reweighting_blocks(64, 8, 256)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(3, 3, 128, 128, generator=g).cuda()
+    metax = torch.rand(2, 3, 64, 64, generator=g).cuda()
+    mask = torch.from_numpy(synth_masks(2, 64, 6)).cuda()
+    tgt = torch.from_numpy(synth_targets(3, 2, 7, max_gt=3))
+    runs = []
+    had = 'first' in engine.TC_PARTS
+    try:
+        for first in (False, True):
+            (engine.TC_PARTS.add if first else engine.TC_PARTS.discard)('first')
+            m = Darknet([dict(b) for b in det], [dict(b) for b in ler])
+            seeded_init(m, 4)
+            m = m.cuda().train()
+            L = m.models[len(m.models) - 1]
+            L.verbose = False
+            L.seen = 20000
+            out = m(x, metax, mask)
+            loss = L(out, tgt)
+            loss.backward()
+            runs.append((out.detach().clone(), loss.item(), {n: p.grad.detach().clone() for n, p in m.named_parameters()},
+                         {n: b.detach().clone() for n, b in m.named_buffers() if 'running' in n}))
+    finally:
+        (engine.TC_PARTS.add if had else engine.TC_PARTS.discard)('first')
+    (o0, l0, g0, b0), (o1, l1, g1, b1) = runs
+    assert rel(o1, o0) < 1e-5 and abs(l1 - l0) < 1e-5 * abs(l0)
+    for n in g0:
+        assert rel(g1[n], g0[n]) < (1e-3 if n.endswith('conv1.weight') else 2e-4), n     # conv1: dz rounded to fp16 in the new path
+    for n in b0:
+        assert rel(b1[n], b0[n]) < 1e-5, n

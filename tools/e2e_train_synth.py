@@ -110,8 +110,25 @@ def main():
         marks.append((nb, time.time() - t0))
         return nb
     T.MetaTrainer.train_epoch = timed_epoch
-    sys.argv = ['train_meta_b200.py', os.path.join(root, 'meta.data'), os.path.join(root, 'dyn.cfg'), os.path.join(root, 'rw.cfg'),
-                os.path.join(root, 'no_such.weights')]
+    # initial weights: the reference starts from a pretrained trunk; a purely random detector emits box sizes e^N(0, s)
+    # that blow the w/h loss up within a few steps.  Write a Darknet weight file (exercises save_weights / load_weights)
+    # whose head convolution is scaled down so that training starts from near-zero box offsets.
+    wfile = os.path.join(root, 'init.weights')
+    if rank == 0 and not os.path.exists(wfile):
+        import torch
+        from fewshot_detection_b200.darknet_meta import Darknet
+        torch.manual_seed(0)
+        m0 = Darknet(det, netcfg.reweighting_net_blocks())
+        head = [mod for mod in m0.models if isinstance(mod, torch.nn.Sequential)][-1][0]
+        with torch.no_grad():
+            head.weight.mul_(0.02)
+            head.bias.zero_()
+        m0.save_weights(wfile + '.tmp')
+        os.replace(wfile + '.tmp', wfile)
+        del m0
+    while not os.path.exists(wfile):
+        time.sleep(1)
+    sys.argv = ['train_meta_b200.py', os.path.join(root, 'meta.data'), os.path.join(root, 'dyn.cfg'), os.path.join(root, 'rw.cfg'), wfile]
     os.environ.setdefault('FSDET_SEED', '1')
     from fewshot_detection_b200.cfg import cfg as _cfg
     _cfg.save_interval = 2          # write a weight file inside a 3-epoch run (the default of 10 never would)
