@@ -275,7 +275,7 @@ def main():
     if world > 1:
         dist.barrier()
     from fewshot_detection_b200 import netcfg, _lib, engine as _engine
-    engine_terms = dict(_engine.TC_TERMS, persist=_engine.TC_PERSIST)
+    engine_terms = dict(_engine.TC_TERMS, persist=_engine.TC_PERSIST, cluster=_engine.TC_CLUSTER)
     from fewshot_detection_b200.cfg import cfg
     from fewshot_detection_b200.darknet_meta import Darknet
     from fewshot_detection_b200.optim import FusedSGD

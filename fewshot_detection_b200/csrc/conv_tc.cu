@@ -439,8 +439,8 @@ static int make_tiled_map(CUtensorMap* map, const void* base, long long rows, lo
 //   mode bits 0-1 = TERMS (operand precision, see conv_tc_kernels.cuh), bit 4 = persistent tile loop (short-K only)
 struct TcPlan {
     int bn, bk, nh, terms;
-    bool persist;
-    int tiles_n, tiles_m, grid;
+    bool persist, cluster;
+    int tiles_n, tiles_m, grid;      // tiles_m counts the padding tile of an odd tile count in cluster mode
 };
 
 static TcPlan tc_plan(long long M, int Cin, int Cout, int ksize, int mode) {
@@ -453,6 +453,8 @@ static TcPlan tc_plan(long long M, int Cin, int Cout, int ksize, int mode) {
     pl.persist = small_k && (mode & 16);
     pl.tiles_n = ceil_div(Cout, pl.bn);
     pl.tiles_m = ceil_div(M, TC_BM);
+    pl.cluster = (mode & 32) && !pl.persist && pl.tiles_m >= 2;
+    if (pl.cluster) pl.tiles_m = (pl.tiles_m + 1) / 2 * 2;      // CTA pairs: an odd tail gets an all-padding partner
     const long long total = (long long)pl.tiles_n * pl.tiles_m;
     if (pl.persist) {
         long long g = total < kNumSMs ? total : kNumSMs;
@@ -466,8 +468,36 @@ static TcPlan tc_plan(long long M, int Cin, int Cout, int ksize, int mode) {
 
 template <int BN, int BK, int NH, int TERMS, bool PERSIST, int MINB>
 static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                     const CUtensorMap& zmap, const TcArgs& a, int grid, cudaStream_t s) {
+                     const CUtensorMap& zmap, const TcArgs& a, int grid, bool cluster, cudaStream_t s) {
     using Cfg = TcCfg<BN, BK, NH, TERMS, PERSIST, MINB>;
+    if constexpr (!PERSIST) {
+        if (cluster) {      // CTA pairs sharing the weight tile (TMA multicast)
+            auto kern = conv_tc_kernel<BN, BK, NH, TERMS, false, MINB, 2>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+            if (e != cudaSuccess) {
+                set_error("conv_tc(cluster): cudaFuncSetAttribute(%d bytes): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+                return (int)e;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)grid);
+            cfg.blockDim = dim3(192);
+            cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, b_hi, b_lo, zmap, a);
+            if (e != cudaSuccess) {
+                set_error("conv_tc(cluster): launch: %s", cudaGetErrorString(e));
+                return (int)e;
+            }
+            return launch_status("conv_tc(cluster)");
+        }
+    }
     auto kern = conv_tc_kernel<BN, BK, NH, TERMS, PERSIST, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -480,12 +510,12 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
 
 template <int BN, int BK, int NH, bool PERSIST, int MINB>
 static int launch_tc_terms(int terms, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
-                           const CUtensorMap& b_lo, const CUtensorMap& zmap, const TcArgs& a, int grid, cudaStream_t s) {
+                           const CUtensorMap& b_lo, const CUtensorMap& zmap, const TcArgs& a, int grid, bool cluster, cudaStream_t s) {
     switch (terms) {
-        case 0: return launch_tc<BN, BK, 1, 0, PERSIST, MINB>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, s);
-        case 1: return launch_tc<BN, BK, 1, 1, PERSIST, MINB>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, s);
-        case 2: return launch_tc<BN, BK, 1, 2, PERSIST, MINB>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, s);
-        default: return launch_tc<BN, BK, NH, 3, PERSIST, MINB>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, s);
+        case 0: return launch_tc<BN, BK, 1, 0, PERSIST, MINB>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, cluster, s);
+        case 1: return launch_tc<BN, BK, 1, 1, PERSIST, MINB>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, cluster, s);
+        case 2: return launch_tc<BN, BK, 1, 2, PERSIST, MINB>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, cluster, s);
+        default: return launch_tc<BN, BK, NH, 3, PERSIST, MINB>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, cluster, s);
     }
 }
 
@@ -500,11 +530,12 @@ static int run_tc(const void* x_hi, const void* x_lo, const void* w_hi, const vo
         if (rc) return rc;
     }
     const long long K = (long long)a.ks * a.ks * a.cpitch;
-    rc = make_tiled_map(&b_hi, w_hi, a.Cout, K, pl.bn, pl.bk);
+    const int b_rows = pl.cluster ? pl.bn / 2 : pl.bn;      // cluster mode: each CTA of a pair loads half of the weight rows
+    rc = make_tiled_map(&b_hi, w_hi, a.Cout, K, b_rows, pl.bk);
     if (rc) return rc;
     b_lo = b_hi;
     if (pl.terms & 2) {
-        rc = make_tiled_map(&b_lo, w_lo, a.Cout, K, pl.bn, pl.bk);
+        rc = make_tiled_map(&b_lo, w_lo, a.Cout, K, b_rows, pl.bk);
         if (rc) return rc;
     }
     CUtensorMap zmap;   // fp32 output [M][ldz] (first Cout columns): 32 x 32 boxes, 128-byte swizzle
@@ -524,16 +555,17 @@ static int run_tc(const void* x_hi, const void* x_lo, const void* w_hi, const vo
     a.tiles_n = pl.tiles_n;
     a.tiles_total = pl.tiles_n * pl.tiles_m;
     const int t = pl.terms;
+    const bool cl = pl.cluster;
     if (pl.bk == 32) {
         if (pl.persist) {
-            if (pl.bn == 128) return launch_tc_terms<128, 32, 1, true, 1>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, s);
-            return launch_tc_terms<64, 32, 1, true, 1>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, s);
+            if (pl.bn == 128) return launch_tc_terms<128, 32, 1, true, 1>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, false, s);
+            return launch_tc_terms<64, 32, 1, true, 1>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, false, s);
         }
-        if (pl.bn == 128) return launch_tc_terms<128, 32, 1, false, 2>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, s);
-        return launch_tc_terms<64, 32, 1, false, 2>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, s);
+        if (pl.bn == 128) return launch_tc_terms<128, 32, 1, false, 2>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, cl, s);
+        return launch_tc_terms<64, 32, 1, false, 2>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, cl, s);
     }
-    if (pl.bn == 128) return launch_tc_terms<128, 64, NHI, false, 1>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, s);
-    return launch_tc_terms<64, 64, NHI, false, 1>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, s);
+    if (pl.bn == 128) return launch_tc_terms<128, 64, NHI, false, 1>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, cl, s);
+    return launch_tc_terms<64, 64, NHI, false, 1>(t, a_hi, a_lo, b_hi, b_lo, zmap, a, pl.grid, cl, s);
 }
 
 }  // namespace fsdet
@@ -611,7 +643,7 @@ extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void*
                                  const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin, int cpitch, int Cout,
                                  int ksize, int accumulate, int mode, float* stat_partial, void* stream) {
     const int terms = mode & 3;
-    FSDET_CHECK_ARG((mode & ~0x13) == 0, "conv_tc_fwd: unknown mode bits 0x%x", mode);
+    FSDET_CHECK_ARG((mode & ~0x33) == 0, "conv_tc_fwd: unknown mode bits 0x%x", mode);
     FSDET_CHECK_ARG(x_hi && w_hi && z && (!(terms & 1) || x_lo) && (!(terms & 2) || w_lo), "conv_tc_fwd: null pointer (mode %d)", mode);
     FSDET_CHECK_ARG(fsdet_conv_tc_supported(Cin, Cout, ksize) && cpitch >= Cin && cpitch % 8 == 0,
                     "conv_tc_fwd: unsupported Cin=%d (pitch %d) Cout=%d k=%d", Cin, cpitch, Cout, ksize);

@@ -46,8 +46,12 @@ TC_TERMS = _parse_terms(os.environ.get('FSDET_TC_TERMS'))
 TC_PERSIST = os.environ.get('FSDET_TC_PERSIST', '0') == '1'
 
 
+# thread-block clusters of two CTAs sharing the weight tile through TMA multicast (one-tile-per-CTA flavours)
+TC_CLUSTER = os.environ.get('FSDET_TC_CLUSTER', '0') == '1'
+
+
 def tc_mode(name):
-    return TC_TERMS[name] | (16 if TC_PERSIST else 0)
+    return TC_TERMS[name] | (16 if TC_PERSIST else 0) | (32 if TC_CLUSTER else 0)
 
 LEAKY_SLOPE = 0.1
 BN_EPS = 1e-5
@@ -617,7 +621,7 @@ class NetRunner(object):
             assert cout_p == s.cout, 'BatchNorm conv with Cout % 4 != 0 is unsupported'
             z = Act.new(B, H, W, s.cout, dev)
             use_batch_stats = training or not bn.track_running_stats
-            rows_cap = max(_lib.lib.fsdet_conv_stat_rows(npix), _lib.lib.fsdet_colstats_rows(npix), (npix + 127) // 128)
+            rows_cap = max(_lib.lib.fsdet_conv_stat_rows(npix), _lib.lib.fsdet_colstats_rows(npix), (npix + 127) // 128 + 1)
             stat = _empty(rows_cap + _lib.lib.fsdet_bn_stat_scratch_rows(), 4 * s.cout, device=dev) if use_batch_stats else None
             wp = getattr(self, '_wp', {}).get(id(wuse))
             rows = self._conv('fwd', x, wuse, None, z, stat, cin_p, s.cout, s.k, 0, st, wplanes=wp['fwd'] if wp else None)

@@ -77,8 +77,8 @@ class MetaTrainer(object):
         self.region_loss.seen = model.seen           # train_meta.py:93
         self.log = log
         self.losses = collections.deque(maxlen=100)   # detached loss tensors of the most recent steps (no host sync)
+        import os
         if use_graph is None:
-            import os
             use_graph = any(p.is_cuda for p in model.parameters()) and os.environ.get('FSDET_NO_GRAPH', '0') != '1'
         self.graphed = None
         if use_graph:
@@ -86,7 +86,8 @@ class MetaTrainer(object):
             from .graph import GraphedTrainStep
             if self.reducer is None:
                 self.reducer = GradAllReducer(model)      # flat gradient buffer: in-place all-reduce and fused SGD
-            self.graphed = GraphedTrainStep(model, self.region_loss, optimizer, self.reducer, strict=False)
+            self.graphed = GraphedTrainStep(model, self.region_loss, optimizer, self.reducer,
+                                            strict=os.environ.get('FSDET_STRICT_CAPTURE', '0') == '1')
 
     def adjust_learning_rate(self, batch):
         lr = learning_rate_at(batch, self.learning_rate, self.steps, self.scales)

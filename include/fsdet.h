@@ -128,7 +128,9 @@ int fsdet_pad_channels(const float* in, int cin, float* out, int cout, size_t ro
  *     3 = fp32-grade (reproduces the fp32 reference incl. its max-pool arg-max
  *     decisions), 0 = plain fp16 x fp16 -> fp32.  Planes that are not used may be
  *     NULL.  Bit 4 (16): persistent tile loop for short-K layers (one CTA per
- *     SM, double-buffered TMEM accumulators).
+ *     SM, double-buffered TMEM accumulators).  Bit 5 (32): thread-block clusters
+ *     of two CTAs that share the weight tile through TMA multicast (ignored in
+ *     persistent mode and for single-tile problems).
  * x_hi/x_lo dense NHWC [B*H*W][cpitch] fp16, w_hi/w_lo [Cout][k*k*cpitch] fp16,
  * amax_x / amax_w: device floats holding the tensors' absolute maxima (NULL =
  * planes are unscaled).  Output fp32 z[p][n] (+ previous z when accumulate

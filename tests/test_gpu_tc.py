@@ -107,7 +107,8 @@ def planes_nchw(t, B, H, W, C):
 
 
 # mode = operand terms (bits 0-1) | 16 for the persistent tile loop (short-K layers only; ignored by the others)
-MODES = [3, 3 | 16, 0, 0 | 16, 1, 2]
+#        | 32 for CTA pairs sharing the weight tile through TMA multicast (one-tile-per-CTA flavours)
+MODES = [3, 3 | 16, 0, 0 | 16, 1, 2, 3 | 32, 0 | 32, 2 | 32]
 
 
 @pytest.mark.parametrize('mode', MODES)

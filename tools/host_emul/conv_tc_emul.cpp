@@ -205,6 +205,12 @@ static inline void named_bar_sync(int id, int nthreads) {
     }
 }
 
+// thread-block clusters are not modelled (blocks run one after another): the cluster flavour is never instantiated here
+static inline uint32_t cluster_ctarank() { return 0; }
+static inline void cluster_sync_all() {}
+static inline void tma_load_2d_mc(void*, const CUtensorMap*, uint64_t*, int, int, uint16_t) { g_deadlock.store(true); }
+static inline void umma_commit_mc(uint64_t*, uint16_t) { g_deadlock.store(true); }
+
 #include "../../fewshot_detection_b200/csrc/conv_tc_kernels.cuh"
 static_assert(EMUL_BM == TC_BM, "tile height of the models");
 
