@@ -73,6 +73,9 @@ class _Entry(object):
     def size(self):
         if self._arr is not None:
             return int(self._arr.shape[1]), int(self._arr.shape[0])
+        hit = I._CACHE.get(self.item)
+        if hit is not None:
+            return int(hit.shape[1]), int(hit.shape[0])
         from PIL import Image
         with Image.open(self.item) as im:
             return im.size
@@ -140,7 +143,7 @@ class DetectionBatcher(object):
         if len(shapes) != 1:
             raise ValueError('a batch must not straddle a multi-scale boundary (indices %r)' % (list(indices),))
         W, H = params[0]['shape']
-        pixels = [e.pixels() for e in entries]
+        pixels = I.PackedImages(I.decode_many([e.item if e._arr is None else e._arr for e in entries]))
         fill = I.fill_truth_detection_meta if cfg.metayolo else I.fill_truth_detection
         labels = [fill(e.label, W, H, p['flip'], p['dx'], p['dy'], 1. / p['sx'], 1. / p['sy']) for e, p in zip(entries, params)]
         return pixels, (W, H), params, torch.from_numpy(np.stack(labels))
@@ -230,7 +233,8 @@ class MetaBatcher(object):
                 raise ValueError('support image (%d, %r) has no usable box (the reference returns (None, None))' % (clsid, metaind))
             chosen.append(r)
             clsids.append(clsid)
-        return [e.pixels() for e, _, _ in chosen], [p for _, p, _ in chosen], [r for _, _, r in chosen], clsids
+        pixels = I.PackedImages(I.decode_many([e.item if e._arr is None else e._arr for e, _, _ in chosen]))
+        return pixels, [p for _, p, _ in chosen], [r for _, _, r in chosen], clsids
 
     def finish(self, prepared):
         pixels, params, rect_list, clsids = prepared

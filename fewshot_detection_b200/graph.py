@@ -63,7 +63,10 @@ class GraphedTrainStep(object):
         loss.backward()
         self.reducer.finish()
         self.opt.step()
-        return loss
+        # detached: a loss that still references its autograd graph keeps the parameters' AccumulateGrad nodes alive,
+        # and those remember the stream they were created on - a later capture on another stream would then make the
+        # autograd engine wait on uncaptured work (cudaErrorStreamCaptureIsolation)
+        return loss.detach()
 
     # ------------------------------------------------------------------ capture
     def _key(self, x, metax, target):
@@ -101,8 +104,9 @@ class GraphedTrainStep(object):
             self.reducer.overlap = overlap
             self.reducer.begin_step()
             out = self.model(*e.static[:3])
-            e.loss = self.loss_mod(out, e.static[3])
-            e.loss.backward()
+            loss = self.loss_mod(out, e.static[3])
+            loss.backward()
+            e.loss = loss.detach()
             if overlap:
                 self.reducer.finish()          # join: the capturing stream waits for the bucket all-reduces
             if with_opt:
