@@ -594,7 +594,7 @@ constexpr int kBnSplits = 64;
 static int bwd_rows(int B, int H, int W) {
     long long nwin = (long long)B * ((H + 1) / 2) * ((W + 1) / 2);
     long long r = (nwin + 63) / 64;
-    if (r > 8 * kNumSMs) r = 8 * kNumSMs;
+    if (r > 6 * kNumSMs) r = 6 * kNumSMs;   // whole waves of the 3 resident CTAs per SM (8 x would leave a 2/3-empty third wave)
     if (r < 1) r = 1;
     return (int)r;
 }

@@ -143,10 +143,15 @@ class DetectionBatcher(object):
         if len(shapes) != 1:
             raise ValueError('a batch must not straddle a multi-scale boundary (indices %r)' % (list(indices),))
         W, H = params[0]['shape']
-        pixels = I.PackedImages(I.decode_many([e.item if e._arr is None else e._arr for e in entries]))
+        pixels = I.PackedImages(I.decode_many([e.item if e._arr is None else e._arr for e in entries])).marshal(params, W, H)
         fill = I.fill_truth_detection_meta if cfg.metayolo else I.fill_truth_detection
         labels = [fill(e.label, W, H, p['flip'], p['dx'], p['dy'], 1. / p['sx'], 1. / p['sy']) for e, p in zip(entries, params)]
-        return pixels, (W, H), params, torch.from_numpy(np.stack(labels))
+        target = torch.from_numpy(np.stack(labels))
+        try:
+            target = target.pin_memory()          # the step uploads it asynchronously
+        except RuntimeError:
+            pass
+        return pixels, (W, H), params, target
 
     def finish(self, prepared):
         """Device half: one augmentation launch for the whole batch."""
@@ -234,16 +239,21 @@ class MetaBatcher(object):
             chosen.append(r)
             clsids.append(clsid)
         pixels = I.PackedImages(I.decode_many([e.item if e._arr is None else e._arr for e, _, _ in chosen]))
-        return pixels, [p for _, p, _ in chosen], [r for _, _, r in chosen], clsids
+        pixels.marshal([p for _, p, _ in chosen], self.meta_shape[0], self.meta_shape[1])
+        rects = torch.from_numpy(np.array([r for _, _, r in chosen], dtype=np.int32).reshape(len(chosen), 4))
+        try:
+            rects = rects.pin_memory()
+        except RuntimeError:
+            pass
+        return pixels, [p for _, p, _ in chosen], rects, clsids
 
     def finish(self, prepared):
-        pixels, params, rect_list, clsids = prepared
+        pixels, params, rects, clsids = prepared
         metax = I.augment_batch(pixels, self.meta_shape, params, filter=self.filter)
         n = len(pixels)
-        rects = np.array(rect_list, dtype=np.int32).reshape(n, 4)
         w, h = self.mask_shape
         mask = torch.empty(n, 1, h, w, dtype=torch.float32, device=metax.device)
-        I.call('fsdet_box_masks', I.ptr(torch.from_numpy(rects).to(metax.device)), n, h, w, I.ptr(mask), I._st())
+        I.call('fsdet_box_masks', I.ptr(rects.to(metax.device, non_blocking=True)), n, h, w, I.ptr(mask), I._st())
         if self.with_ids:
             return metax, mask, clsids
         return metax, mask

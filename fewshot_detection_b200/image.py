@@ -105,12 +105,28 @@ class PackedImages(object):
             flat[o:o + a.size] = a.reshape(-1)
         self.buf = buf
 
+        self.tables = None
+
     def __len__(self):
         return len(self.shapes)
 
     def to_device(self, device):
         d = self.buf.to(device, non_blocking=True)
         return [d[o:o + h * w * 3].view(h, w, 3) for o, (h, w, _) in zip(self.offsets, self.shapes)]
+
+    def marshal(self, params, W, H):
+        """Build the per-image argument tables of the augmentation launch NOW (host side, possibly in the background
+        thread), in pinned memory, so that the device half of the batch issues only asynchronous copies."""
+        geom, color, kmax = marshal_params([(h, w) for h, w, _ in self.shapes], params, W, H)
+
+        def pin(t):
+            try:
+                return t.pin_memory()
+            except RuntimeError:
+                return t
+        self.tables = (pin(torch.from_numpy(geom)), pin(torch.from_numpy(color)), kmax, pin(torch.empty(len(self.shapes), dtype=torch.int64)),
+                       (int(W), int(H)))
+        return self
 
 
 def _as_u8_hwc(img, device):
@@ -160,10 +176,19 @@ def augment_batch(images, shape, params, filter=None, device=None, out=None, ret
     n = len(images)
     assert len(params) == n
     srcs = images.to_device(device) if isinstance(images, PackedImages) else [_as_u8_hwc(im, device) for im in images]
-    geom, color, kmax = marshal_params([(int(s.size(0)), int(s.size(1))) for s in srcs], params, W, H)
-    ptrs = torch.tensor([s.data_ptr() for s in srcs], dtype=torch.int64).to(device)
-    geom_d = torch.from_numpy(geom).to(device)
-    color_d = torch.from_numpy(color).to(device)
+    if isinstance(images, PackedImages) and images.tables is not None and images.tables[4] == (W, H):
+        # tables prepared on the host side in pinned memory: nothing here blocks the launching thread
+        geom_h, color_h, kmax, ptr_h, _ = images.tables
+        for i, s_ in enumerate(srcs):
+            ptr_h[i] = s_.data_ptr()
+        ptrs = ptr_h.to(device, non_blocking=True)
+        geom_d = geom_h.to(device, non_blocking=True)
+        color_d = color_h.to(device, non_blocking=True)
+    else:
+        geom, color, kmax = marshal_params([(int(s.size(0)), int(s.size(1))) for s in srcs], params, W, H)
+        ptrs = torch.tensor([s.data_ptr() for s in srcs], dtype=torch.int64).to(device)
+        geom_d = torch.from_numpy(geom).to(device)
+        color_d = torch.from_numpy(color).to(device)
     ws_bytes = int(lib.fsdet_augment_workspace_bytes(n, W, H, kmax))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=device)
     status = torch.zeros(1, dtype=torch.int32, device=device)
@@ -193,9 +218,17 @@ def data_augmentation(img, shape, jitter, hue, saturation, exposure, flag=True, 
 def _load_boxes(lab):
     """`np.loadtxt(labpath)` reshaped to [-1, 5] (image.py:94-98), or an array passed directly."""
     if isinstance(lab, str):
-        if not (os.path.exists(lab) and os.path.getsize(lab)):
+        hit = _LABELS.get(lab)
+        if hit is None:
+            if not (os.path.exists(lab) and os.path.getsize(lab)):
+                hit = False
+            else:
+                hit = np.reshape(np.loadtxt(lab), (-1, 5))
+            if len(_LABELS) < 1000000:
+                _LABELS[lab] = hit                  # label files are parsed once per process
+        if hit is False:
             return None
-        bs = np.loadtxt(lab)
+        bs = hit.copy()                             # callers transform the rows in place
     else:
         bs = np.array(lab, dtype=np.float64)
         if bs.size == 0:
@@ -322,6 +355,7 @@ def _decode(img):
 
 
 _POOL = [None]
+_LABELS = {}
 
 
 def decode_many(items):
