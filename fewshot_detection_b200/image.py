@@ -95,11 +95,10 @@ class PackedImages(object):
         for a in arrays:
             self.offsets.append(total)
             total += (a.size + 255) // 256 * 256             # 256-byte aligned starts
-        buf = torch.empty(max(total, 1), dtype=torch.uint8)
         try:
-            buf = buf.pin_memory()
+            buf = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
         except RuntimeError:
-            pass
+            buf = torch.empty(max(total, 1), dtype=torch.uint8)
         flat = buf.numpy()
         for a, o in zip(arrays, self.offsets):
             flat[o:o + a.size] = a.reshape(-1)

@@ -134,10 +134,16 @@ class BackgroundPrep(object):
         self._q = queue.Queue(maxsize=depth)
         self._done = object()
 
+        self.busy_s = 0.0      # time the worker spent preparing (diagnostics)
+
         def work():
+            import time as _t
             try:
                 for t in thunks:
-                    self._q.put((True, t()))
+                    t0 = _t.time()
+                    item = t()
+                    self.busy_s += _t.time() - t0
+                    self._q.put((True, item))
                 self._q.put((True, self._done))
             except BaseException as e:      # hand the failure to the consumer instead of dying silently
                 self._q.put((False, e))

@@ -132,14 +132,28 @@ class MetaTrainer(object):
             prep = BackgroundPrep((lambda i=i, r=r: (batcher.prepare(r), meta.prepare(range(i * n_meta, (i + 1) * n_meta))))
                                   for i, r in enumerate(ranges))
             stream = ((batcher.finish(q), meta.finish(s)) for q, s in prep)
+            self._prep = prep
         else:
             stream = (((data, target), meta.batch(range(i * n_meta, (i + 1) * n_meta))) for i, (data, target) in enumerate(batcher))
+        prof = os.environ.get('FSDET_TRAIN_PROFILE', '0') == '1'
+        t_wait = t_step = 0.0
+        tp = time.time()
         for nb, ((data, target), support) in enumerate(stream, 1):
             metax, mask = support[:2]
+            if prof:
+                t_wait += time.time() - tp
+                tp = time.time()
             self.adjust_learning_rate(self.processed_batches)
             self.processed_batches = self.processed_batches + 1
             loss = self.train_step(data, metax, mask, target)
             self.losses.append(loss.detach())
+            if prof:
+                t_step += time.time() - tp
+                tp = time.time()
+        if prof and nb:
+            self.log('host time per step: %.1f ms waiting for / finishing the input batch, %.1f ms launching the step, '
+                     'background preparation %.1f ms per batch'
+                     % (1e3 * t_wait / nb, 1e3 * t_step / nb, 1e3 * getattr(getattr(self, '_prep', None), 'busy_s', 0.0) / nb))
         dt = time.time() - t0
         self.log('training with %f samples/s' % (len(batcher) * self.world / max(dt, 1e-9)))
         if self.backupdir is not None and (epoch + 1) % self.save_interval == 0:
