@@ -252,6 +252,28 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def teardown(dist, holders):
+    """Leave the process group without hanging: CUDA graphs that captured NCCL work must be destroyed BEFORE their
+    communicator, and a watchdog ends the process if the teardown itself stalls (the JSON line is already out)."""
+    import gc
+    sys.stdout.flush()
+    sys.stderr.flush()
+    wd = threading.Timer(30.0, lambda: os._exit(0))
+    wd.daemon = True
+    wd.start()
+    try:
+        for h in holders:
+            if h is not None and hasattr(h, 'entries'):
+                h.entries.clear()
+        holders.clear()
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+    except Exception as e:
+        sys.stderr.write('destroy_process_group: %r\n' % (e,))
+    wd.cancel()
+
+
 def main():
     args = parse()
     if args.impl == 'reference':
@@ -265,9 +287,10 @@ def main():
     dev = torch.device('cuda', local)
     import torch.distributed as dist
     if world > 1:
-        if rank == 0:      # communicator / algorithm lines (NVLS, rings, trees) of rank 0 on stderr
+        if rank == 0:      # communicator / algorithm lines (NVLS, rings, trees) of rank 0 - on STDERR: stdout carries the JSON line
             os.environ.setdefault('NCCL_DEBUG', 'INFO')
             os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT,GRAPH,TUNING')
+            os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     import __graft_entry__
     if rank == 0:
@@ -502,7 +525,7 @@ def main():
             cfg.neg_ratio = 'full'
             torch.cuda.empty_cache()
 
-    if graphed is not None and not os.environ.get('FSDET_BENCH_NO_EXTRAS'):
+    if graphed is not None and world == 1 and not os.environ.get('FSDET_BENCH_NO_EXTRAS'):
         extra_line('neg1', B, ncls, side, 1, max(4, args.steps // 2))
         extra_line('eager', B, ncls, side, 'full', 3, graph=False)
         extra_line('configs3', B, 20, 416, 0, max(4, args.steps // 2))
@@ -590,10 +613,7 @@ def main():
 
     if rank != 0:
         if world > 1:
-            try:
-                dist.destroy_process_group()
-            except Exception as e:
-                sys.stderr.write('destroy_process_group: %r\n' % (e,))
+            teardown(dist, [graphed])
         return
 
     cpu_baseline = None
@@ -657,10 +677,7 @@ def main():
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
-        try:
-            dist.destroy_process_group()
-        except Exception as e:
-            sys.stderr.write('destroy_process_group: %r\n' % (e,))
+        teardown(dist, [graphed])
 
 
 if __name__ == '__main__':

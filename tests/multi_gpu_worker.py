@@ -95,6 +95,9 @@ def main():
         if graph:
             sys.stderr.write('rank %d: in-graph all-reduce %s, %d capture(s)\n' % (rank, 'fell back to two graphs' if gs.in_graph_allreduce is False else 'captured', gs.captures))
         runs.append((losses, torch.cat([p.detach().reshape(-1) for p in m.parameters()])))
+        if graph:
+            gs.entries.clear()      # graphs that captured NCCL work must be gone before their communicator is destroyed
+            del gs
     (l0, p0), (l1, p1) = runs
     for a, b in zip(l0, l1):
         assert abs(a - b) <= 1e-5 * abs(a), (l0, l1)
@@ -103,8 +106,16 @@ def main():
     dist.broadcast(ref, 0)
     assert torch.equal(ref, p1), 'replicas diverged'
     dist.barrier()
-    print('MULTI_OK rank %d all-reduce err %.1e' % (rank, e))
+    print('MULTI_OK rank %d all-reduce err %.1e' % (rank, e), flush=True)
+    import gc
+    import threading
+    gc.collect()
+    torch.cuda.synchronize()
+    wd = threading.Timer(30.0, lambda: os._exit(0))      # never let a stalled teardown hang the test
+    wd.daemon = True
+    wd.start()
     dist.destroy_process_group()
+    wd.cancel()
 
 
 if __name__ == '__main__':

@@ -16,5 +16,5 @@ def test_two_rank_allreduce_equals_sum_of_shards_and_graph_step_matches_eager():
         pytest.skip('needs 2 GPUs')
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
            '--master-port', '29611', os.path.join(ROOT, 'tests', 'multi_gpu_worker.py')]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
     assert r.returncode == 0 and r.stdout.count('MULTI_OK') == 2, r.stdout[-4000:]

@@ -121,6 +121,11 @@ def main():
     model.loss.verbose = rank == 0
     tr.fit(init_epoch, max_epochs)
     if world > 1:
+        if tr.graphed is not None:
+            tr.graphed.entries.clear()      # graphs that captured NCCL work go before their communicator
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
     return 0
 
