@@ -249,7 +249,29 @@ def run_reference(args):
         'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Point fd 1 at stderr for the whole run and keep the original for the JSON line: NCCL's version / INFO lines,
+    the reference-style 'class_scale' print and anything a library writes to stdout would otherwise sit beside the
+    one line the driver parses."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + '\n').encode()
+    fd = _JSON_FD if _JSON_FD is not None else 1
+    while data:
+        data = data[os.write(fd, data):]
 
 
 def teardown(dist, holders):
@@ -276,6 +298,7 @@ def teardown(dist, holders):
 
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == 'reference':
         return run_reference(args)
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -288,9 +311,9 @@ def main():
     import torch.distributed as dist
     if world > 1:
         if rank == 0:      # communicator / algorithm lines (NVLS, rings, trees) of rank 0 - on STDERR: stdout carries the JSON line
-            os.environ.setdefault('NCCL_DEBUG', 'INFO')
-            os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT,GRAPH,TUNING')
-            os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+            if not os.environ.get('FSDET_NCCL_QUIET'):
+                os.environ['NCCL_DEBUG'] = 'INFO'
+                os.environ.setdefault('NCCL_DEBUG_SUBSYS', 'INIT,GRAPH,TUNING')
         dist.init_process_group('nccl', device_id=dev)
     import __graft_entry__
     if rank == 0:
@@ -674,8 +697,7 @@ def main():
                           'cpu_rows': ncls, 'note': 'decode + threshold 0.005 + NMS 0.45 of all (image, class) rows; the CPU '
                                                     'figure is the oracle port on the first image only (n_cls rows)'},
     }
-    print(json.dumps(line))
-    sys.stdout.flush()
+    emit(line)
     if world > 1:
         teardown(dist, [graphed])
 
