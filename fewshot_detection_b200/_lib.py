@@ -40,6 +40,7 @@ SIGNATURES = {
     'fsdet_pad_channels': ('pipizp', 'i'),
     'fsdet_conv_tc_supported': ('iii', 'i'),
     'fsdet_conv_tc_stat_rows': ('iiiiiii', 'i'),
+    'fsdet_conv_tc_uses_halo': ('iiiiiii', 'i'),
     'fsdet_conv_tc_fwd': ('pppppppiiiiiiiiiipp', 'i'),
     'fsdet_conv_tc_wgrad_supported': ('iii', 'i'),
     'fsdet_conv_tc_wgrad_workspace_floats': ('iiiiiii', 'z'),

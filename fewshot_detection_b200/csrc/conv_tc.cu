@@ -125,6 +125,7 @@ constexpr int TC_BK = 64;                       // halves per 128-byte row (im2c
 constexpr int TC_A_BYTES = 128 * TC_BK * 2;     // 16 KB per plane
 
 #include "conv_tc_kernels.cuh"   // inside namespace fsdet
+#include "conv_halo_kernels.cuh" // halo-tile flavour of the high-resolution 3x3 layers
 
 // ------------------------------------------------------------------ weight gradient
 //   dw[co][tap][ci] = sum_p dz[p][co] * x[p + tap][ci]
@@ -441,11 +442,38 @@ struct TcPlan {
     int bn, bk, nh, terms;
     bool persist, cluster;
     int tiles_n, tiles_m, grid;      // tiles_m counts the padding tile of an odd tile count in cluster mode
+    bool halo;                       // halo-tile kernel (conv_halo_kernels.cuh): 8 x 16 pixel tiles, persistent grid
+    int tiles_x, tiles_y;
 };
 
-static TcPlan tc_plan(long long M, int Cin, int Cout, int ksize, int mode) {
+// The halo-tile kernel takes the 3x3 layers whose input tile is worth keeping in shared memory: 3-term arithmetic, at most
+// 128 input and output channels (short K: the im2col kernel is L2-bound there), a width that tiles by 8, little padding
+// waste in the 16-row direction and enough tiles to fill the persistent grid.  mode bit 6 switches it off.
+static bool halo_ok(int B, int H, int W, int Cin, int Cout, int ksize, int mode) {
+    if (ksize != 3 || (mode & 3) != 3 || (mode & 0x70)) return false;
+    if (!(Cin == 32 || Cin == 64 || Cin == 128) || Cout > 128) return false;
+    if (W % HALO_TW != 0) return false;
+    const int ty = ceil_div(H, HALO_TH);
+    if ((long long)ty * HALO_TH * 10 > (long long)H * 11) return false;          // more than 10 % of the MMA rows would be padding
+    return (long long)B * ty * (W / HALO_TW) >= 2LL * kNumSMs;
+}
+
+static TcPlan tc_plan(long long M, int Cin, int Cout, int ksize, int mode, int B = 0, int H = 0, int W = 0) {
     TcPlan pl;
     pl.terms = mode & 3;
+    pl.halo = B > 0 && halo_ok(B, H, W, Cin, Cout, ksize, mode);
+    pl.tiles_x = pl.tiles_y = 0;
+    if (pl.halo) {
+        pl.bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
+        pl.bk = 32; pl.nh = 1; pl.persist = true; pl.cluster = false;
+        pl.tiles_n = 1;
+        pl.tiles_x = W / HALO_TW;
+        pl.tiles_y = ceil_div(H, HALO_TH);
+        const long long total = (long long)B * pl.tiles_x * pl.tiles_y;
+        pl.tiles_m = (int)total;
+        pl.grid = (int)(total < kNumSMs ? total : kNumSMs);
+        return pl;
+    }
     const bool small_k = (Cin % 64 != 0) || (ksize * ksize * Cin <= 2304);
     pl.bn = Cout >= 128 ? 128 : 64;
     pl.bk = small_k ? 32 : 64;
@@ -519,8 +547,90 @@ static int launch_tc_terms(int terms, const CUtensorMap& a_hi, const CUtensorMap
     }
 }
 
+// ---- halo-tile flavour: tensor maps and launch
+// activation plane [B][H][W][cpitch] fp16 -> tiled 4-D map, box = (32 channels, 8 x, 18 y) with zero fill outside
+static int make_halo_act_map(CUtensorMap* map, const void* base, int B, int H, int W, int C, int cpitch) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)W * cpitch * 2, (cuuint64_t)H * W * cpitch * 2};
+    cuuint32_t box[4] = {32, (cuuint32_t)HALO_TW, (cuuint32_t)(HALO_TH + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = driver_fns().encodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("conv_halo: activation tensor map failed (%d) B=%d H=%d W=%d C=%d pitch=%d", (int)r, B, H, W, C, cpitch);
+        return -3;
+    }
+    return 0;
+}
+
+// fp32 output [B][H][W][ldz] (first Cout channels): boxes of (32 channels, 8 x, 4 y), 128-byte swizzle
+static int make_halo_out_map(CUtensorMap* map, float* z, int B, int H, int W, int Cout, int ldz) {
+    cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ldz * 4, (cuuint64_t)W * ldz * 4, (cuuint64_t)H * W * ldz * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)HALO_TW, 4, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = driver_fns().encodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, z, dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("conv_halo: output tensor map failed (%d) B=%d H=%d W=%d Cout=%d ldz=%d", (int)r, B, H, W, Cout, ldz);
+        return -3;
+    }
+    return 0;
+}
+
+template <int BN, int NCH>
+static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                       const CUtensorMap& zmap, const HaloArgs& a, int grid, cudaStream_t s) {
+    constexpr bool BRES = NCH * BN <= 64;          // the whole weight operand (9 * NCH blocks of BN x 64 B x 2 planes) stays in shared memory
+    using Cfg = HaloCfg<BN, NCH, BRES>;
+    auto kern = conv_halo_kernel<BN, NCH, BRES>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+        set_error("conv_halo: cudaFuncSetAttribute(%d bytes): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+        return (int)e;
+    }
+    kern<<<grid, 224, Cfg::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, zmap, a);
+    return launch_status("conv_halo");
+}
+
+template <int BN>
+static int launch_halo_nch(int nch, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+                           const CUtensorMap& zmap, const HaloArgs& a, int grid, cudaStream_t s) {
+    switch (nch) {
+        case 1: return launch_halo<BN, 1>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, s);
+        case 2: return launch_halo<BN, 2>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, s);
+        default: return launch_halo<BN, 4>(a_hi, a_lo, b_hi, b_lo, zmap, a, grid, s);
+    }
+}
+
+static int run_halo(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int B, const TcArgs& a, const TcPlan& pl,
+                    cudaStream_t s) {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo, zmap;
+    int rc = make_halo_act_map(&a_hi, x_hi, B, a.H, a.W, a.Cin, a.cpitch);
+    if (rc) return rc;
+    rc = make_halo_act_map(&a_lo, x_lo, B, a.H, a.W, a.Cin, a.cpitch);
+    if (rc) return rc;
+    const long long K = 9LL * a.cpitch;
+    rc = make_tiled_map(&b_hi, w_hi, a.Cout, K, pl.bn, 32);
+    if (rc) return rc;
+    rc = make_tiled_map(&b_lo, w_lo, a.Cout, K, pl.bn, 32);
+    if (rc) return rc;
+    rc = make_halo_out_map(&zmap, a.z, B, a.H, a.W, a.Cout, a.ldz);
+    if (rc) return rc;
+    HaloArgs h;
+    h.amax_a = a.amax_a; h.amax_b = a.amax_b; h.stats = a.stats; h.H = a.H; h.W = a.W; h.Cout = a.Cout; h.cpitch = a.cpitch;
+    h.tiles_x = pl.tiles_x; h.tiles_y = pl.tiles_y; h.tiles_total = pl.tiles_m; h.accumulate = a.accumulate;
+    const int nch = a.Cin / 32;
+    if (pl.bn == 32) return launch_halo_nch<32>(nch, a_hi, a_lo, b_hi, b_lo, zmap, h, pl.grid, s);
+    if (pl.bn == 64) return launch_halo_nch<64>(nch, a_hi, a_lo, b_hi, b_lo, zmap, h, pl.grid, s);
+    return launch_halo_nch<128>(nch, a_hi, a_lo, b_hi, b_lo, zmap, h, pl.grid, s);
+}
+
 static int run_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int B, TcArgs a, int mode, cudaStream_t s) {
-    const TcPlan pl = tc_plan(a.M, a.Cin, a.Cout, a.ks, mode);
+    const TcPlan pl = tc_plan(a.M, a.Cin, a.Cout, a.ks, mode, B, a.H, a.W);
+    if (pl.halo) return run_halo(x_hi, x_lo, w_hi, w_lo, B, a, pl, s);
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     int rc = make_im2col_map(&a_hi, x_hi, B, a.H, a.W, a.Cin, a.ks, TC_BM, a.cpitch, pl.bk);
     if (rc) return rc;
@@ -635,15 +745,19 @@ extern "C" int fsdet_conv_tc_supported(int Cin, int Cout, int ksize) {
 }
 
 extern "C" int fsdet_conv_tc_stat_rows(int B, int H, int W, int Cin, int Cout, int ksize, int mode) {
-    const TcPlan pl = tc_plan((long long)B * H * W, Cin, Cout, ksize, mode);
+    const TcPlan pl = tc_plan((long long)B * H * W, Cin, Cout, ksize, mode, B, H, W);
     return pl.persist ? pl.grid / pl.tiles_n : pl.tiles_m;
+}
+
+extern "C" int fsdet_conv_tc_uses_halo(int B, int H, int W, int Cin, int Cout, int ksize, int mode) {
+    return halo_ok(B, H, W, Cin, Cout, ksize, mode) ? 1 : 0;
 }
 
 extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* amax_x,
                                  const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin, int cpitch, int Cout,
                                  int ksize, int accumulate, int mode, float* stat_partial, void* stream) {
     const int terms = mode & 3;
-    FSDET_CHECK_ARG((mode & ~0x33) == 0, "conv_tc_fwd: unknown mode bits 0x%x", mode);
+    FSDET_CHECK_ARG((mode & ~0x73) == 0, "conv_tc_fwd: unknown mode bits 0x%x", mode);
     FSDET_CHECK_ARG(x_hi && w_hi && z && (!(terms & 1) || x_lo) && (!(terms & 2) || w_lo), "conv_tc_fwd: null pointer (mode %d)", mode);
     FSDET_CHECK_ARG(fsdet_conv_tc_supported(Cin, Cout, ksize) && cpitch >= Cin && cpitch % 8 == 0,
                     "conv_tc_fwd: unsupported Cin=%d (pitch %d) Cout=%d k=%d", Cin, cpitch, Cout, ksize);

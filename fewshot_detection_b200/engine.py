@@ -50,8 +50,12 @@ TC_PERSIST = os.environ.get('FSDET_TC_PERSIST', '0') == '1'
 TC_CLUSTER = os.environ.get('FSDET_TC_CLUSTER', '0') == '1'
 
 
+# halo-tile kernel for the high-resolution 3x3 layers (csrc/conv_halo_kernels.cuh): on unless FSDET_TC_HALO=0
+TC_HALO = os.environ.get('FSDET_TC_HALO', '1') != '0'
+
+
 def tc_mode(name):
-    return TC_TERMS[name] | (16 if TC_PERSIST else 0) | (32 if TC_CLUSTER else 0)
+    return TC_TERMS[name] | (16 if TC_PERSIST else 0) | (32 if TC_CLUSTER else 0) | (0 if TC_HALO else 64)
 
 LEAKY_SLOPE = 0.1
 BN_EPS = 1e-5

@@ -130,7 +130,12 @@ int fsdet_pad_channels(const float* in, int cin, float* out, int cout, size_t ro
  *     NULL.  Bit 4 (16): persistent tile loop for short-K layers (one CTA per
  *     SM, double-buffered TMEM accumulators).  Bit 5 (32): thread-block clusters
  *     of two CTAs that share the weight tile through TMA multicast (ignored in
- *     persistent mode and for single-tile problems).
+ *     persistent mode and for single-tile problems).  Bit 6 (64): never take the
+ *     halo-tile kernel.  By default (bits 4-6 clear, mode 3) the 3x3 layers with
+ *     Cin in {32, 64, 128}, Cout <= 128, W % 8 == 0 and enough 8 x 16 pixel tiles
+ *     run the halo-tile kernel (csrc/conv_halo_kernels.cuh: the input tile is
+ *     fetched once with its halo for all nine taps instead of once per tap - those
+ *     layers are L2-bandwidth bound otherwise); fsdet_conv_tc_uses_halo tells.
  * x_hi/x_lo dense NHWC [B*H*W][cpitch] fp16, w_hi/w_lo [Cout][k*k*cpitch] fp16,
  * amax_x / amax_w: device floats holding the tensors' absolute maxima (NULL =
  * planes are unscaled).  Output fp32 z[p][n] (+ previous z when accumulate
@@ -141,6 +146,7 @@ int fsdet_pad_channels(const float* in, int cin, float* out, int cout, size_t ro
  * pass over z); the layout fsdet_bn_finalize reads. */
 int fsdet_conv_tc_supported(int Cin, int Cout, int ksize);
 int fsdet_conv_tc_stat_rows(int B, int H, int W, int Cin, int Cout, int ksize, int mode);
+int fsdet_conv_tc_uses_halo(int B, int H, int W, int Cin, int Cout, int ksize, int mode);
 int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* amax_x,
                       const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin, int cpitch, int Cout,
                       int ksize, int accumulate, int mode, float* stat_partial, void* stream);

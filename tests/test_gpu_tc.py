@@ -163,6 +163,69 @@ def test_conv_tc_fwd(L, B, H, W, Cin, Cout, k, mode):
     assert rel(got2, 2 * ref) < tol
 
 
+HALO_CASES = [
+    # B, H, W, Cin, cpitch, Cout     (3x3; every shape is one the plan sends to the halo-tile kernel)
+    (4, 208, 208, 32, 32, 64),      # conv2 forward: weights resident in shared memory
+    (4, 208, 208, 32, 64, 64),      # the engine's layout: 32 channels in 64-channel-pitched planes
+    (4, 208, 208, 64, 64, 32),      # conv2 input gradient: N = 32, two chunks, resident
+    (5, 104, 104, 64, 64, 128),     # conv3 / conv5 forward: streamed weights; 104 rows overhang the 16-row tiles
+    (5, 104, 104, 128, 128, 64),    # conv3 / conv5 input gradient: four chunks
+    (3, 104, 104, 128, 128, 128),
+    (13, 40, 48, 32, 32, 48),       # Cout < BN and not a multiple of 32, H not a multiple of 16
+    (7, 64, 56, 64, 64, 96),
+]
+
+
+@pytest.mark.parametrize('B,H,W,Cin,cpitch,Cout', HALO_CASES)
+def test_conv_halo_fwd(L, B, H, W, Cin, cpitch, Cout):
+    """The halo-tile kernel (8 x 16 pixel tiles, input tile + halo fetched once for all nine taps) against the float64
+    convolution of the planes it multiplies and of the fp32 inputs (1e-5), against the im2col kernel on the same planes
+    (mode | 64), with its fused BatchNorm statistics and in accumulate mode."""
+    k = 3
+    assert L.lib.fsdet_conv_tc_uses_halo(B, H, W, Cin, Cout, k, 3) == 1
+    assert L.lib.fsdet_conv_tc_uses_halo(B, H, W, Cin, Cout, k, 3 | 64) == 0
+    g = torch.Generator(device='cuda').manual_seed(B + H + Cin + Cout)
+    x = torch.randn(B, Cin, H, W, device='cuda', generator=g)
+    w = torch.randn(Cout, Cin, k, k, device='cuda', generator=g) * 0.05
+    X = split(L, nhwc(x), cpitch)
+    w2 = w.permute(0, 2, 3, 1).contiguous().view(Cout * k * k, Cin)
+    Wp = split(L, w2, cpitch)                       # [Cout*9][cpitch]: k = tap * cpitch + c
+    if cpitch > Cin:                                # poison the padding channels: they must never be multiplied
+        for t in (X.hi, X.lo, Wp.hi, Wp.lo):
+            t[:, Cin:] = 777.0
+    sx, sw = plane_scale(X), plane_scale(Wp)
+    xh, xl = planes_nchw(X.hi, B, H, W, Cin), planes_nchw(X.lo, B, H, W, Cin)
+    wh = Wp.hi[:, :Cin].double().reshape(Cout, k, k, Cin).permute(0, 3, 1, 2)
+    wl = Wp.lo[:, :Cin].double().reshape(Cout, k, k, Cin).permute(0, 3, 1, 2)
+    conv = lambda a, b: F.conv2d(a, b, None, 1, 1)
+    ref = (conv(xh, wh) + conv(xl, wh) + conv(xh, wl)) / (sx * sw)
+    ld = Cout + 4
+    outs = {}
+    for mode in (3, 3 | 64):
+        z = torch.zeros(B * H * W, ld, device='cuda')
+        rows = L.lib.fsdet_conv_tc_stat_rows(B, H, W, Cin, Cout, k, mode)
+        part = torch.full((rows, 4 * Cout), 123.0, device='cuda')
+        L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), X.lo.data_ptr(), Wp.hi.data_ptr(), Wp.lo.data_ptr(), X.a, Wp.a, z.data_ptr(), ld,
+               B, H, W, Cin, cpitch, Cout, k, 0, mode, part.data_ptr(), st())
+        torch.cuda.synchronize()
+        got = z[:, :Cout].contiguous().view(B, H, W, Cout).permute(0, 3, 1, 2)
+        assert rel(got, ref) < TOL_TC, mode
+        assert rel(got, conv(x.double(), w.double())) < TOL_TC
+        assert (z[:, Cout:] == 0).all()
+        zz = z[:, :Cout]
+        s = part.double().sum(0)
+        assert rel(s[:Cout], zz.double().sum(0)) < 1e-5 or (s[:Cout] - zz.double().sum(0)).abs().max() < 1e-3
+        assert rel(s[Cout:2 * Cout], (zz.double() ** 2).sum(0)) < 1e-5
+        assert torch.equal(part[:, 2 * Cout:3 * Cout].min(0)[0], zz.min(0)[0])
+        assert torch.equal(part[:, 3 * Cout:].max(0)[0], zz.max(0)[0])
+        outs[mode] = got.clone()
+        L.call('fsdet_conv_tc_fwd', X.hi.data_ptr(), X.lo.data_ptr(), Wp.hi.data_ptr(), Wp.lo.data_ptr(), X.a, Wp.a, z.data_ptr(), ld,
+               B, H, W, Cin, cpitch, Cout, k, 1, mode, None, st())
+        got2 = z[:, :Cout].contiguous().view(B, H, W, Cout).permute(0, 3, 1, 2)
+        assert rel(got2, 2 * ref) < TOL_TC
+    assert rel(outs[3], outs[3 | 64]) < 2e-6      # same products, different accumulation order
+
+
 def test_conv_tc_term_modes_precision(L):
     """What each mode costs in accuracy on a long-K layer (printed; the bars are loose upper bounds)."""
     B, H, W, Cin, Cout, k = 2, 13, 13, 1024, 1024, 3
