@@ -24,8 +24,10 @@
 // Arithmetic: 3-term fp16 hi/lo scheme (conv_tc_kernels.cuh, TERMS = 3) - D_hi += A_hi * B_hi, D_lo += A_lo * B_hi +
 // A_hi * B_lo, summed in the epilogue.  K <= 1152 here, so one hi accumulator (the im2col short-K flavour's choice).
 //
-// Warps (224 threads): 0 = activation producer (+ resident weights), 1 = MMA issuer / TMEM owner, 2-5 = epilogue,
-// 6 = weight-ring producer (idle when the weights are resident).
+// Warps (352 threads): 0 = activation producer (+ resident weights), 1 = MMA issuer / TMEM owner, 2-9 = epilogue (two
+// warps per TMEM lane quarter, alternating 32-column chunks: at these tile shapes the epilogue's instruction stream, not
+// the tensor pipe, paces a 4-warp epilogue - profiles/ncu_r02b.md), 10 = weight-ring producer (idle when the weights
+// are resident).
 #pragma once
 
 struct HaloArgs {
@@ -37,6 +39,9 @@ struct HaloArgs {
     int tiles_x, tiles_y;
     int tiles_total;     // B * tiles_x * tiles_y
     int accumulate;
+    int flags;           // bit 2: fuse the two MMAs that share A_hi into one of width 2*BN (B_hi | B_lo are adjacent).
+                         // Timing experiments only (results invalid): bit 0 = fetch one halo copy instead of three,
+                         // bit 1 = no output stores, bit 3 = hi*hi term only
 };
 
 constexpr int HALO_TW = 8, HALO_TH = 16;
@@ -50,7 +55,7 @@ struct HaloCfg {
     static constexpr int BBLK = BN * 64;                           // one (tap, chunk) weight block of one plane
     static constexpr int BSTAGE = 2 * BBLK;                        // hi + lo
     static constexpr int NKB = 9 * NCH;                            // k-blocks (tap, chunk) per tile
-    static constexpr int EPI_BYTES = 4 * 2 * 4096;
+    static constexpr int EPI_BYTES = 8 * 4096;                     // one 32 x 32 fp32 staging block per epilogue warp
     static constexpr int STAT_BYTES = 4 * BN * 16;
     static constexpr int BUDGET = 227 * 1024 - 1024 - 256;
     static constexpr int FREE_FOR_B = BUDGET - SA * HALO_ASTAGE_BYTES - EPI_BYTES - STAT_BYTES;
@@ -68,21 +73,21 @@ struct HaloCfg {
 };
 
 template <int BN, int NCH, bool BRES>
-__global__ void __launch_bounds__(224, 1)
+__global__ void __launch_bounds__(352, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                  const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
                  const __grid_constant__ CUtensorMap tmZ, const HaloArgs p) {
     using Cfg = HaloCfg<BN, NCH, BRES>;
     constexpr int SA = Cfg::SA, SB = Cfg::SB;
     FSDET_TC_DYN_SMEM(smem_raw);
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = tc_align_smem(smem_raw);
     uint8_t* epi = smem + Cfg::OFF_EPI;
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
     uint64_t* a_empty = a_full + SA;
     uint64_t* b_full = a_empty + SA;              // [SB] ring, or [0] only when the weights are resident
     uint64_t* b_empty = b_full + 8;
     uint64_t* acc_full = b_empty + 8;             // [2] MMA issuer -> epilogue
-    uint64_t* acc_empty = acc_full + 2;           // [2] epilogue (4 warps) -> MMA issuer
+    uint64_t* acc_empty = acc_full + 2;           // [2] epilogue (8 warps) -> MMA issuer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5;
@@ -106,7 +111,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&acc_full[a], 1);
-            mbar_init(&acc_empty[a], 4);
+            mbar_init(&acc_empty[a], 8);
         }
         fence_barrier_init();
     }
@@ -120,6 +125,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
         if (lane == 0) {
             if (BRES) {          // the whole weight operand, once
                 mbar_expect_tx(&b_full[0], (uint32_t)(Cfg::NKB * Cfg::BSTAGE));
+#pragma unroll 1
                 for (int kb = 0; kb < Cfg::NKB; ++kb) {
                     const int chunk = kb / 9, tap = kb - chunk * 9;
                     uint8_t* st = smem + Cfg::OFF_B + kb * Cfg::BSTAGE;
@@ -137,16 +143,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
                     const int s = it % SA;
                     mbar_wait(&a_empty[s], ((it / SA) & 1) ^ 1);
                     uint8_t* st = smem + s * HALO_ASTAGE_BYTES;
-                    mbar_expect_tx(&a_full[s], (uint32_t)HALO_ASTAGE_BYTES);
-#pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
+                    const int ncopy = (p.flags & 1) ? 1 : 3;
+                    mbar_expect_tx(&a_full[s], (uint32_t)(ncopy * 2 * HALO_COPY_BYTES));
+                    for (int dx = 0; dx < ncopy; ++dx) {
                         tma_load_tiled_4d(st + dx * HALO_COPY_BYTES, &tmAhi, &a_full[s], chunk * 32, x0 + dx, y0, img);
                         tma_load_tiled_4d(st + (3 + dx) * HALO_COPY_BYTES, &tmAlo, &a_full[s], chunk * 32, x0 + dx, y0, img);
                     }
                 }
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == 10) {
         if (!BRES && lane == 0) {
             unsigned it = 0;                                   // weight stages issued so far
             for (int tile = (int)blockIdx.x; tile < tiles_total; tile += (int)gridDim.x) {
@@ -165,6 +171,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=f16, both K-major, N=BN, M=128
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // N = 2*BN
             if (BRES) {
                 mbar_wait(&b_full[0], 0);
                 tc_fence_after();
@@ -177,11 +184,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
                 const uint32_t dhi = tmem_base + a * (uint32_t)Cfg::ACC_COLS;
                 const uint32_t dlo = dhi + (uint32_t)BN;
                 uint32_t started = 0;
+#pragma unroll 1
                 for (int chunk = 0; chunk < NCH; ++chunk, ++ita) {
                     const int sa = ita % SA;
                     mbar_wait(&a_full[sa], (ita / SA) & 1);
                     tc_fence_after();
                     const uint32_t abase = smem_u32(smem + sa * HALO_ASTAGE_BYTES);
+#pragma unroll 1
                     for (int tap = 0; tap < 9; ++tap, ++itb) {
                         const int dy = tap / 3, dx = tap - dy * 3;
                         int sb;
@@ -201,9 +210,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
                             const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 halves = 32 B along K inside the swizzle atom
-                            umma_f16(dhi, ahi + adv, bhi + adv, idesc, started);
-                            umma_f16(dlo, alo + adv, bhi + adv, idesc, started);
-                            umma_f16(dlo, ahi + adv, blo + adv, idesc, 1u);
+                            if (p.flags & 8) {
+                                umma_f16(dhi, ahi + adv, bhi + adv, idesc, started);
+                            } else if (p.flags & 4) {
+                                // [D_hi | D_lo] += A_hi * [B_hi | B_lo] (one MMA of width 2*BN: A_hi is read once), D_lo += A_lo * B_hi
+                                umma_f16(dhi, ahi + adv, bhi + adv, idesc2, started);
+                                umma_f16(dlo, alo + adv, bhi + adv, idesc, 1u);
+                            } else {
+                                umma_f16(dhi, ahi + adv, bhi + adv, idesc, started);
+                                umma_f16(dlo, alo + adv, bhi + adv, idesc, started);
+                                umma_f16(dlo, ahi + adv, blo + adv, idesc, 1u);
+                            }
                             started = 1u;
                         }
                         if (!BRES) umma_commit(&b_empty[sb]);
@@ -214,14 +231,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
             }
         }
     } else {
-        // epilogue warps 2..5 -> TMEM lane quarters (warp % 4); each warp owns 4 spatial rows x 8 pixels of the tile
+        // epilogue warps 2..9 -> TMEM lane quarter warp % 4 (4 spatial rows x 8 pixels of the tile), column chunks ch with
+        // ch % 2 == half (BN = 32: the second warp of a quarter only hands the accumulators back)
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const float inv = 1.f / (scale_from_amax(p.amax_a ? ldg_f32(p.amax_a) : 0.f) * scale_from_amax(p.amax_b ? ldg_f32(p.amax_b) : 0.f));
-        uint8_t* stage_buf = epi + quarter * 8192;             // two 4 KB buffers per warp
+        uint8_t* buf = epi + (warp - 2) * 4096;
         const bool want_stats = p.stats != nullptr;
-        float ssum[BN / 32], esum[BN / 32], ssq[BN / 32], esq[BN / 32], smin[BN / 32], smax[BN / 32];
+        constexpr int NCHW = BN >= 64 ? BN / 64 : 1;           // chunks per warp
+        float ssum[NCHW], esum[NCHW], ssq[NCHW], esq[NCHW], smin[NCHW], smax[NCHW];
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) { ssum[c] = esum[c] = ssq[c] = esq[c] = 0.f; smin[c] = INFINITY; smax[c] = -INFINITY; }
+        for (int c = 0; c < NCHW; ++c) { ssum[c] = esum[c] = ssq[c] = esq[c] = 0.f; smin[c] = INFINITY; smax[c] = -INFINITY; }
         unsigned t = 0, stores = 0;                            // tiles done, TMA stores issued by this warp
         for (int tile = (int)blockIdx.x; tile < tiles_total; tile += (int)gridDim.x, ++t) {
             const unsigned a = t & 1u;
@@ -231,59 +251,47 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
             const int x0 = tx * HALO_TW, y0 = ty * HALO_TH + quarter * 4;   // this warp's 8 x 4 pixel block
             mbar_wait(&acc_full[a], (t >> 1) & 1u);
             tc_fence_after();
-            if (y0 < p.H) {                                    // warp-uniform: some of its rows are inside the image
-                // validity of this lane's pixel as a statistics ROW mask: bit rr set <=> tile row rr of the quarter is a pixel
-                uint32_t vmask = 0;
-                for (int rr = 0; rr < 32; ++rr)
-                    if (y0 + (rr >> 3) < p.H && x0 + (rr & 7) < p.W) vmask |= 1u << rr;
+            if (y0 < p.H && (BN >= 64 || half == 0)) {         // warp-uniform: some of its rows are inside the image
+                // statistics row mask: bit rr set <=> row rr of the block (pixel x0 + rr % 8, y0 + rr / 8) is inside the image
+                uint32_t vmask = 0xffffffffu;
+                if (y0 + 4 > p.H || x0 + HALO_TW > p.W) {
+                    vmask = 0;
+                    for (int rr = 0; rr < 32; ++rr)
+                        if (y0 + (rr >> 3) < p.H && x0 + (rr & 7) < p.W) vmask |= 1u << rr;
+                }
 #pragma unroll
-                for (int ch = 0; ch < BN / 32; ++ch) {
-                    uint32_t rv[32];
-                    float acc[32];
-                    const uint32_t taddr = tmem_base + a * (uint32_t)Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16) + ch * 32;
-                    tmem_ld32(taddr + BN, rv);                 // lo terms first (small), then the hi*hi sum
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(rv[j]);
-                    tmem_ld32(taddr, rv);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(rv[j]);
+                for (int cw = 0; cw < NCHW; ++cw) {
+                    const int ch = BN >= 64 ? cw * 2 + half : 0;
                     const int n0 = ch * 32;
                     if (n0 < p.Cout) {                         // warp-uniform
-                        uint8_t* buf = stage_buf + (stores & 1u) * 4096;
-                        if (stores >= 2) {                     // the store that last read this buffer must have drained
-                            if (lane == 0) tma_store_wait_read<1>();
+                        float acc[32];
+                        const uint32_t taddr = tmem_base + a * (uint32_t)Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16) + ch * 32;
+                        epi_load_scaled<true>(taddr, taddr + BN, inv, acc);
+                        if (stores >= 1) {                     // the previous store must have read the staging block
+                            if (lane == 0) tma_store_wait_read<0>();
                             __syncwarp();
                         }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float4 v = make_float4(acc[4 * j] * inv, acc[4 * j + 1] * inv, acc[4 * j + 2] * inv, acc[4 * j + 3] * inv);
-                            *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
-                        }
+                        epi_stage_row(buf, lane, acc);
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0) {
+                        if (lane == 0 && !(p.flags & 2)) {
                             if (p.accumulate) tma_reduce_add_4d(&tmZ, buf, n0, x0, y0, img);
                             else tma_store_4d(&tmZ, buf, n0, x0, y0, img);
                             tma_store_commit();
                         }
                         ++stores;
                         if (want_stats) {
-                            // column `lane` of the staged 32x32 tile (conflict-free under the swizzle), rows outside the image excluded
-                            float s = 0.f, q = 0.f, mn = INFINITY, mx = -INFINITY;
-                            for (int rr = 0; rr < 32; ++rr) {
-                                if (!((vmask >> rr) & 1u)) continue;
-                                const float v = *reinterpret_cast<const float*>(buf + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + (lane & 3) * 4);
-                                s += v; q += v * v; mn = fminf(mn, v); mx = fmaxf(mx, v);
-                            }
-                            tc_kahan_add(ssum[ch], esum[ch], s);
-                            tc_kahan_add(ssq[ch], esq[ch], q);
-                            smin[ch] = fminf(smin[ch], mn);
-                            smax[ch] = fmaxf(smax[ch], mx);
+                            float s1, q1, mn, mx;
+                            epi_col_stats(buf, lane, vmask, s1, q1, mn, mx);
+                            tc_kahan_add(ssum[cw], esum[cw], s1);
+                            tc_kahan_add(ssq[cw], esq[cw], q1);
+                            smin[cw] = fminf(smin[cw], mn);
+                            smax[cw] = fmaxf(smax[cw], mx);
                         }
                     }
                 }
             }
-            // this warp's TMEM reads of set `a` are complete (tcgen05.wait::ld in tmem_ld32): hand the set back
+            // this warp's TMEM reads of set `a` are complete (tcgen05.wait::ld in epi_load_scaled): hand the set back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[a]);
@@ -291,14 +299,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
         if (lane == 0) tma_store_wait_read<0>();               // shared memory must outlive the bulk reads
         __syncwarp();
         if (want_stats) {
-            // fold the four warps (pixel quarters) in a fixed order and write this CTA's partial row
+            // fold the four pixel quarters in a fixed order and write this CTA's partial row
             float4* sbuf = reinterpret_cast<float4*>(epi + Cfg::EPI_BYTES);   // [4][BN]
+            if (BN >= 64 || half == 0) {
 #pragma unroll
-            for (int ch = 0; ch < BN / 32; ++ch)
-                sbuf[quarter * BN + ch * 32 + lane] = make_float4(ssum[ch] - esum[ch], ssq[ch] - esq[ch], smin[ch], smax[ch]);
-            named_bar_sync(1, 128);
+                for (int cw = 0; cw < NCHW; ++cw) {
+                    const int ch = BN >= 64 ? cw * 2 + half : 0;
+                    sbuf[quarter * BN + ch * 32 + lane] = make_float4(ssum[cw] - esum[cw], ssq[cw] - esq[cw], smin[cw], smax[cw]);
+                }
+            }
+            named_bar_sync(1, 256);
             const int e = (warp - 2) * 32 + lane;
-            for (int c = e; c < BN; c += 128) {
+            for (int c = e; c < BN; c += 256) {
                 float4 tt = sbuf[c];
 #pragma unroll
                 for (int qq = 1; qq < 4; ++qq) {

@@ -21,6 +21,7 @@
 //   warps 2-5: epilogue, tcgen05.ld the fp32 accumulator (lane = pixel) and store z rows.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -591,7 +592,7 @@ static int launch_halo(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
         set_error("conv_halo: cudaFuncSetAttribute(%d bytes): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
         return (int)e;
     }
-    kern<<<grid, 224, Cfg::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, zmap, a);
+    kern<<<grid, 352, Cfg::SMEM_BYTES, s>>>(a_hi, a_lo, b_hi, b_lo, zmap, a);
     return launch_status("conv_halo");
 }
 
@@ -622,6 +623,8 @@ static int run_halo(const void* x_hi, const void* x_lo, const void* w_hi, const 
     HaloArgs h;
     h.amax_a = a.amax_a; h.amax_b = a.amax_b; h.stats = a.stats; h.H = a.H; h.W = a.W; h.Cout = a.Cout; h.cpitch = a.cpitch;
     h.tiles_x = pl.tiles_x; h.tiles_y = pl.tiles_y; h.tiles_total = pl.tiles_m; h.accumulate = a.accumulate;
+    const char* dbg = getenv("FSDET_HALO_FLAGS");      // developer knob (tools/halo_bench.py): see HaloArgs::flags
+    h.flags = dbg ? atoi(dbg) : 0;
     const int nch = a.Cin / 32;
     if (pl.bn == 32) return launch_halo_nch<32>(nch, a_hi, a_lo, b_hi, b_lo, zmap, h, pl.grid, s);
     if (pl.bn == 64) return launch_halo_nch<64>(nch, a_hi, a_lo, b_hi, b_lo, zmap, h, pl.grid, s);

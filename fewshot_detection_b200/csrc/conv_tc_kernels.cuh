@@ -92,6 +92,63 @@ __device__ __forceinline__ void tc_kahan_add(float& s, float& e, float x) {
     s = t;
 }
 
+// ---- epilogue building blocks (shared with conv_halo_kernels.cuh).  One epilogue warp handles 32 tile rows (its TMEM lane
+// quarter) x 32 columns at a time: TMEM -> registers -> 128-byte-swizzled 4 KB staging block -> TMA store, and - for
+// BatchNorm layers - the column statistics read back from the staged block.  Kept lean on purpose: at 128 x 64 tiles the
+// epilogue's instruction count, not the tensor pipe, paced the short-K kernels (profiles/ncu_r02b.md).
+
+// dynamic shared memory aligned to 1 KB WITHOUT leaving the shared address space (a round trip through uintptr_t makes
+// every later access a generic LD / ST)
+__device__ __forceinline__ uint8_t* tc_align_smem(uint8_t* raw) { return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u); }
+
+// acc[j] = (hi[j] + lo[j]) * inv for the 32 columns at taddr_hi / taddr_lo (both loads in flight, one wait)
+template <bool HAS_LO>
+__device__ __forceinline__ void epi_load_scaled(uint32_t taddr_hi, uint32_t taddr_lo, float inv, float (&acc)[32]) {
+    uint32_t rh[32], rl[32];
+    if (HAS_LO) tmem_ld32_nowait(taddr_lo, rl);
+    tmem_ld32_nowait(taddr_hi, rh);
+    tmem_ld_wait();
+    if (HAS_LO) tmem_ld_use(rl);
+    tmem_ld_use(rh);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = HAS_LO ? (__uint_as_float(rl[j]) + __uint_as_float(rh[j])) * inv : __uint_as_float(rh[j]) * inv;
+}
+
+// row `lane` of the 32 x 32 fp32 block into the staging buffer (16-byte chunk j of row r lives at chunk j ^ (r & 7))
+__device__ __forceinline__ void epi_stage_row(uint8_t* buf, int lane, const float (&acc)[32]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+}
+
+// statistics of column `lane` of a staged block over the rows whose bit is set in `vmask` (conflict-free: the 16-byte
+// chunks of a row are a permutation); four independent partial chains
+__device__ __forceinline__ void epi_col_stats(const uint8_t* buf, int lane, uint32_t vmask, float& s, float& q, float& mn, float& mx) {
+    const uint8_t* col = buf + (lane & 3) * 4;
+    const int cj = lane >> 2;
+    float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
+    float pmn[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, pmx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    if (vmask == 0xffffffffu) {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+            const float v = *reinterpret_cast<const float*>(col + rr * 128 + ((cj ^ (rr & 7)) << 4));
+            ps[rr & 3] += v; pq[rr & 3] = fmaf(v, v, pq[rr & 3]); pmn[rr & 3] = fminf(pmn[rr & 3], v); pmx[rr & 3] = fmaxf(pmx[rr & 3], v);
+        }
+    } else {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+            const float v = *reinterpret_cast<const float*>(col + rr * 128 + ((cj ^ (rr & 7)) << 4));
+            const bool ok = (vmask >> rr) & 1u;
+            ps[rr & 3] += ok ? v : 0.f; pq[rr & 3] = fmaf(ok ? v : 0.f, v, pq[rr & 3]);
+            pmn[rr & 3] = fminf(pmn[rr & 3], ok ? v : INFINITY); pmx[rr & 3] = fmaxf(pmx[rr & 3], ok ? v : -INFINITY);
+        }
+    }
+    s = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+    q = (pq[0] + pq[1]) + (pq[2] + pq[3]);
+    mn = fminf(fminf(pmn[0], pmn[1]), fminf(pmn[2], pmn[3]));
+    mx = fmaxf(fmaxf(pmx[0], pmx[1]), fmaxf(pmx[2], pmx[3]));
+}
+
 // CLUSTER = 2 (one-tile-per-CTA flavours only): two CTAs of a thread-block cluster work on two M tiles of the SAME
 // channel range; each loads its own activation tiles and only HALF of the weight tile, multicast into both CTAs'
 // shared memory - the weight operand crosses the L2 -> SM fabric once per pair instead of once per CTA (the 128 x 128
@@ -106,7 +163,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NSETS = Cfg::NSETS;
     FSDET_TC_DYN_SMEM(smem_raw);
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = tc_align_smem(smem_raw);
     uint8_t* epi = smem + Cfg::EPI_OFF;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
     uint64_t* empty_bar = full_bar + STAGES;
@@ -244,36 +301,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
             const long long mrow = m0 + quarter * 32;
             mbar_wait(&acc_full[a], (t / NSETS) & 1u);
             tc_fence_after();
+            const long long left = p.M - mrow;                 // rows beyond the tensor's last pixel are excluded from the statistics
+            const uint32_t vmask = left >= 32 ? 0xffffffffu : (left > 0 ? ((1u << (int)left) - 1u) : 0u);
 #pragma unroll
             for (int ch = 0; ch < BN / 32; ++ch) {
-                uint32_t r[32];
-                float acc[32];
-                const uint32_t taddr = tmem_base + a * (uint32_t)Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16) + ch * 32;
-                if constexpr (TERMS != 0) {
-                    tmem_ld32(taddr + NH * BN, r);             // lo terms first (small), then the hi*hi partial sums
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-                }
-                for (int h = nhi - 1; h >= 0; --h) {
-                    tmem_ld32(taddr + h * BN, r);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
-                }
                 const int n0 = n_tile * BN + ch * 32;
                 if (n0 < p.Cout && mrow < p.M) {               // warp-uniform
+                    float acc[32];
+                    const uint32_t taddr = tmem_base + a * (uint32_t)Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16) + ch * 32;
+                    if constexpr (NH == 1) {
+                        epi_load_scaled<TERMS != 0>(taddr, taddr + NH * BN, inv, acc);
+                    } else {                                   // lo terms first (small), then the rotating hi*hi partial sums
+                        uint32_t r[32];
+                        if constexpr (TERMS != 0) {
+                            tmem_ld32(taddr + NH * BN, r);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+                        }
+                        for (int h = nhi - 1; h >= 0; --h) {
+                            tmem_ld32(taddr + h * BN, r);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] *= inv;
+                    }
                     uint8_t* buf = stage_buf + (stores & 1u) * 4096;
                     if (stores >= 2) {                         // the store that last read this buffer must have drained
                         if (lane == 0) tma_store_wait_read<1>();
                         __syncwarp();
                     }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 v = make_float4(acc[4 * j] * inv, acc[4 * j + 1] * inv, acc[4 * j + 2] * inv, acc[4 * j + 3] * inv);
-                        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
-                    }
+                    epi_stage_row(buf, lane, acc);
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
@@ -283,15 +344,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                     }
                     ++stores;
                     if (want_stats) {
-                        // column `lane` of the staged 32x32 tile (conflict-free: the 16-byte chunks of a row are a
-                        // permutation), rows beyond the tensor's last pixel excluded
-                        const long long left = p.M - mrow;
-                        const int nvalid = left < 32 ? (int)left : 32;
-                        float s = 0.f, q = 0.f, mn = INFINITY, mx = -INFINITY;
-                        for (int rr = 0; rr < nvalid; ++rr) {
-                            const float v = *reinterpret_cast<const float*>(buf + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + (lane & 3) * 4);
-                            s += v; q += v * v; mn = fminf(mn, v); mx = fmaxf(mx, v);
-                        }
+                        float s, q, mn, mx;
+                        epi_col_stats(buf, lane, vmask, s, q, mn, mx);
                         tc_kahan_add(ssum[ch], esum[ch], s);
                         tc_kahan_add(ssq[ch], esq[ch], q);
                         smin[ch] = fminf(smin[ch], mn);

@@ -31,7 +31,7 @@ CASES = [
 
 
 @pytest.mark.parametrize('B,H,W,Cin,cpitch,Cout,ctas,acc,stats', CASES)
-def test_halo_kernel_control_flow(emul, B, H, W, Cin, cpitch, Cout, ctas, acc, stats):
+def test_halo_kernel_control_flow(emul, B, H, W, Cin, cpitch, Cout, ctas, acc, stats, flags=0):
     rs = np.random.RandomState(B * 100 + H + Cin + Cout + ctas)
     x = rs.randn(B, H, W, Cin).astype(np.float32)
     w = (rs.randn(Cout, 9, Cin) * 0.1).astype(np.float32)
@@ -48,7 +48,7 @@ def test_halo_kernel_control_flow(emul, B, H, W, Cin, cpitch, Cout, ctas, acc, s
     z0 = rs.randn(M, ld).astype(np.float32) if acc else np.full((M, ld), 7.0, dtype=np.float32)
     z = z0.copy()
     st = np.full((ctas, 4 * Cout), 123.0, dtype=np.float32) if stats else None
-    rc = emul.emul_conv_halo(P(xhp), P(xlp), P(whp), P(wlp), P(ax), P(aw), P(z), ld, B, H, W, Cin, cpitch, Cout, acc, ctas, P(st))
+    rc = emul.emul_conv_halo(P(xhp), P(xlp), P(whp), P(wlp), P(ax), P(aw), P(z), ld, B, H, W, Cin, cpitch, Cout, acc, ctas, P(st), flags)
     assert rc == 0, 'barrier deadlock in the kernel' if rc == -100 else rc
     ref = expected(xh, xl, wh, wl, ax, aw, 3, 3)
     got = z[:, :Cout].astype(np.float64) - (z0[:, :Cout] if acc else 0)
@@ -70,3 +70,9 @@ def test_slow_epilogue(emul):
         test_halo_kernel_control_flow(emul, *CASES[3])
     finally:
         emul.emul_set_ld_delay_us(0)
+
+
+@pytest.mark.parametrize('case', [0, 2, 4, 5])
+def test_fused_hi_lo_mma(emul, case):
+    """flags bit 2: A_hi * [B_hi | B_lo] as ONE MMA of width 2*BN into the adjacent hi / lo accumulators - same products."""
+    test_halo_kernel_control_flow(emul, *CASES[case], flags=4)

@@ -170,7 +170,7 @@ HALO_CASES = [
     (4, 208, 208, 64, 64, 32),      # conv2 input gradient: N = 32, two chunks, resident
     (5, 104, 104, 64, 64, 128),     # conv3 / conv5 forward: streamed weights; 104 rows overhang the 16-row tiles
     (5, 104, 104, 128, 128, 64),    # conv3 / conv5 input gradient: four chunks
-    (3, 104, 104, 128, 128, 128),
+    (4, 104, 104, 128, 128, 128),
     (13, 40, 48, 32, 32, 48),       # Cout < BN and not a multiple of 32, H not a multiple of 16
     (7, 64, 56, 64, 64, 96),
 ]

@@ -60,7 +60,7 @@ static int run_halo(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* 
     act(&mAh, x_hi); act(&mAl, x_lo); wgt(&mBh, w_hi); wgt(&mBl, w_lo);
     { MapModel mm{}; mm.kind = 4; mm.z = z; mm.rows = a.Cout; mm.B = B; mm.H = a.H; mm.W = a.W; mm.ldz = ldz; memset(&mZ, 0, sizeof(mZ)); memcpy(&mZ, &mm, sizeof(mm)); }
     g_deadlock.store(false);
-    emul::launch(dim3(ctas), dim3(224), Cfg::SMEM_BYTES, [&]() {
+    emul::launch(dim3(ctas), dim3(352), Cfg::SMEM_BYTES, [&]() {
         if (threadIdx.x == 0) {
             memset(g_tmem, 0, sizeof(g_tmem));
             std::lock_guard<std::mutex> l(g_mu);
@@ -88,11 +88,11 @@ static int run_halo_nch(int nch, const uint16_t* x_hi, const uint16_t* x_lo, con
 // stats: optional [ctas][4*Cout] partial rows
 extern "C" int emul_conv_halo(const uint16_t* x_hi, const uint16_t* x_lo, const uint16_t* w_hi, const uint16_t* w_lo,
                               const float* amax_x, const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin, int cpitch,
-                              int Cout, int accumulate, int ctas, float* stats) {
+                              int Cout, int accumulate, int ctas, float* stats, int flags) {
     if (W % 8 != 0 || Cin % 32 != 0 || Cout > 128) return -1;
     HaloArgs a;
     a.amax_a = amax_x; a.amax_b = amax_w; a.stats = stats; a.H = H; a.W = W; a.Cout = Cout; a.cpitch = cpitch;
-    a.tiles_x = W / 8; a.tiles_y = (H + 15) / 16; a.tiles_total = B * a.tiles_x * a.tiles_y; a.accumulate = accumulate;
+    a.tiles_x = W / 8; a.tiles_y = (H + 15) / 16; a.tiles_total = B * a.tiles_x * a.tiles_y; a.accumulate = accumulate; a.flags = flags;
     if (ctas > a.tiles_total) return -1;
     const int bn = Cout <= 32 ? 32 : (Cout <= 64 ? 64 : 128);
     if (bn == 32) return run_halo_nch<32>(Cin / 32, x_hi, x_lo, w_hi, w_lo, a, z, ldz, B, Cin, ctas);

@@ -182,6 +182,10 @@ static inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     for (int j = 0; j < 32; ++j) memcpy(&r[j], &g_tmem[row][col + j], 4);
 }
 
+static inline void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+static inline void tmem_ld_wait() {}
+static inline void tmem_ld_use(uint32_t (&)[32]) {}
+
 // barrier over a subset of the block's threads (bar.sync id, n): generation counter per id
 struct NamedBar { int waiting = 0; long long gen = 0; };
 static NamedBar g_named[16];
