@@ -39,7 +39,7 @@ struct HaloArgs {
     int tiles_x, tiles_y;
     int tiles_total;     // B * tiles_x * tiles_y
     int accumulate;
-    int flags;           // bit 2: fuse the two MMAs that share A_hi into one of width 2*BN (B_hi | B_lo are adjacent).
+    int flags;           // developer knob FSDET_HALO_FLAGS.  bit 2: three MMAs per K step instead of the fused pair (same products).
                          // Timing experiments only (results invalid): bit 0 = fetch one halo copy instead of three,
                          // bit 1 = no output stores, bit 3 = hi*hi term only
 };
@@ -121,9 +121,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // The three issuing roles run with their whole warp converged and issue under elect_one() (see tc_ptx.cuh).
     if (warp == 0) {
-        if (lane == 0) {
-            if (BRES) {          // the whole weight operand, once
+        if (BRES) {          // the whole weight operand, once
+            if (elect_one()) {
                 mbar_expect_tx(&b_full[0], (uint32_t)(Cfg::NKB * Cfg::BSTAGE));
 #pragma unroll 1
                 for (int kb = 0; kb < Cfg::NKB; ++kb) {
@@ -133,15 +134,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
                     tma_load_2d(st + Cfg::BBLK, &tmBlo, &b_full[0], tap * p.cpitch + chunk * 32, 0);
                 }
             }
-            unsigned it = 0;                                   // activation stages issued so far
-            for (int tile = (int)blockIdx.x; tile < tiles_total; tile += (int)gridDim.x) {
-                const int img = tile / tiles_img;
-                const int r = tile - img * tiles_img;
-                const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-                const int x0 = tx * HALO_TW - 1, y0 = ty * HALO_TH - 1;
-                for (int chunk = 0; chunk < NCH; ++chunk, ++it) {
-                    const int s = it % SA;
-                    mbar_wait(&a_empty[s], ((it / SA) & 1) ^ 1);
+            __syncwarp();
+        }
+        unsigned it = 0;                                   // activation stages issued so far
+        for (int tile = (int)blockIdx.x; tile < tiles_total; tile += (int)gridDim.x) {
+            const int img = tile / tiles_img;
+            const int r = tile - img * tiles_img;
+            const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+            const int x0 = tx * HALO_TW - 1, y0 = ty * HALO_TH - 1;
+#pragma unroll 1
+            for (int chunk = 0; chunk < NCH; ++chunk, ++it) {
+                const int s = it % SA;
+                mbar_wait_warp(&a_empty[s], ((it / SA) & 1) ^ 1);
+                if (elect_one()) {
                     uint8_t* st = smem + s * HALO_ASTAGE_BYTES;
                     const int ncopy = (p.flags & 1) ? 1 : 3;
                     mbar_expect_tx(&a_full[s], (uint32_t)(ncopy * 2 * HALO_COPY_BYTES));
@@ -150,90 +155,104 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
                         tma_load_tiled_4d(st + (3 + dx) * HALO_COPY_BYTES, &tmAlo, &a_full[s], chunk * 32, x0 + dx, y0, img);
                     }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 10) {
-        if (!BRES && lane == 0) {
+        if (!BRES) {
             unsigned it = 0;                                   // weight stages issued so far
             for (int tile = (int)blockIdx.x; tile < tiles_total; tile += (int)gridDim.x) {
+#pragma unroll 1
                 for (int kb = 0; kb < Cfg::NKB; ++kb, ++it) {
                     const int chunk = kb / 9, tap = kb - chunk * 9;
                     const int s = it % SB;
-                    mbar_wait(&b_empty[s], ((it / SB) & 1) ^ 1);
-                    uint8_t* st = smem + Cfg::OFF_B + s * Cfg::BSTAGE;
-                    mbar_expect_tx(&b_full[s], (uint32_t)Cfg::BSTAGE);
-                    tma_load_2d(st, &tmBhi, &b_full[s], tap * p.cpitch + chunk * 32, 0);
-                    tma_load_2d(st + Cfg::BBLK, &tmBlo, &b_full[s], tap * p.cpitch + chunk * 32, 0);
+                    mbar_wait_warp(&b_empty[s], ((it / SB) & 1) ^ 1);
+                    if (elect_one()) {
+                        uint8_t* st = smem + Cfg::OFF_B + s * Cfg::BSTAGE;
+                        mbar_expect_tx(&b_full[s], (uint32_t)Cfg::BSTAGE);
+                        tma_load_2d(st, &tmBhi, &b_full[s], tap * p.cpitch + chunk * 32, 0);
+                        tma_load_2d(st + Cfg::BBLK, &tmBlo, &b_full[s], tap * p.cpitch + chunk * 32, 0);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=f16, both K-major, N=BN, M=128
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t idesc2 = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // N = 2*BN
-            if (BRES) {
-                mbar_wait(&b_full[0], 0);
-                tc_fence_after();
-            }
-            unsigned ita = 0, itb = 0, t = 0;
-            for (int tile = (int)blockIdx.x; tile < tiles_total; tile += (int)gridDim.x, ++t) {
-                const unsigned a = t & 1u;
-                mbar_wait(&acc_empty[a], ((t >> 1) & 1u) ^ 1u);    // the epilogue has drained this accumulator set
-                tc_fence_after();
-                const uint32_t dhi = tmem_base + a * (uint32_t)Cfg::ACC_COLS;
-                const uint32_t dlo = dhi + (uint32_t)BN;
-                uint32_t started = 0;
+        // instruction descriptors: D=f32, A=B=f16, both K-major, M=128; N=BN, and N=2*BN for the fused hi|lo MMA
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc2 = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const bool fused = !(p.flags & 4);                 // flags bit 2 now selects the three-MMA form (A / B experiments)
+        const bool hi_only = (p.flags & 8) != 0;
+        if (BRES) {
+            mbar_wait_warp(&b_full[0], 0);
+            tc_fence_after();
+        }
+        const uint32_t smem_base = smem_u32(smem);
+        unsigned ita = 0, itb = 0, t = 0;
+        for (int tile = (int)blockIdx.x; tile < tiles_total; tile += (int)gridDim.x, ++t) {
+            const unsigned a = t & 1u;
+            mbar_wait_warp(&acc_empty[a], ((t >> 1) & 1u) ^ 1u);    // the epilogue has drained this accumulator set
+            tc_fence_after();
+            const uint32_t dhi = tmem_base + a * (uint32_t)Cfg::ACC_COLS;
+            const uint32_t dlo = dhi + (uint32_t)BN;
+            uint32_t started = 0;
 #pragma unroll 1
-                for (int chunk = 0; chunk < NCH; ++chunk, ++ita) {
-                    const int sa = ita % SA;
-                    mbar_wait(&a_full[sa], (ita / SA) & 1);
-                    tc_fence_after();
-                    const uint32_t abase = smem_u32(smem + sa * HALO_ASTAGE_BYTES);
+            for (int chunk = 0; chunk < NCH; ++chunk, ++ita) {
+                const int sa = ita % SA;
+                mbar_wait_warp(&a_full[sa], (ita / SA) & 1);
+                tc_fence_after();
+                const uint32_t a0 = umma_desc_lo(smem_base + sa * HALO_ASTAGE_BYTES);
 #pragma unroll 1
-                    for (int tap = 0; tap < 9; ++tap, ++itb) {
-                        const int dy = tap / 3, dx = tap - dy * 3;
+                for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx, ++itb) {
                         int sb;
                         if (BRES) {
-                            sb = chunk * 9 + tap;
+                            sb = chunk * 9 + dy * 3 + dx;
                         } else {
                             sb = itb % SB;
-                            mbar_wait(&b_full[sb], (itb / SB) & 1);
+                            mbar_wait_warp(&b_full[sb], (itb / SB) & 1);
                             tc_fence_after();
                         }
-                        const uint32_t bbase = smem_u32(smem + Cfg::OFF_B + sb * Cfg::BSTAGE);
-                        const uint32_t aoff = (uint32_t)(dx * HALO_COPY_BYTES + dy * (HALO_TW * 64));
-                        const uint64_t ahi = umma_desc_k_sw64(abase + aoff);
-                        const uint64_t alo = umma_desc_k_sw64(abase + 3 * HALO_COPY_BYTES + aoff);
-                        const uint64_t bhi = umma_desc_k_sw64(bbase);
-                        const uint64_t blo = umma_desc_k_sw64(bbase + Cfg::BBLK);
+                        if (elect_one()) {
+                            const uint32_t ah = a0 + (uint32_t)((dx * HALO_COPY_BYTES + dy * (HALO_TW * 64)) >> 4);
+                            const uint32_t al = ah + (uint32_t)((3 * HALO_COPY_BYTES) >> 4);
+                            const uint32_t bh = umma_desc_lo(smem_base + Cfg::OFF_B + sb * Cfg::BSTAGE);
+                            const uint32_t bl = bh + (uint32_t)(Cfg::BBLK >> 4);
+                            constexpr uint32_t HI = UMMA_DESC_HI_K_SW64;
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 halves = 32 B along K inside the swizzle atom
-                            if (p.flags & 8) {
-                                umma_f16(dhi, ahi + adv, bhi + adv, idesc, started);
-                            } else if (p.flags & 4) {
-                                // [D_hi | D_lo] += A_hi * [B_hi | B_lo] (one MMA of width 2*BN: A_hi is read once), D_lo += A_lo * B_hi
-                                umma_f16(dhi, ahi + adv, bhi + adv, idesc2, started);
-                                umma_f16(dlo, alo + adv, bhi + adv, idesc, 1u);
-                            } else {
-                                umma_f16(dhi, ahi + adv, bhi + adv, idesc, started);
-                                umma_f16(dlo, alo + adv, bhi + adv, idesc, started);
-                                umma_f16(dlo, ahi + adv, blo + adv, idesc, 1u);
+                            for (uint32_t k = 0; k < 2; ++k) {     // 16 halves = 32 B along K inside the swizzle atom: + 2 in the descriptor
+                                if (hi_only) {
+                                    umma_f16_lohi(dhi, ah + 2 * k, HI, bh + 2 * k, HI, idesc, started);
+                                } else if (fused) {
+                                    // [D_hi | D_lo] (+)= A_hi * [B_hi | B_lo]: ONE MMA of width 2*BN (the lo block follows the hi block
+                                    // in shared memory, the lo accumulator follows the hi accumulator in TMEM); D_lo += A_lo * B_hi
+                                    umma_f16_lohi(dhi, ah + 2 * k, HI, bh + 2 * k, HI, idesc2, started);
+                                    umma_f16_lohi(dlo, al + 2 * k, HI, bh + 2 * k, HI, idesc, 1u);
+                                } else {
+                                    umma_f16_lohi(dhi, ah + 2 * k, HI, bh + 2 * k, HI, idesc, started);
+                                    umma_f16_lohi(dlo, al + 2 * k, HI, bh + 2 * k, HI, idesc, started);
+                                    umma_f16_lohi(dlo, ah + 2 * k, HI, bl + 2 * k, HI, idesc, 1u);
+                                }
+                                started = 1u;
                             }
-                            started = 1u;
+                            if (!BRES) umma_commit(&b_empty[sb]);
                         }
-                        if (!BRES) umma_commit(&b_empty[sb]);
+                        started = 1u;
+                        __syncwarp();
                     }
-                    umma_commit(&a_empty[sa]);     // frees the activation stage when these MMAs have read it
                 }
-                umma_commit(&acc_full[a]);         // accumulator set complete
+                if (elect_one()) umma_commit(&a_empty[sa]);     // frees the activation stage when these MMAs have read it
+                __syncwarp();
             }
+            if (elect_one()) umma_commit(&acc_full[a]);         // accumulator set complete
+            __syncwarp();
         }
     } else {
         // epilogue warps 2..9 -> TMEM lane quarter warp % 4 (4 spatial rows x 8 pixels of the tile), column chunks ch with
         // ch % 2 == half (BN = 32: the second warp of a quarter only hands the accumulators back)
         const int quarter = warp & 3;
+        const bool leader = elect_one();                       // issues (and later waits for) this warp's TMA stores
         const int half = (warp - 2) >> 2;
         const float inv = 1.f / (scale_from_amax(p.amax_a ? ldg_f32(p.amax_a) : 0.f) * scale_from_amax(p.amax_b ? ldg_f32(p.amax_b) : 0.f));
         uint8_t* buf = epi + (warp - 2) * 4096;
@@ -268,13 +287,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
                         const uint32_t taddr = tmem_base + a * (uint32_t)Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16) + ch * 32;
                         epi_load_scaled<true>(taddr, taddr + BN, inv, acc);
                         if (stores >= 1) {                     // the previous store must have read the staging block
-                            if (lane == 0) tma_store_wait_read<0>();
+                            if (leader) tma_store_wait_read<0>();
                             __syncwarp();
                         }
                         epi_stage_row(buf, lane, acc);
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0 && !(p.flags & 2)) {
+                        if (leader && !(p.flags & 2)) {
                             if (p.accumulate) tma_reduce_add_4d(&tmZ, buf, n0, x0, y0, img);
                             else tma_store_4d(&tmZ, buf, n0, x0, y0, img);
                             tma_store_commit();
@@ -294,9 +313,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
             // this warp's TMEM reads of set `a` are complete (tcgen05.wait::ld in epi_load_scaled): hand the set back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[a]);
+            if (leader) mbar_arrive(&acc_empty[a]);
         }
-        if (lane == 0) tma_store_wait_read<0>();               // shared memory must outlive the bulk reads
+        if (leader) tma_store_wait_read<0>();               // shared memory must outlive the bulk reads
         __syncwarp();
         if (want_stats) {
             // fold the four pixel quarters in a fixed order and write this CTA's partial row

@@ -210,12 +210,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // issuing roles: whole warp converged, instructions under elect_one() (tc_ptx.cuh)
     if (warp == 0) {
-        if (lane == 0) {
-            const int HW = p.H * p.W;
-            for (int kb = 0; kb < nk; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+        const int HW = p.H * p.W;
+#pragma unroll 1
+        for (int kb = 0; kb < nk; ++kb) {
+            const int s = kb % STAGES;
+            mbar_wait_warp(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+            if (elect_one()) {
                 uint8_t* st = smem + s * Cfg::STAGE_BYTES;
                 mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
                 const long long p0 = pbeg + (long long)kb * WG_BP;
@@ -240,33 +242,42 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDhi, const __grid_constant
                                            (uint16_t)sx, (uint16_t)r);
                 }
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // D=f32, A=B=f16, both MN-major, N=BN, M=128
-            const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            uint32_t lo_started = 0;
-            for (int kb = 0; kb < nk; ++kb) {
-                const int s = kb % STAGES;
-                mbar_wait(&full_bar[s], (kb / STAGES) & 1);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                const uint64_t ahi = umma_desc_mn_sw128(sa, WG_BLK), alo = umma_desc_mn_sw128(sa + Cfg::OFF_ALO, WG_BLK);
-                const uint64_t bhi = umma_desc_mn_sw128(sa + Cfg::OFF_BHI, WG_BLK);
-                const uint64_t blo = umma_desc_mn_sw128(sa + Cfg::OFF_BLO, WG_BLK);
+        // D=f32, A=B=f16, both MN-major, N=BN, M=128
+        const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // MN-major 128-byte-swizzle descriptors as (lo, hi): lo = address >> 4 | (distance to the next 64-element block) >> 4 << 16
+        constexpr uint32_t HI = UMMA_DESC_HI_K_SW128;          // SBO 1024 B (next group of 8 pixels along K), version, SWIZZLE_128B
+        constexpr uint32_t LBO = (uint32_t)(WG_BLK >> 4) << 16;
+        const uint32_t smem_base = smem_u32(smem);
+#pragma unroll 1
+        for (int kb = 0; kb < nk; ++kb) {
+            const int s = kb % STAGES;
+            mbar_wait_warp(&full_bar[s], (kb / STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t ah = (((smem_base + s * Cfg::STAGE_BYTES) & 0x3FFFF) >> 4) | LBO;
+                const uint32_t al = ah + (uint32_t)(Cfg::OFF_ALO >> 4);
+                const uint32_t bh = ah + (uint32_t)(Cfg::OFF_BHI >> 4);
+                const uint32_t bl = ah + (uint32_t)(Cfg::OFF_BLO >> 4);
+                const uint32_t dhi = tmem_base + (uint32_t)((kb % NH) * BN);
+                const uint32_t dlo = tmem_base + (uint32_t)(NH * BN);
 #pragma unroll
-                for (int k = 0; k < WG_BP / 16; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 2048 >> 4);  // 16 pixels = two 8-row groups of 1024 B
-                    const uint32_t dhi = tmem_base + (uint32_t)((kb % NH) * BN);
-                    const uint32_t dlo = tmem_base + (uint32_t)(NH * BN);
-                    umma_f16(dhi, ahi + adv, bhi + adv, idesc, (kb >= NH || k > 0) ? 1u : 0u);
-                    if (TERMS & 1) { umma_f16(dlo, alo + adv, bhi + adv, idesc, lo_started); lo_started = 1u; }
-                    if (TERMS & 2) { umma_f16(dlo, ahi + adv, blo + adv, idesc, lo_started); lo_started = 1u; }
+                for (uint32_t k = 0; k < WG_BP / 16; ++k) {
+                    const uint32_t adv = k * (2048u >> 4);         // 16 pixels = two 8-row groups of 1024 B
+                    const uint32_t first_hi = (kb >= NH || k > 0) ? 1u : 0u;
+                    const uint32_t first_lo = (kb > 0 || k > 0) ? 1u : 0u;
+                    umma_f16_lohi(dhi, ah + adv, HI, bh + adv, HI, idesc, first_hi);
+                    if (TERMS & 1) umma_f16_lohi(dlo, al + adv, HI, bh + adv, HI, idesc, first_lo);
+                    if (TERMS & 2) umma_f16_lohi(dlo, ah + adv, HI, bl + adv, HI, idesc, (TERMS & 1) ? 1u : first_lo);
                 }
                 umma_commit(&empty_bar[s]);
             }
-            umma_commit(tmem_full_bar);
+            __syncwarp();
         }
+        if (elect_one()) umma_commit(tmem_full_bar);
+        __syncwarp();
     } else {
         const int quarter = warp & 3;
         const int co = co0 + quarter * 32 + lane;
@@ -451,7 +462,7 @@ struct TcPlan {
 // 128 input and output channels (short K: the im2col kernel is L2-bound there), a width that tiles by 8, little padding
 // waste in the 16-row direction and enough tiles to fill the persistent grid.  mode bit 6 switches it off.
 static bool halo_ok(int B, int H, int W, int Cin, int Cout, int ksize, int mode) {
-    if (ksize != 3 || (mode & 3) != 3 || (mode & 0x70)) return false;
+    if (ksize != 3 || (mode & 3) != 3 || (mode & 0x70)) return false;     // bit 7 (no fused MMA) does not change the plan
     if (!(Cin == 32 || Cin == 64 || Cin == 128) || Cout > 128) return false;
     if (W % HALO_TW != 0) return false;
     const int ty = ceil_div(H, HALO_TH);
@@ -624,7 +635,7 @@ static int run_halo(const void* x_hi, const void* x_lo, const void* w_hi, const 
     h.amax_a = a.amax_a; h.amax_b = a.amax_b; h.stats = a.stats; h.H = a.H; h.W = a.W; h.Cout = a.Cout; h.cpitch = a.cpitch;
     h.tiles_x = pl.tiles_x; h.tiles_y = pl.tiles_y; h.tiles_total = pl.tiles_m; h.accumulate = a.accumulate;
     const char* dbg = getenv("FSDET_HALO_FLAGS");      // developer knob (tools/halo_bench.py): see HaloArgs::flags
-    h.flags = dbg ? atoi(dbg) : 0;
+    h.flags = (dbg ? atoi(dbg) : 0) | (a.nofuse ? 4 : 0);
     const int nch = a.Cin / 32;
     if (pl.bn == 32) return launch_halo_nch<32>(nch, a_hi, a_lo, b_hi, b_lo, zmap, h, pl.grid, s);
     if (pl.bn == 64) return launch_halo_nch<64>(nch, a_hi, a_lo, b_hi, b_lo, zmap, h, pl.grid, s);
@@ -760,7 +771,7 @@ extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void*
                                  const float* amax_w, float* z, int ldz, int B, int H, int W, int Cin, int cpitch, int Cout,
                                  int ksize, int accumulate, int mode, float* stat_partial, void* stream) {
     const int terms = mode & 3;
-    FSDET_CHECK_ARG((mode & ~0x73) == 0, "conv_tc_fwd: unknown mode bits 0x%x", mode);
+    FSDET_CHECK_ARG((mode & ~0xf3) == 0, "conv_tc_fwd: unknown mode bits 0x%x", mode);
     FSDET_CHECK_ARG(x_hi && w_hi && z && (!(terms & 1) || x_lo) && (!(terms & 2) || w_lo), "conv_tc_fwd: null pointer (mode %d)", mode);
     FSDET_CHECK_ARG(fsdet_conv_tc_supported(Cin, Cout, ksize) && cpitch >= Cin && cpitch % 8 == 0,
                     "conv_tc_fwd: unsupported Cin=%d (pitch %d) Cout=%d k=%d", Cin, cpitch, Cout, ksize);
@@ -772,7 +783,7 @@ extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void*
     TcArgs a;
     a.z = z; a.amax_a = amax_x; a.amax_b = amax_w; a.stats = stat_partial; a.ldz = ldz; a.H = H; a.W = W; a.Cin = Cin;
     a.Cout = Cout; a.ks = ksize; a.pad = (ksize - 1) / 2; a.cpitch = cpitch; a.M = (long long)B * H * W;
-    a.accumulate = accumulate; a.tiles_n = a.tiles_total = 0;
+    a.accumulate = accumulate; a.tiles_n = a.tiles_total = 0; a.nofuse = (mode & 128) ? 1 : 0;
     if (a.M == 0) return 0;
     FSDET_CHECK_ARG(a.M < (1ll << 31) - 256, "conv_tc_fwd: too many pixels");
     return run_tc(x_hi, x_lo, w_hi, w_lo, B, a, mode, (cudaStream_t)stream);

@@ -48,6 +48,7 @@ struct TcArgs {
     long long M;      // B*H*W
     int accumulate;
     int tiles_n, tiles_total;
+    int nofuse;       // mode bit 7: keep A_hi * B_hi and A_hi * B_lo as two MMAs (A / B comparisons of the fused form)
 };
 
 constexpr int TC_BM = 128;
@@ -207,19 +208,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Both issuing roles run with their whole warp converged and issue under elect_one() (tc_ptx.cuh: no serialising loops
+    // around the TMA / MMA instructions, descriptors advance by one 32-bit add).
     if (warp == 0) {
-        if (lane == 0) {
-            const int HW = p.H * p.W;
-            unsigned it = 0;                                   // k-blocks issued so far (all tiles)
-            for (int tile = first_tile; tile < tiles_total; tile += tile_step) {
-                const int n_tile = tile % tiles_n;
-                const long long m0 = (long long)(tile / tiles_n) * TC_BM;
-                const int img = (int)(m0 / HW);
-                const int rem = (int)(m0 - (long long)img * HW);
-                const int ph = rem / p.W, pw = rem - ph * p.W;
-                for (int kb = 0; kb < nk; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        const int HW = p.H * p.W;
+        unsigned it = 0;                                   // k-blocks issued so far (all tiles)
+        for (int tile = first_tile; tile < tiles_total; tile += tile_step) {
+            const int n_tile = tile % tiles_n;
+            const long long m0 = (long long)(tile / tiles_n) * TC_BM;
+            const int img = (int)(m0 / HW);
+            const int rem = (int)(m0 - (long long)img * HW);
+            const int ph = rem / p.W, pw = rem - ph * p.W;
+#pragma unroll 1
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait_warp(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                if (elect_one()) {
                     uint8_t* st = smem + s * Cfg::STAGE_BYTES;
                     mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
                     const int tap = kb / kchunks;
@@ -241,51 +245,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                         if (TERMS & 2) tma_load_2d(st + Cfg::OFF_BLO, &tmBlo, &full_bar[s], tap * p.cpitch + c0, n_tile * BN);
                     }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=f16, both K-major, N=BN, M=128
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-            unsigned it = 0;
-            unsigned t = 0;                                    // tiles done by this CTA
-            for (int tile = first_tile; tile < tiles_total; tile += tile_step, ++t) {
-                const unsigned a = t % NSETS;
-                mbar_wait(&acc_empty[a], ((t / NSETS) & 1u) ^ 1u);    // the epilogue has drained this accumulator set
+        // instruction descriptors: D=f32, A=B=f16, both K-major, M=128, N=BN (and N=2*BN for the fused hi|lo MMA)
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        const uint32_t idesc2 = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        constexpr uint32_t HI = BK == 64 ? UMMA_DESC_HI_K_SW128 : UMMA_DESC_HI_K_SW64;
+        // TERMS = 3 with one hi accumulator: A_hi * [B_hi | B_lo] is ONE MMA of width 2*BN - the lo plane follows the hi
+        // plane in the stage and the lo accumulator follows the hi accumulator in TMEM (A_hi is read once, two MMAs per K step)
+        constexpr bool CAN_FUSE = TERMS == 3 && NH == 1 && 2 * BN <= 256;
+        const bool fused = CAN_FUSE && !p.nofuse;
+        const uint32_t smem_base = smem_u32(smem);
+        unsigned it = 0;
+        unsigned t = 0;                                    // tiles done by this CTA
+        for (int tile = first_tile; tile < tiles_total; tile += tile_step, ++t) {
+            const unsigned a = t % NSETS;
+            mbar_wait_warp(&acc_empty[a], ((t / NSETS) & 1u) ^ 1u);    // the epilogue has drained this accumulator set
+            tc_fence_after();
+            const uint32_t acc = tmem_base + a * (uint32_t)Cfg::ACC_COLS;
+#pragma unroll 1
+            for (int kb = 0; kb < nk; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait_warp(&full_bar[s], (it / STAGES) & 1);
                 tc_fence_after();
-                const uint32_t acc = tmem_base + a * (uint32_t)Cfg::ACC_COLS;
-                uint32_t lo_started = 0;
-                for (int kb = 0; kb < nk; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES);
-                    uint64_t ahi, alo, bhi, blo;
-                    if constexpr (BK == 64) {
-                        ahi = umma_desc_k_sw128(sa); alo = umma_desc_k_sw128(sa + Cfg::OFF_ALO);
-                        bhi = umma_desc_k_sw128(sa + Cfg::OFF_BHI); blo = umma_desc_k_sw128(sa + Cfg::OFF_BLO);
-                    } else {
-                        ahi = umma_desc_k_sw64(sa); alo = umma_desc_k_sw64(sa + Cfg::OFF_ALO);
-                        bhi = umma_desc_k_sw64(sa + Cfg::OFF_BHI); blo = umma_desc_k_sw64(sa + Cfg::OFF_BLO);
-                    }
+                if (elect_one()) {
+                    const uint32_t ah = umma_desc_lo(smem_base + s * Cfg::STAGE_BYTES);
+                    const uint32_t al = ah + (uint32_t)(Cfg::OFF_ALO >> 4);
+                    const uint32_t bh = ah + (uint32_t)(Cfg::OFF_BHI >> 4);
+                    const uint32_t bl = ah + (uint32_t)(Cfg::OFF_BLO >> 4);
+                    const uint32_t dhi = acc + (uint32_t)((kb % NH) * BN);
+                    const uint32_t dlo = acc + (uint32_t)(NH * BN);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 halves = 32 B along K inside the swizzle atom
-                        const uint32_t dhi = acc + (uint32_t)((kb % NH) * BN);
-                        const uint32_t dlo = acc + (uint32_t)(NH * BN);
-                        umma_f16(dhi, ahi + adv, bhi + adv, idesc, (kb >= NH || k > 0) ? 1u : 0u);
-                        if (TERMS & 1) { umma_f16(dlo, alo + adv, bhi + adv, idesc, lo_started); lo_started = 1u; }
-                        if (TERMS & 2) { umma_f16(dlo, ahi + adv, blo + adv, idesc, lo_started); lo_started = 1u; }
+                    for (uint32_t k = 0; k < BK / 16; ++k) {       // 16 halves = 32 B along K inside the swizzle atom: + 2 in the descriptor
+                        const uint32_t first_hi = (kb >= NH || k > 0) ? 1u : 0u;
+                        const uint32_t first_lo = (kb > 0 || k > 0) ? 1u : 0u;
+                        if (fused) {
+                            umma_f16_lohi(dhi, ah + 2 * k, HI, bh + 2 * k, HI, idesc2, first_lo);
+                            umma_f16_lohi(dlo, al + 2 * k, HI, bh + 2 * k, HI, idesc, 1u);
+                        } else {
+                            umma_f16_lohi(dhi, ah + 2 * k, HI, bh + 2 * k, HI, idesc, first_hi);
+                            if (TERMS & 1) umma_f16_lohi(dlo, al + 2 * k, HI, bh + 2 * k, HI, idesc, first_lo);
+                            if (TERMS & 2) umma_f16_lohi(dlo, ah + 2 * k, HI, bl + 2 * k, HI, idesc, (TERMS & 1) ? 1u : first_lo);
+                        }
                     }
                     if (CLUSTER == 2) umma_commit_mc(&empty_bar[s], (uint16_t)3);   // both producers write into this CTA's slot
                     else umma_commit(&empty_bar[s]);   // frees the smem slot when these MMAs have read it
                 }
-                umma_commit(&acc_full[a]);        // accumulator set complete
+                __syncwarp();
             }
+            if (elect_one()) umma_commit(&acc_full[a]);        // accumulator set complete
+            __syncwarp();
         }
     } else {
         // epilogue warps 2..5 -> TMEM lane quarters (warp % 4); each warp owns 32 output pixels of the tile
         const int quarter = warp & 3;
+        const bool leader = elect_one();                       // issues (and later waits for) this warp's TMA stores
         const float inv = 1.f / (scale_from_amax(p.amax_a ? ldg_f32(p.amax_a) : 0.f) * scale_from_amax(p.amax_b ? ldg_f32(p.amax_b) : 0.f));
         const int nhi = nk < NH ? nk : NH;
         uint8_t* stage_buf = epi + quarter * 8192;             // two 4 KB buffers per warp
@@ -331,13 +347,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                     }
                     uint8_t* buf = stage_buf + (stores & 1u) * 4096;
                     if (stores >= 2) {                         // the store that last read this buffer must have drained
-                        if (lane == 0) tma_store_wait_read<1>();
+                        if (leader) tma_store_wait_read<1>();
                         __syncwarp();
                     }
                     epi_stage_row(buf, lane, acc);
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) {
+                    if (leader) {
                         if (p.accumulate) tma_reduce_add_2d(&tmZ, buf, n0, (int)mrow);
                         else tma_store_2d(&tmZ, buf, n0, (int)mrow);
                         tma_store_commit();
@@ -356,9 +372,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
             // this warp's TMEM reads of set `a` are complete (tcgen05.wait::ld in tmem_ld32): hand the set back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[a]);
+            if (leader) mbar_arrive(&acc_empty[a]);
         }
-        if (lane == 0) tma_store_wait_read<0>();               // shared memory must outlive the bulk reads
+        if (leader) tma_store_wait_read<0>();               // shared memory must outlive the bulk reads
         __syncwarp();
         if (want_stats) {
             // fold the four warps (pixel quarters) in a fixed order and write this CTA's partial row

@@ -35,6 +35,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// the same wait executed by a whole converged warp (the issuing roles, see elect_one below)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -93,6 +95,43 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// One lane of a CONVERGED warp (elect.sync).  The issuing roles run their loops with the whole warp and put only the
+// TMA / MMA / commit instructions under `if (elect_one())`: the compiler then knows that a single thread executes them
+// and takes their operands from uniform registers directly.  Under `if (lane == 0)` it cannot know, and wraps every such
+// instruction in a serialising ELECT / R2UR / BRA.U.ANY loop - measured at ~100 clocks per tcgen05.mma issued
+// (profiles/ncu_r02b.md), i.e. issue-bound for every tile narrower than 256 columns.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// shared-memory matrix descriptors as (lo, hi) words: hi is constant per layout, lo = ((address >> 4) & 0x3fff) | LBO << 16 -
+// advancing inside a tile is one 32-bit add of (bytes >> 4) to lo (addresses < 256 KB never carry into the LBO field)
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+constexpr uint32_t UMMA_DESC_HI_K_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);      // SBO 512 B, version 1, SWIZZLE_64B
+constexpr uint32_t UMMA_DESC_HI_K_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);    // SBO 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 
 // K-major, 128-byte swizzle shared-memory matrix descriptor (tile rows of 128 B, 8-row groups 1024 B apart)

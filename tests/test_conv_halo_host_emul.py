@@ -73,6 +73,7 @@ def test_slow_epilogue(emul):
 
 
 @pytest.mark.parametrize('case', [0, 2, 4, 5])
-def test_fused_hi_lo_mma(emul, case):
-    """flags bit 2: A_hi * [B_hi | B_lo] as ONE MMA of width 2*BN into the adjacent hi / lo accumulators - same products."""
+def test_three_mma_form(emul, case):
+    """flags bit 2: the three separate MMAs per K step instead of the default pair A_hi * [B_hi | B_lo] (ONE MMA of width
+    2*BN into the adjacent hi / lo accumulators) + A_lo * B_hi - same products."""
     test_halo_kernel_control_flow(emul, *CASES[case], flags=4)

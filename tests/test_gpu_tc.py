@@ -108,7 +108,8 @@ def planes_nchw(t, B, H, W, C):
 
 # mode = operand terms (bits 0-1) | 16 for the persistent tile loop (short-K layers only; ignored by the others)
 #        | 32 for CTA pairs sharing the weight tile through TMA multicast (one-tile-per-CTA flavours)
-MODES = [3, 3 | 16, 0, 0 | 16, 1, 2, 3 | 32, 0 | 32, 2 | 32]
+#        | 128 for the unfused three-MMA form of mode 3 (default: x_hi * [w_hi | w_lo] as one MMA where one hi accumulator is kept)
+MODES = [3, 3 | 16, 0, 0 | 16, 1, 2, 3 | 32, 0 | 32, 2 | 32, 3 | 128, 3 | 16 | 128]
 
 
 @pytest.mark.parametrize('mode', MODES)
@@ -201,7 +202,7 @@ def test_conv_halo_fwd(L, B, H, W, Cin, cpitch, Cout):
     ref = (conv(xh, wh) + conv(xl, wh) + conv(xh, wl)) / (sx * sw)
     ld = Cout + 4
     outs = {}
-    for mode in (3, 3 | 64):
+    for mode in (3, 3 | 128, 3 | 64):
         z = torch.zeros(B * H * W, ld, device='cuda')
         rows = L.lib.fsdet_conv_tc_stat_rows(B, H, W, Cin, Cout, k, mode)
         part = torch.full((rows, 4 * Cout), 123.0, device='cuda')
@@ -224,6 +225,7 @@ def test_conv_halo_fwd(L, B, H, W, Cin, cpitch, Cout):
         got2 = z[:, :Cout].contiguous().view(B, H, W, Cout).permute(0, 3, 1, 2)
         assert rel(got2, 2 * ref) < TOL_TC
     assert rel(outs[3], outs[3 | 64]) < 2e-6      # same products, different accumulation order
+    assert rel(outs[3], outs[3 | 128]) < 2e-6
 
 
 def test_conv_tc_term_modes_precision(L):

@@ -86,9 +86,15 @@ static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
             if ((uint32_t)g_bars[bar].phase != parity) return;   // the phase with this parity has completed
         }
         if (g_deadlock.load()) return;
-        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) { g_deadlock.store(true); return; }
-        std::this_thread::yield();
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) { g_deadlock.store(true); return; }
+        std::this_thread::sleep_for(std::chrono::microseconds(20));   // whole warps poll (elect_one pattern): keep the lock free
     }
+}
+// whole-warp wait: OS threads are not lock-step, a slow lane could miss a complete phase flip that lane 0 already acted
+// on - so lane 0 polls and the warp converges behind it
+static inline void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+    __syncwarp();
 }
 static inline void fence_barrier_init() {}
 static inline void fence_proxy_async() {}
@@ -175,6 +181,13 @@ static inline void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uin
         }
 }
 static inline void umma_commit(uint64_t* bar) { mbar_arrive(bar); }
+// (lo, hi) descriptor words: lo = byte offset >> 4, hi = one of the layout constants (only the row pitch matters to the model)
+static inline bool elect_one() { return (threadIdx.x & 31) == 0; }
+static inline uint32_t umma_desc_lo(uint32_t saddr) { return saddr >> 4; }
+constexpr uint32_t UMMA_DESC_HI_K_SW64 = 64, UMMA_DESC_HI_K_SW128 = 128;
+static inline void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    umma_f16(tmem_d, (uint64_t)a_lo | ((uint64_t)a_hi << 32), (uint64_t)b_lo | ((uint64_t)b_hi << 32), idesc, accumulate);
+}
 static std::atomic<int> g_ld_delay_us{0};   // slows the epilogue down so that a missing accumulator hand-back shows
 static inline void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     if (g_ld_delay_us.load() > 0) std::this_thread::sleep_for(std::chrono::microseconds(g_ld_delay_us.load()));
@@ -280,7 +293,7 @@ extern "C" int emul_conv_tc(const uint16_t* x_hi, const uint16_t* x_lo, const ui
     TcArgs a;
     a.z = z; a.amax_a = amax_x; a.amax_b = amax_w; a.stats = stats; a.ldz = ldz; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout;
     a.ks = ks; a.pad = (ks - 1) / 2; a.cpitch = cpitch; a.M = (long long)B * H * W; a.accumulate = accumulate;
-    a.tiles_n = a.tiles_total = 0;
+    a.tiles_n = a.tiles_total = 0; a.nofuse = 0;
     if (bk == 32 && persist) {
         if (bn == 64) return run_terms<64, 32, 1, true, 1>(terms, x_hi, x_lo, w_hi, w_lo, a, B, ctas);
         if (bn == 128) return run_terms<128, 32, 1, true, 1>(terms, x_hi, x_lo, w_hi, w_lo, a, B, ctas);
