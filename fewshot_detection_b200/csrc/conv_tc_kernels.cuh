@@ -255,7 +255,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         constexpr uint32_t HI = BK == 64 ? UMMA_DESC_HI_K_SW128 : UMMA_DESC_HI_K_SW64;
         // TERMS = 3 with one hi accumulator: A_hi * [B_hi | B_lo] is ONE MMA of width 2*BN - the lo plane follows the hi
         // plane in the stage and the lo accumulator follows the hi accumulator in TMEM (A_hi is read once, two MMAs per K step)
-        constexpr bool CAN_FUSE = TERMS == 3 && NH == 1 && 2 * BN <= 256;
+        // With rotating hi accumulators (NH > 1, long K) the fused form keeps TWO (hi | lo) pairs [hi0 | lo0 | hi1 | lo1] -
+        // the same 4 * BN TMEM columns as [hi0 | hi1 | hi2 | lo] - and k-block kb accumulates into pair kb % 2.
+        constexpr bool CAN_FUSE = TERMS == 3 && 2 * BN <= 256 && (NH == 1 || NH == 3);
         const bool fused = CAN_FUSE && !p.nofuse;
         const uint32_t smem_base = smem_u32(smem);
         unsigned it = 0;
@@ -277,13 +279,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                     const uint32_t bl = ah + (uint32_t)(Cfg::OFF_BLO >> 4);
                     const uint32_t dhi = acc + (uint32_t)((kb % NH) * BN);
                     const uint32_t dlo = acc + (uint32_t)(NH * BN);
+                    constexpr int NP = NH == 1 ? 1 : 2;            // (hi | lo) accumulator pairs of the fused form
+                    const uint32_t dpair = acc + (uint32_t)((kb % NP) * 2 * BN);
 #pragma unroll
                     for (uint32_t k = 0; k < BK / 16; ++k) {       // 16 halves = 32 B along K inside the swizzle atom: + 2 in the descriptor
                         const uint32_t first_hi = (kb >= NH || k > 0) ? 1u : 0u;
                         const uint32_t first_lo = (kb > 0 || k > 0) ? 1u : 0u;
                         if (fused) {
-                            umma_f16_lohi(dhi, ah + 2 * k, HI, bh + 2 * k, HI, idesc2, first_lo);
-                            umma_f16_lohi(dlo, al + 2 * k, HI, bh + 2 * k, HI, idesc, 1u);
+                            umma_f16_lohi(dpair, ah + 2 * k, HI, bh + 2 * k, HI, idesc2, (kb >= NP || k > 0) ? 1u : 0u);
+                            umma_f16_lohi(dpair + BN, al + 2 * k, HI, bh + 2 * k, HI, idesc, 1u);
                         } else {
                             umma_f16_lohi(dhi, ah + 2 * k, HI, bh + 2 * k, HI, idesc, first_hi);
                             if (TERMS & 1) umma_f16_lohi(dlo, al + 2 * k, HI, bh + 2 * k, HI, idesc, first_lo);
@@ -327,6 +331,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                     const uint32_t taddr = tmem_base + a * (uint32_t)Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16) + ch * 32;
                     if constexpr (NH == 1) {
                         epi_load_scaled<TERMS != 0>(taddr, taddr + NH * BN, inv, acc);
+                    } else if (TERMS == 3 && NH == 3 && 2 * BN <= 256 && !p.nofuse) {
+                        // fused pairs [hi0 | lo0 | hi1 | lo1]: lo terms first (small), then the two hi*hi partial sums
+                        float t2[32];
+                        if (nk > 1) {
+                            epi_load_scaled<true>(taddr + BN, taddr + 3 * BN, 1.f, acc);        // lo0 + lo1
+                            epi_load_scaled<true>(taddr, taddr + 2 * BN, 1.f, t2);              // hi0 + hi1
+                        } else {                                                            // a single k-block never touches pair 1
+                            epi_load_scaled<false>(taddr + BN, 0u, 1.f, acc);
+                            epi_load_scaled<false>(taddr, 0u, 1.f, t2);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc[j] = (acc[j] + t2[j]) * inv;
                     } else {                                   // lo terms first (small), then the rotating hi*hi partial sums
                         uint32_t r[32];
                         if constexpr (TERMS != 0) {

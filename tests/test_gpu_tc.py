@@ -172,7 +172,7 @@ HALO_CASES = [
     (5, 104, 104, 64, 64, 128),     # conv3 / conv5 forward: streamed weights; 104 rows overhang the 16-row tiles
     (5, 104, 104, 128, 128, 64),    # conv3 / conv5 input gradient: four chunks
     (4, 104, 104, 128, 128, 128),
-    (13, 40, 48, 32, 32, 48),       # Cout < BN and not a multiple of 32, H not a multiple of 16
+    (17, 46, 48, 32, 32, 48),       # Cout < BN and not a multiple of 32, H not a multiple of 16
     (7, 64, 56, 64, 64, 96),
 ]
 
