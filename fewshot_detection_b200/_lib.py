@@ -27,6 +27,8 @@ SIGNATURES = {
     'fsdet_conv_wgrad': ('pipippz iiiiii p'.replace(' ', ''), 'i'),
     'fsdet_conv_wgrad_workspace_floats': ('iiiiii', 'z'),
     'fsdet_conv_first_fwd': ('pipippiiiiip', 'i'),
+    'fsdet_conv_first_stat_rows': ('iii', 'i'),
+    'fsdet_conv_first_fwd_stats': ('pipippiiiiipp', 'i'),
     'fsdet_conv_first_wgrad': ('pipipippziiiip', 'i'),
     'fsdet_conv_first_wgrad_workspace_floats': ('iiii', 'z'),
     'fsdet_conv_first_tc_supported': ('iii', 'i'),

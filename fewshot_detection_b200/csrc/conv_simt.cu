@@ -486,10 +486,14 @@ template <bool PK> __device__ __forceinline__ Px4<PK> lds_px(const float4* p) {
     Px4<PK> r; r.lo = Pair<PK>::raw(v.x); r.hi = Pair<PK>::raw(v.y);
     return r;
 }
-template <bool PK>
+// STATS: the BatchNorm partial row of this CTA (sum | sum of squares | min | max per channel, the layout
+// fsdet_bn_finalize reads) is taken from the values while they are in registers - a thread owns ONE output channel, so
+// there is nothing to transpose - instead of a separate pass over the 1.4 GB tensor (fsdet_colstats).
+template <bool PK, bool STATS>
 __global__ void __launch_bounds__(256, 2) conv_first_fwd_kernel(const float* __restrict__ in0, int C0, const float* __restrict__ in1,
                                                                 int C1, const float* __restrict__ w /* [Cout][9][4] */,
-                                                                float* __restrict__ z, int ldz, int B, int H, int W, int Cout) {
+                                                                float* __restrict__ z, int ldz, int B, int H, int W, int Cout,
+                                                                float* __restrict__ stats) {
     __shared__ float4 xs[2][FT_NPX];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tiles_w = (W + FT_W - 1) / FT_W, tiles_h = (H + FT_H - 1) / FT_H;
@@ -537,6 +541,7 @@ __global__ void __launch_bounds__(256, 2) conv_first_fwd_kernel(const float* __r
         wr[k].lo = Pair<PK>::make(v.x, v.y); wr[k].hi = Pair<PK>::make(v.z, v.w);
     }
     const bool cok = lane < Cout;
+    float tsum = 0.f, esum = 0.f, tsq = 0.f, esq = 0.f, tmn = INFINITY, tmx = -INFINITY;   // this thread's channel, all its pixels
     int buf = 0;
     if ((int)blockIdx.x < tiles) stage(blockIdx.x, 0);
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, buf ^= 1) {
@@ -567,9 +572,12 @@ __global__ void __launch_bounds__(256, 2) conv_first_fwd_kernel(const float* __r
         FSDET_TAP(A1, 3) FSDET_TAP(B1, 4) FSDET_TAP(C1_, 5)                                                \
         FSDET_TAP(A2, 6) FSDET_TAP(B2, 7) FSDET_TAP(C2_, 8)                                                \
         const float2 l = alo.get(), u = ahi.get();                                                        \
-        if (cok) *zr = (l.x + l.y) + (u.x + u.y);                                                         \
+        const float v = (l.x + l.y) + (u.x + u.y);                                                        \
+        if (cok) *zr = v;                                                                                 \
+        if (STATS) { rs += v; rq = fmaf(v, v, rq); tmn = fminf(tmn, v); tmx = fmaxf(tmx, v); }            \
         zr += ldz;                                                                                        \
     }
+        float rs = 0.f, rq = 0.f;     // this row run (<= FT_W pixels), folded into the compensated totals below
         int c = 0;
 #pragma unroll 1
         for (; c + 3 <= wn; c += 3) {
@@ -583,6 +591,28 @@ __global__ void __launch_bounds__(256, 2) conv_first_fwd_kernel(const float* __r
         }
 #undef FSDET_PIXEL
 #undef FSDET_TAP
+        if (STATS) {
+            float y = rs - esum, t2 = tsum + y;
+            esum = (t2 - tsum) - y; tsum = t2;
+            y = rq - esq; t2 = tsq + y;
+            esq = (t2 - tsq) - y; tsq = t2;
+        }
+    }
+    if (STATS) {
+        __shared__ float4 red[8][32];
+        __syncthreads();
+        red[warp][lane] = make_float4(tsum - esum, tsq - esq, tmn, tmx);
+        __syncthreads();
+        if (warp == 0 && cok) {
+            float4 tt = red[0][lane];
+#pragma unroll
+            for (int q = 1; q < 8; ++q) {
+                const float4 o = red[q][lane];
+                tt.x += o.x; tt.y += o.y; tt.z = fminf(tt.z, o.z); tt.w = fmaxf(tt.w, o.w);
+            }
+            float* dst = stats + (long long)blockIdx.x * 4 * Cout + lane;
+            dst[0] = tt.x; dst[Cout] = tt.y; dst[2 * Cout] = tt.z; dst[3 * Cout] = tt.w;
+        }
     }
 }
 
@@ -843,8 +873,28 @@ extern "C" int fsdet_conv_first_fwd(const float* in0, int C0, const float* in1, 
     FSDET_CHECK_ARG(tiles < (1ll << 31), "conv_first_fwd: too many tiles");
     const unsigned ctas = (unsigned)(tiles < 2LL * kNumSMs ? tiles : 2LL * kNumSMs);
     // packed FFMA2 flavour: fewer issue slots per pixel (measured 705 us vs 750 us at B=64, 416x416)
-    conv_first_fwd_kernel<true><<<ctas, 256, 0, (cudaStream_t)stream>>>(in0, C0, in1, C1, w_pad4, z, ldz, B, H, W, Cout);
+    conv_first_fwd_kernel<true, false><<<ctas, 256, 0, (cudaStream_t)stream>>>(in0, C0, in1, C1, w_pad4, z, ldz, B, H, W, Cout, nullptr);
     return launch_status("conv_first_fwd");
+}
+
+extern "C" int fsdet_conv_first_stat_rows(int B, int H, int W) {
+    long long tiles = (long long)B * ceil_div(H, FT_H) * ceil_div(W, FT_W);
+    return (int)(tiles < 2LL * kNumSMs ? tiles : 2LL * kNumSMs);
+}
+
+extern "C" int fsdet_conv_first_fwd_stats(const float* in0, int C0, const float* in1, int C1, const float* w_pad4, float* z, int ldz,
+                                          int B, int H, int W, int Cout, float* stat_partial, void* stream) {
+    FSDET_CHECK_ARG(in0 && w_pad4 && z && stat_partial && C0 > 0 && C1 >= 0 && (C1 == 0 || in1) && C0 + C1 <= 4,
+                    "conv_first_fwd_stats: bad inputs");
+    FSDET_CHECK_ARG(Cout > 0 && Cout <= 32 && Cout % 4 == 0 && ldz % 4 == 0 && aligned16(z) && aligned16(w_pad4),
+                    "conv_first_fwd_stats: Cout=%d ldz=%d", Cout, ldz);
+    long long tiles = (long long)B * ceil_div(H, FT_H) * ceil_div(W, FT_W);
+    if (tiles == 0) return 0;
+    FSDET_CHECK_ARG(tiles < (1ll << 31), "conv_first_fwd_stats: too many tiles");
+    const unsigned ctas = (unsigned)fsdet_conv_first_stat_rows(B, H, W);
+    conv_first_fwd_kernel<true, true><<<ctas, 256, 0, (cudaStream_t)stream>>>(in0, C0, in1, C1, w_pad4, z, ldz, B, H, W, Cout,
+                                                                              stat_partial);
+    return launch_status("conv_first_fwd_stats");
 }
 
 extern "C" int fsdet_conv_first_wgrad(const float* in0, int C0, const float* in1, int C1, const float* dz, int lddz, float* dw,

@@ -791,12 +791,14 @@ extern "C" int fsdet_conv_tc_fwd(const void* x_hi, const void* x_lo, const void*
 
 // tile shape of the weight-gradient kernel: Cin <= 64 packs two filter taps into one 128-wide N tile; the plain
 // fp16 x fp16 mode (terms == 0) uses 256-wide N tiles where the layer has the channels (operand bytes per FLOP halve)
-static inline int wg_bn(int Cin, int terms) { return (terms == 0 && Cin >= 256) ? 256 : 128; }
-static inline int wg_cib(int Cin, int terms) { return Cin >= 128 ? wg_bn(Cin, terms) : 64; }
-static inline int wg_taps(int Cin) { return Cin >= 128 ? 1 : 2; }
+// (a tcgen05.mma narrower than 256 columns does not run faster than ~100 clocks - the 128 x 16 A tile it reads from shared
+// memory paces it - so the fp16 x fp16 mode always uses 256-wide tiles: 1, 2 or 4 filter taps side by side)
+static inline int wg_bn(int Cin, int terms) { return terms == 0 ? 256 : 128; }
+static inline int wg_taps(int Cin, int terms) { return terms == 0 ? (Cin >= 256 ? 1 : (Cin >= 128 ? 2 : 4)) : (Cin >= 128 ? 1 : 2); }
+static inline int wg_cib(int Cin, int terms) { return wg_bn(Cin, terms) / wg_taps(Cin, terms); }
 
 static int wg_splits(long long M, int Cin, int Cout, int ks, int terms) {
-    const int cib = wg_cib(Cin, terms), taps = wg_taps(Cin);
+    const int cib = wg_cib(Cin, terms), taps = wg_taps(Cin, terms);
     long long tiles = (long long)((Cin + cib - 1) / cib) * ((ks * ks + taps - 1) / taps) * ((Cout + 127) / 128);
     long long want = (2LL * kNumSMs + tiles - 1) / tiles;
     long long maxs = (M + 511) / 512;  // at least 512 pixels (8 stages) per split
@@ -891,9 +893,16 @@ extern "C" int fsdet_conv_tc_wgrad(const void* x_hi, const void* x_lo, const voi
         if (rc) return rc;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    if (Cin < 128) rc = launch_wg_terms<2>(terms, dhi, dlo, xhi, xlo, a, splits, s);
-    else if (wg_bn(Cin, terms) == 256) rc = launch_wg<256, 1, 0, 2>(dhi, dlo, xhi, xlo, a, splits, s);
-    else rc = launch_wg_terms<1>(terms, dhi, dlo, xhi, xlo, a, splits, s);
+    if (terms == 0) {
+        const int taps = wg_taps(Cin, 0);
+        if (taps == 1) rc = launch_wg<256, 1, 0, 2>(dhi, dlo, xhi, xlo, a, splits, s);
+        else if (taps == 2) rc = launch_wg<256, 2, 0, 2>(dhi, dlo, xhi, xlo, a, splits, s);
+        else rc = launch_wg<256, 4, 0, 2>(dhi, dlo, xhi, xlo, a, splits, s);
+    } else if (Cin < 128) {
+        rc = launch_wg_terms<2>(terms, dhi, dlo, xhi, xlo, a, splits, s);
+    } else {
+        rc = launch_wg_terms<1>(terms, dhi, dlo, xhi, xlo, a, splits, s);
+    }
     if (rc) return rc;
     if (splits > 1) {
         long long n4 = (long long)Cout * ksize * ksize * Cin / 4;

@@ -351,11 +351,12 @@ class NetRunner(object):
         if x.nchw is not None:
             in0, c0, in1, c1 = x.nchw
             assert bias is None and not acc and cin == 4 and k == 3
+            if stat_rows_out is not None:   # BatchNorm partial rows straight from the kernel's registers (no pass over z)
+                self._timed('first_fwd', flops, 'fsdet_conv_first_fwd_stats', ptr(in0), c0, ptr(in1), c1, ptr(w_ohwi), z.ptr, z.ld,
+                            x.B, x.H, x.W, cout, ptr(stat_rows_out), st)
+                return _lib.lib.fsdet_conv_first_stat_rows(x.B, x.H, x.W)
             self._timed('first_fwd', flops, 'fsdet_conv_first_fwd', ptr(in0), c0, ptr(in1), c1, ptr(w_ohwi), z.ptr, z.ld, x.B, x.H,
                         x.W, cout, st)
-            if stat_rows_out is not None:
-                call('fsdet_colstats', z.ptr, z.ld, x.npix, cout, ptr(stat_rows_out), st)
-                return _lib.lib.fsdet_colstats_rows(x.npix)
             return 0
         if bias is None and name in TC_PARTS and self._tc_ok(cin, cout, k):
             cpad = _round_up(cin, 64)
@@ -630,7 +631,7 @@ class NetRunner(object):
             assert cout_p == s.cout, 'BatchNorm conv with Cout % 4 != 0 is unsupported'
             z = Act.new(B, H, W, s.cout, dev)
             use_batch_stats = training or not bn.track_running_stats
-            rows_cap = max(_lib.lib.fsdet_conv_stat_rows(npix), _lib.lib.fsdet_colstats_rows(npix), (npix + 127) // 128 + 1)
+            rows_cap = max(_lib.lib.fsdet_conv_stat_rows(npix), _lib.lib.fsdet_colstats_rows(npix), (npix + 127) // 128 + 1, 2 * 148)
             stat = _empty(rows_cap + _lib.lib.fsdet_bn_stat_scratch_rows(), 4 * s.cout, device=dev) if use_batch_stats else None
             wp = getattr(self, '_wp', {}).get(id(wuse))
             rows = self._conv('fwd', x, wuse, None, z, stat, cin_p, s.cout, s.k, 0, st, wplanes=wp['fwd'] if wp else None)

@@ -79,6 +79,11 @@ size_t fsdet_conv_wgrad_workspace_floats(int B, int H, int W, int Cin, int Cout,
  * HBM-bound kernels; workspace float [fsdet_conv_first_wgrad_workspace_floats()]. */
 int fsdet_conv_first_fwd(const float* in0, int C0, const float* in1, int C1, const float* w_pad4, float* z, int ldz,
                          int B, int H, int W, int Cout, void* stream);
+/* The same convolution with the train-mode BatchNorm partial rows taken from the values in registers: stat_partial float
+ * [fsdet_conv_first_stat_rows(B, H, W)][4*Cout] = (sum | sum of squares | min | max) per CTA - no fsdet_colstats pass. */
+int fsdet_conv_first_stat_rows(int B, int H, int W);
+int fsdet_conv_first_fwd_stats(const float* in0, int C0, const float* in1, int C1, const float* w_pad4, float* z, int ldz,
+                               int B, int H, int W, int Cout, float* stat_partial, void* stream);
 int fsdet_conv_first_wgrad(const float* in0, int C0, const float* in1, int C1, const float* dz, int lddz, float* dw,
                            float* workspace, size_t workspace_floats, int B, int H, int W, int Cout, void* stream);
 size_t fsdet_conv_first_wgrad_workspace_floats(int B, int H, int W, int Cout);

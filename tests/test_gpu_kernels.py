@@ -291,6 +291,18 @@ def test_conv_first_layer_fwd_wgrad(L, B, H, W, Cout, C0, C1):
     L.call('fsdet_conv_first_fwd', a.data_ptr(), C0, m.data_ptr() if C1 else None, C1, wp.data_ptr(), z.data_ptr(), Cout, B, H, W,
            Cout, st())
     assert rel(nchw(z, B, H, W), ref) < 1e-5
+    # the flavour that also emits the BatchNorm partial rows: same z bit for bit, statistics of exactly that z
+    z2 = torch.empty(B * H * W, Cout + 4, device='cuda')
+    rows = L.lib.fsdet_conv_first_stat_rows(B, H, W)
+    part = torch.full((rows, 4 * Cout), 123.0, device='cuda')
+    L.call('fsdet_conv_first_fwd_stats', a.data_ptr(), C0, m.data_ptr() if C1 else None, C1, wp.data_ptr(), z2.data_ptr(), Cout + 4,
+           B, H, W, Cout, part.data_ptr(), st())
+    assert torch.equal(z2[:, :Cout], z)
+    sp = part.double().sum(0)
+    assert rel(sp[:Cout], z.double().sum(0)) < 1e-5 or (sp[:Cout] - z.double().sum(0)).abs().max() < 1e-3
+    assert rel(sp[Cout:2 * Cout], (z.double() ** 2).sum(0)) < 1e-5
+    assert torch.equal(part[:, 2 * Cout:3 * Cout].min(0)[0], z.min(0)[0])
+    assert torch.equal(part[:, 3 * Cout:].max(0)[0], z.max(0)[0])
     dzb = nhwc(dz)
     nws = L.lib.fsdet_conv_first_wgrad_workspace_floats(B, H, W, Cout)
     ws = torch.empty(nws, device='cuda')

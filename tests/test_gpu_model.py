@@ -195,7 +195,10 @@ def test_tiny_mini_train_step_vs_oracle(path):
     from oracle import darknet as ODK, region_loss as ORL
     from seeding import seeded_init, synth_targets
     blocks = netcfg.mini_tiny_blocks(128, 8)
-    x = torch.rand(3, 3, 128, 128, generator=torch.Generator().manual_seed(6))
+    # input seed 7: with seed 6 one 2x2 max-pool window of the 4x4 map holds a near tie - any change of the float32 summation
+    # order flips its arg-max and moves 1/4096 of the gradient paths (1e-2 on every earlier layer; tools/diag_mini.py prints
+    # seeds 6..11: 6 is the only one, and only after the BatchNorm statistics' summation order changed)
+    x = torch.rand(3, 3, 128, 128, generator=torch.Generator().manual_seed(7))
     tgt = torch.from_numpy(synth_targets(3, 1, 7, max_gt=4)[:, 0, :])
     tgt[:, 0::5] = torch.floor(tgt[:, 0::5] * 0) + (torch.arange(50) % 20).double()  # class ids < 20
 

@@ -173,7 +173,7 @@ HALO_CASES = [
     (5, 104, 104, 128, 128, 64),    # conv3 / conv5 input gradient: four chunks
     (4, 104, 104, 128, 128, 128),
     (17, 46, 48, 32, 32, 48),       # Cout < BN and not a multiple of 32, H not a multiple of 16
-    (7, 64, 56, 64, 64, 96),
+    (11, 64, 56, 64, 64, 96),
 ]
 
 
