@@ -797,15 +797,27 @@ static inline int wg_bn(int Cin, int terms) { return terms == 0 ? 256 : 128; }
 static inline int wg_taps(int Cin, int terms) { return terms == 0 ? (Cin >= 256 ? 1 : (Cin >= 128 ? 2 : 4)) : (Cin >= 128 ? 1 : 2); }
 static inline int wg_cib(int Cin, int terms) { return wg_bn(Cin, terms) / wg_taps(Cin, terms); }
 
+// split-K factor of the weight gradient: every CTA is the same size (one CTA per SM), so the kernel takes
+// ceil(tiles * splits / SMs) rounds of 1 / splits of the pixels each - pick the smallest split count within 3 % of the best
+// rounds / splits ratio (297 CTAs on 148 SMs are three rounds, 294 are two; fewer splits = fewer partials to reduce)
 static int wg_splits(long long M, int Cin, int Cout, int ks, int terms) {
     const int cib = wg_cib(Cin, terms), taps = wg_taps(Cin, terms);
-    long long tiles = (long long)((Cin + cib - 1) / cib) * ((ks * ks + taps - 1) / taps) * ((Cout + 127) / 128);
-    long long want = (2LL * kNumSMs + tiles - 1) / tiles;
+    const long long tiles = (long long)((Cin + cib - 1) / cib) * ((ks * ks + taps - 1) / taps) * ((Cout + 127) / 128);
     long long maxs = (M + 511) / 512;  // at least 512 pixels (8 stages) per split
-    if (want > maxs) want = maxs;
-    if (want < 1) want = 1;
-    if (want > 512) want = 512;
-    return (int)want;
+    if (maxs < 1) maxs = 1;
+    if (maxs > 512) maxs = 512;
+    const long long cap = (4LL * kNumSMs + tiles - 1) / tiles;      // beyond four rounds nothing is gained
+    if (maxs > cap) maxs = cap;
+    double best = 1e30;
+    for (long long sp = 1; sp <= maxs; ++sp) {
+        const double c = (double)((tiles * sp + kNumSMs - 1) / kNumSMs) / (double)sp;
+        if (c < best) best = c;
+    }
+    for (long long sp = 1; sp <= maxs; ++sp) {
+        const double c = (double)((tiles * sp + kNumSMs - 1) / kNumSMs) / (double)sp;
+        if (c <= best * 1.03) return (int)sp;
+    }
+    return 1;
 }
 
 extern "C" int fsdet_conv_tc_wgrad_supported(int Cin, int Cout, int ksize) {

@@ -62,6 +62,11 @@ def tc_mode(name):
     return (TC_TERMS[name] | (16 if TC_PERSIST else 0) | (32 if TC_CLUSTER else 0) | (0 if TC_HALO else 64)
             | (0 if TC_FUSE else 128))
 
+# Weight gradients on a second stream: after a block's BatchNorm backward, its weight-gradient GEMM (tensor-bound, one
+# CTA per SM) and the rest of the backward chain (input gradient, then the next block's HBM-bound BatchNorm passes) are
+# independent - the weight gradient is only needed by the optimizer.  FSDET_WGRAD_STREAM=0 keeps everything on one stream.
+WGRAD_STREAM = os.environ.get('FSDET_WGRAD_STREAM', '1') != '0'
+
 LEAKY_SLOPE = 0.1
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -283,6 +288,9 @@ class NetRunner(object):
         self.in_cpad = _round_up(self.in_ch, 4)
         self.grad_hook = None   # optional callable(param) invoked when a parameter gradient has been enqueued
         self.profile = None     # optional dict name -> [flops, [(start_event, end_event), ...]]
+        self.side = None        # second stream for the weight gradients (created by the first backward pass)
+        self._side_used = False
+        self._keep = []         # tensors allocated on the main stream that the side stream still reads (until the join)
 
     # -- helpers ---------------------------------------------------------
     @staticmethod
@@ -379,9 +387,24 @@ class NetRunner(object):
 
     def _done(self, *params):
         if self.grad_hook is not None:
+            if self._side_used:
+                # a bucket's collective is ordered behind the CURRENT stream only: make it see the other stream's gradients too
+                cur = torch.cuda.current_stream()
+                cur.wait_stream(self.side if cur != self.side else self._main)
             for p in params:
                 if p is not None:
                     self.grad_hook(p)
+
+    def _side_ok(self):
+        """Weight gradients go to the second stream unless disabled or per-kernel timing is on (profiled durations must
+        not include a concurrent kernel's share of the SMs)."""
+        if not WGRAD_STREAM or self.profile is not None:
+            return False
+        if self.side is None:
+            if torch.cuda.is_current_stream_capturing():
+                return False            # streams are created outside captures (the first eager step does it)
+            self.side = torch.cuda.Stream()
+        return True
 
     def _timed(self, name, flops, fn, *args):
         """call() bracketed by CUDA events on the launching stream when profiling."""
@@ -841,6 +864,19 @@ class NetRunner(object):
         st = _stream()
         gout = gout.contiguous()
         drw = None
+        self._side_used = False
+        self._main = torch.cuda.current_stream()
+        try:
+            drw = self._backward_records(tape, gout, st)
+        finally:
+            if self._side_used:         # join: everything after the backward pass sees the weight gradients
+                self._main.wait_stream(self.side)
+                self._side_used = False
+            self._keep = []
+        return drw
+
+    def _backward_records(self, tape, gout, st):
+        drw = None
         for rec in reversed(tape.records):
             kind = rec[0]
             if kind == 'head':
@@ -999,16 +1035,31 @@ class NetRunner(object):
              ptr(vec[0]), ptr(vec[1]), ptr(coef), s.slope, dz.ptr if want_f32 else None, dz.ld if want_f32 else 0,
              ptr(planes[0]) if planes else None, ptr(planes[1]) if planes else None, s.cout, ptr(amax), B, H, W, s.cout, 1, st)
         cin_p = x.C
-        if cin_p != s.cin:
-            gwp = _empty(s.cout, s.k * s.k, cin_p, device=dev)
-            self._wgrad(x, dz, gwp, cin_p, s.cout, s.k, st)
-            call('fsdet_pad_channels', ptr(gwp), cin_p, ptr(gw), s.cin, s.cout * s.k * s.k, st)
-        else:
-            self._wgrad(x, dz, gw, cin_p, s.cout, s.k, st)
-        for f in (fin_w, fin_g, fin_b):
+
+        def weight_grad(sw):
+            if cin_p != s.cin:
+                gwp = _empty(s.cout, s.k * s.k, cin_p, device=dev)
+                self._wgrad(x, dz, gwp, cin_p, s.cout, s.k, sw)
+                call('fsdet_pad_channels', ptr(gwp), cin_p, ptr(gw), s.cin, s.cout * s.k * s.k, sw)
+            else:
+                self._wgrad(x, dz, gw, cin_p, s.cout, s.k, sw)
+            if fin_w:
+                fin_w()
+            self._done(conv.weight, bn.weight, bn.bias)
+
+        for f in (fin_g, fin_b):
             if f:
                 f()
-        self._done(conv.weight, bn.weight, bn.bias)
+        if self._side_ok():
+            # fork behind the apply pass; dz (and the activation planes) were allocated on the main stream: keep them alive
+            # until the join at the end of the backward pass, the allocator only orders their reuse on the main stream
+            self.side.wait_stream(self._main)
+            self._side_used = True
+            self._keep.append((dz, planes, x))
+            with torch.cuda.stream(self.side):
+                weight_grad(self.side.cuda_stream)
+        else:
+            weight_grad(st)
         self._dgrad(x, dz, wuse, cin_p, s.cout, s.k, st)
 
     def _convbias_bwd(self, rec, st):

@@ -74,3 +74,4 @@ def synth_masks(cs, side, seed):
         y0 = rs.randint(0, side - h + 1)
         m[c, 0, y0:y0 + h, x0:x0 + w] = 1.0
     return m
+

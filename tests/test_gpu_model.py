@@ -189,20 +189,24 @@ def test_tiny_yolo_416_config1_vs_reference(path):
 
 
 def test_tiny_mini_train_step_vs_oracle(path):
-    """Plain Darknet + RegionLoss backward (maxpool stride 1, 125-channel head) vs the oracle (float64 truth)."""
+    """Plain Darknet + RegionLoss backward (maxpool stride 1, 125-channel head) vs the oracle (float64 truth).
+
+    Gradients are discontinuous in the max-pool arg-max: with ~2e5 pooling windows per pass the closest pair of competitors
+    is typically 1e-6 apart (relative), the size of ANY float32 implementation's forward error, so about one input in
+    six re-routes one window - and on the 4x4 maps of this model one re-routed window moves every earlier layer's
+    gradient by ~1e-2 (tools/diag_mini.py; the float32 oracle does the same on other seeds).  Forward and loss parity are
+    therefore asserted on every seed, the parameter gradients on the MEDIAN over five input seeds: an arithmetic error
+    shows on all of them, a flip on one."""
     from fewshot_detection_b200 import netcfg
     from fewshot_detection_b200.darknet import Darknet
+    from fewshot_detection_b200.cfg import cfg
     from oracle import darknet as ODK, region_loss as ORL
     from seeding import seeded_init, synth_targets
     blocks = netcfg.mini_tiny_blocks(128, 8)
-    # input seed 7: with seed 6 one 2x2 max-pool window of the 4x4 map holds a near tie - any change of the float32 summation
-    # order flips its arg-max and moves 1/4096 of the gradient paths (1e-2 on every earlier layer; tools/diag_mini.py prints
-    # seeds 6..11: 6 is the only one, and only after the BatchNorm statistics' summation order changed)
-    x = torch.rand(3, 3, 128, 128, generator=torch.Generator().manual_seed(7))
     tgt = torch.from_numpy(synth_targets(3, 1, 7, max_gt=4)[:, 0, :])
     tgt[:, 0::5] = torch.floor(tgt[:, 0::5] * 0) + (torch.arange(50) % 20).double()  # class ids < 20
 
-    def run_oracle(dtype):
+    def run_oracle(dtype, x):
         om = ODK.PlainDarknet([dict(b) for b in blocks])
         seeded_init(om, 5)
         om = om.to(dtype).train()
@@ -213,27 +217,34 @@ def test_tiny_mini_train_step_vs_oracle(path):
         oo.backward(o32.grad.to(dtype))
         return oo.detach().double(), lo.item(), {n: p.grad.detach().double() for n, p in om.named_parameters()}
 
-    o64, l64, g64 = run_oracle(torch.float64)
-    o32, l32, g32 = run_oracle(torch.float32)
-    m = Darknet([dict(b) for b in blocks])
-    seeded_init(m, 5)
-    m = m.cuda().train()
-    from fewshot_detection_b200.cfg import cfg
-    cfg.metayolo = False
-    try:
-        out = m(x.cuda())
-        L = m.models[len(m.models) - 1]
-        L.seen = 20000
-        loss = L(out, tgt)
-        loss.backward()
-    finally:
-        cfg.metayolo = True
-    assert relt(out.detach().cpu(), o64) < TOL
-    assert abs(loss.item() - l64) < TOL * abs(l64)
-    for n, p in m.named_parameters():
-        e_ours = relt(p.grad.detach().cpu().contiguous(), g64[n])
-        e_ref = relt(g32[n], g64[n])
-        assert e_ours < max(TOL, (2 if path == 'fp32' else TC_GRAD_FACTOR) * max(e_ref, 1e-4)), (n, e_ours, e_ref)
+    ratios = []
+    for seed in range(6, 11):
+        x = torch.rand(3, 3, 128, 128, generator=torch.Generator().manual_seed(seed))
+        o64, l64, g64 = run_oracle(torch.float64, x)
+        o32, l32, g32 = run_oracle(torch.float32, x)
+        m = Darknet([dict(b) for b in blocks])
+        seeded_init(m, 5)
+        m = m.cuda().train()
+        cfg.metayolo = False
+        try:
+            out = m(x.cuda())
+            L = m.models[len(m.models) - 1]
+            L.seen = 20000
+            loss = L(out, tgt)
+            loss.backward()
+        finally:
+            cfg.metayolo = True
+        assert relt(out.detach().cpu(), o64) < TOL, seed
+        assert abs(loss.item() - l64) < TOL * abs(l64), seed
+        worst = (0.0, '')
+        for n, p in m.named_parameters():
+            e_ours = relt(p.grad.detach().cpu().contiguous(), g64[n])
+            e_ref = relt(g32[n], g64[n])
+            bar = max(TOL, (2 if path == 'fp32' else TC_GRAD_FACTOR) * max(e_ref, 1e-4))
+            worst = max(worst, (e_ours / bar, n))
+        ratios.append(worst)
+    print('worst (error / bar) per input seed:', ratios)
+    assert sorted(r for r, _ in ratios)[len(ratios) // 2] < 1.0, ratios
 
 
 def test_train_steps_match_oracle_sgd(path):
@@ -242,7 +253,10 @@ def test_train_steps_match_oracle_sgd(path):
     order of magnitude for this batch (train_meta.py:143-147 divides by batch size and lr factor): at 1e-3 on a
     summed loss of ~200 every step moves the weights by O(1) and the trajectory is chaotic - a 5e-4 gradient
     difference becomes a 5 % loss difference two steps later, whatever the arithmetic.  Compared: the losses
-    (1e-3) and the parameter UPDATE p - p0 (relative L2 per tensor; p itself would match trivially)."""
+    (1e-3) and the parameter UPDATE p - p0 (relative L2 per tensor; p itself would match trivially).
+    As in test_tiny_mini_train_step_vs_oracle a max-pool arg-max flip in any of the three steps (likely: ~1 in 6 per pass
+    for any float32 arithmetic) moves the updates of the layers below it by ~1e-2: the losses are asserted on every batch
+    seed, the updates on the best two of three batch seeds."""
     from fewshot_detection_b200 import netcfg
     from fewshot_detection_b200.optim import FusedSGD
     from oracle import darknet as ODK, region_loss as ORL
@@ -250,56 +264,60 @@ def test_train_steps_match_oracle_sgd(path):
     det, ler = netcfg.mini_dynamic_blocks(128, 4), netcfg.mini_reweighting_blocks(64, 4, 128)
     bs, cs = 4, 3
     LR = 2e-5
+    results = []
+    for base in (100, 400, 700):
+        def batch(it):
+            g = torch.Generator().manual_seed(base + it)
+            x = torch.rand(bs, 3, 128, 128, generator=g)
+            metax = torch.rand(cs, 3, 64, 64, generator=g)
+            return (x, metax, torch.from_numpy(synth_masks(cs, 64, base + 100 + it)),
+                    torch.from_numpy(synth_targets(bs, cs, base + 200 + it, max_gt=4)))
 
-    def batch(it):
-        g = torch.Generator().manual_seed(100 + it)
-        x = torch.rand(bs, 3, 128, 128, generator=g)
-        metax = torch.rand(cs, 3, 64, 64, generator=g)
-        return x, metax, torch.from_numpy(synth_masks(cs, 64, 200 + it)), torch.from_numpy(synth_targets(bs, cs, 300 + it, max_gt=4))
+        def run_oracle(dtype):
+            om = ODK.MetaDarknet([dict(b) for b in det], [dict(b) for b in ler])
+            seeded_init(om, 11)
+            om = om.to(dtype).train()
+            p0 = {n: p.detach().double().clone() for n, p in om.named_parameters()}
+            oo = torch.optim.SGD(om.parameters(), lr=LR, momentum=0.9, dampening=0, weight_decay=5e-4)
+            losses = []
+            for it in range(3):
+                x, metax, mask, tgt = batch(it)
+                oo.zero_grad()
+                out = om(x.to(dtype), metax.to(dtype), mask.to(dtype))
+                o32 = out.detach().float().requires_grad_(True)
+                lo = ORL.region_loss_v2(o32, tgt, om.anchors, 5, 1, seen=20000 + it * bs)
+                lo.backward()
+                out.backward(o32.grad.to(dtype))
+                oo.step()
+                losses.append(lo.item())
+            return losses, {n: p.detach().double() - p0[n] for n, p in om.named_parameters()}
 
-    def run_oracle(dtype):
-        om = ODK.MetaDarknet([dict(b) for b in det], [dict(b) for b in ler])
-        seeded_init(om, 11)
-        om = om.to(dtype).train()
-        p0 = {n: p.detach().double().clone() for n, p in om.named_parameters()}
-        oo = torch.optim.SGD(om.parameters(), lr=LR, momentum=0.9, dampening=0, weight_decay=5e-4)
-        losses = []
+        l64, d64 = run_oracle(torch.float64)
+        l32, d32 = run_oracle(torch.float32)
+        m = _meta(det, ler, 11)
+        p0 = {n: p.detach().double().cpu().contiguous().clone() for n, p in m.named_parameters()}
+        og = FusedSGD(m.parameters(), lr=LR, momentum=0.9, dampening=0, weight_decay=5e-4)
+        L = m.models[len(m.models) - 1]
+        L.verbose = False
         for it in range(3):
             x, metax, mask, tgt = batch(it)
-            oo.zero_grad()
-            out = om(x.to(dtype), metax.to(dtype), mask.to(dtype))
-            o32 = out.detach().float().requires_grad_(True)
-            lo = ORL.region_loss_v2(o32, tgt, om.anchors, 5, 1, seen=20000 + it * bs)
-            lo.backward()
-            out.backward(o32.grad.to(dtype))
-            oo.step()
-            losses.append(lo.item())
-        return losses, {n: p.detach().double() - p0[n] for n, p in om.named_parameters()}
-
-    l64, d64 = run_oracle(torch.float64)
-    l32, d32 = run_oracle(torch.float32)
-    m = _meta(det, ler, 11)
-    p0 = {n: p.detach().double().cpu().contiguous().clone() for n, p in m.named_parameters()}
-    og = FusedSGD(m.parameters(), lr=LR, momentum=0.9, dampening=0, weight_decay=5e-4)
-    L = m.models[len(m.models) - 1]
-    L.verbose = False
-    for it in range(3):
-        x, metax, mask, tgt = batch(it)
-        og.zero_grad()
-        L.seen = 20000 + it * bs
-        lg = L(m(x.cuda(), metax.cuda(), mask.cuda()), tgt)
-        lg.backward()
-        og.step()
-        assert abs(lg.item() - l64[it]) < TOL * abs(l64[it]), it
-    worst = 0.0
-    for n, p in m.named_parameters():
-        upd = p.detach().double().cpu().contiguous() - p0[n]
-        e_ours = relt(upd, d64[n])
-        e_ref = relt(d32[n], d64[n])
-        worst = max(worst, e_ours)
-        # fp32 kernels: like the float32 oracle; shipped policy: + the fp16 x fp16 weight gradient (<= 6e-4 per step)
-        assert e_ours < max(TOL if path == 'fp32' else 2 * TOL, 3 * e_ref), (n, e_ours, e_ref)
-    print('worst update error', worst)
+            og.zero_grad()
+            L.seen = 20000 + it * bs
+            lg = L(m(x.cuda(), metax.cuda(), mask.cuda()), tgt)
+            lg.backward()
+            og.step()
+            assert abs(lg.item() - l64[it]) < TOL * abs(l64[it]), (base, it)
+        worst = (0.0, '')
+        for n, p in m.named_parameters():
+            upd = p.detach().double().cpu().contiguous() - p0[n]
+            e_ours = relt(upd, d64[n])
+            e_ref = relt(d32[n], d64[n])
+            # fp32 kernels: like the float32 oracle; shipped policy: + the fp16 x fp16 weight gradient (<= 6e-4 per step)
+            bar = max(TOL if path == 'fp32' else 2 * TOL, 3 * e_ref)
+            worst = max(worst, (e_ours / bar, n))
+        results.append(worst)
+    print('worst update (error / bar) per batch seed:', results)
+    assert sorted(r for r, _ in results)[1] < 1.0, results
 
 
 def test_weight_file_roundtrip(tmp_path):
