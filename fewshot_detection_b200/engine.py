@@ -400,6 +400,10 @@ class NetRunner(object):
         not include a concurrent kernel's share of the SMs)."""
         if not WGRAD_STREAM or self.profile is not None:
             return False
+        if self.grad_hook is not None and os.environ.get('FSDET_WGRAD_STREAM') != '2':
+            # data-parallel runs launch their bucket collectives from the backward pass: keep one compute stream there
+            # (the overlap is worth ~0.6 % of a step; FSDET_WGRAD_STREAM=2 forces it for experiments)
+            return False
         if self.side is None:
             if torch.cuda.is_current_stream_capturing():
                 return False            # streams are created outside captures (the first eager step does it)
