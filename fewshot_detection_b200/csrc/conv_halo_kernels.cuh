@@ -64,11 +64,7 @@ struct HaloCfg {
     static constexpr int OFF_EPI = OFF_B + SB * BSTAGE;
     static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES + STAT_BYTES;
     static constexpr int SMEM_BYTES = OFF_BAR + 1024 + 256;
-    // accumulators of one set: [hi | lo_a | lo_b] where TMEM has the room (BN <= 64) - A_lo * B_hi then accumulates into its
-    // own block lo_b and does not depend on the wide MMA of the same K step (back-to-back tcgen05.mma into the same columns
-    // stall for the accumulate latency unless each is long) - else [hi | lo]
-    static constexpr bool SPLIT_LO = BN <= 64;
-    static constexpr int ACC_COLS = (SPLIT_LO ? 3 : 2) * BN;
+    static constexpr int ACC_COLS = 2 * BN;                        // hi + lo accumulators of one set
     static constexpr int TMEM_COLS = tmem_cols(2 * ACC_COLS);
     static_assert(SB >= 3, "weight ring too small");
     static_assert(!BRES || NKB * BSTAGE <= FREE_FOR_B, "resident weights do not fit");
@@ -199,7 +195,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
             tc_fence_after();
             const uint32_t dhi = tmem_base + a * (uint32_t)Cfg::ACC_COLS;
             const uint32_t dlo = dhi + (uint32_t)BN;
-            const uint32_t dlob = Cfg::SPLIT_LO ? dhi + 2u * (uint32_t)BN : dlo;     // where A_lo * B_hi accumulates
             uint32_t started = 0;
 #pragma unroll 1
             for (int chunk = 0; chunk < NCH; ++chunk, ++ita) {
@@ -233,11 +228,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
                                     // [D_hi | D_lo] (+)= A_hi * [B_hi | B_lo]: ONE MMA of width 2*BN (the lo block follows the hi block
                                     // in shared memory, the lo accumulator follows the hi accumulator in TMEM); D_lo += A_lo * B_hi
                                     umma_f16_lohi(dhi, ah + 2 * k, HI, bh + 2 * k, HI, idesc2, started);
-                                    umma_f16_lohi(dlob, al + 2 * k, HI, bh + 2 * k, HI, idesc, Cfg::SPLIT_LO ? started : 1u);
+                                    umma_f16_lohi(dlo, al + 2 * k, HI, bh + 2 * k, HI, idesc, 1u);
                                 } else {
                                     umma_f16_lohi(dhi, ah + 2 * k, HI, bh + 2 * k, HI, idesc, started);
-                                    umma_f16_lohi(dlob, al + 2 * k, HI, bh + 2 * k, HI, idesc, started);
-                                    umma_f16_lohi(dlo, ah + 2 * k, HI, bl + 2 * k, HI, idesc, Cfg::SPLIT_LO ? started : 1u);
+                                    umma_f16_lohi(dlo, al + 2 * k, HI, bh + 2 * k, HI, idesc, started);
+                                    umma_f16_lohi(dlo, ah + 2 * k, HI, bl + 2 * k, HI, idesc, 1u);
                                 }
                                 started = 1u;
                             }
@@ -290,15 +285,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constan
                     if (n0 < p.Cout) {                         // warp-uniform
                         float acc[32];
                         const uint32_t taddr = tmem_base + a * (uint32_t)Cfg::ACC_COLS + ((uint32_t)(quarter * 32) << 16) + ch * 32;
-                        if (Cfg::SPLIT_LO && !(p.flags & 8)) {
-                            float t2[32];
-                            epi_load_scaled<true>(taddr + BN, taddr + 2 * BN, 1.f, t2);      // lo_a + lo_b (small terms first)
-                            epi_load_scaled<false>(taddr, 0u, 1.f, acc);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) acc[j] = (t2[j] + acc[j]) * inv;
-                        } else {
-                            epi_load_scaled<true>(taddr, taddr + BN, inv, acc);
-                        }
+                        epi_load_scaled<true>(taddr, taddr + BN, inv, acc);
                         if (stores >= 1) {                     // the previous store must have read the staging block
                             if (leader) tma_store_wait_read<0>();
                             __syncwarp();

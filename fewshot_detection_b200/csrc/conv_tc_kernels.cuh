@@ -285,21 +285,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                     for (uint32_t k = 0; k < BK / 16; ++k) {       // 16 halves = 32 B along K inside the swizzle atom: + 2 in the descriptor
                         const uint32_t first_hi = (kb >= NH || k > 0) ? 1u : 0u;
                         const uint32_t first_lo = (kb > 0 || k > 0) ? 1u : 0u;
-                        if (fused && NP == 2 && nk > 1) {
-                            // Two pairs: A_lo * B_hi goes to the OTHER pair's lo accumulator, which this K step's wide MMA does
-                            // not touch - consecutive tcgen05.mma into the same TMEM columns run back to back only when each is
-                            // long enough to cover the accumulate latency (~100 clocks); a 128-column MMA is not.  The first
-                            // step of a pair must not clear the other pair's contributions already in its lo block: three MMAs.
-                            const uint32_t dother = acc + (uint32_t)(((kb + 1) % NP) * 2 * BN) + BN;
-                            if (kb < NP && k == 0) {
-                                umma_f16_lohi(dpair, ah, HI, bh, HI, idesc, 0u);
-                                umma_f16_lohi(dpair + BN, ah, HI, bl, HI, idesc, kb > 0 ? 1u : 0u);
-                                umma_f16_lohi(dother, al, HI, bh, HI, idesc, kb > 0 ? 1u : 0u);
-                            } else {
-                                umma_f16_lohi(dpair, ah + 2 * k, HI, bh + 2 * k, HI, idesc2, 1u);
-                                umma_f16_lohi(dother, al + 2 * k, HI, bh + 2 * k, HI, idesc, 1u);
-                            }
-                        } else if (fused) {
+                        if (fused) {
                             umma_f16_lohi(dpair, ah + 2 * k, HI, bh + 2 * k, HI, idesc2, (kb >= NP || k > 0) ? 1u : 0u);
                             umma_f16_lohi(dpair + BN, al + 2 * k, HI, bh + 2 * k, HI, idesc, 1u);
                         } else {
