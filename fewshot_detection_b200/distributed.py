@@ -58,8 +58,8 @@ class GradAllReducer(object):
         self.overlap = True   # launch bucket all-reduces from inside backward (False: one call in finish())
         self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         for r in (getattr(model, '_det', None), getattr(model, '_ler', None), getattr(model, '_net', None)):
-            if r is not None:
-                r.grad_hook = self.grad_ready
+            if r is not None:     # a single process has no collective to launch from the backward pass
+                r.grad_hook = self.grad_ready if self.world > 1 else None
 
     def begin_step(self):
         for b in self.buckets:
