@@ -58,9 +58,12 @@ __global__ void __launch_bounds__(1024) colsum_double_kernel(const float* __rest
 
 // reduction over the double-precision partial rows of the backward pass: columns [0, nsum) are summed (fixed
 // order), columns [nsum, ncols) hold maxima
+// `zero`: optional device float cleared here (the atomicMax target of the kernel that follows on the same stream - one graph
+// node less than a memset per layer)
 __global__ void __launch_bounds__(1024) colsum_dd_kernel(const double* __restrict__ part, int nparts, int ncols, int nsum,
-                                                         double* __restrict__ out) {
+                                                         double* __restrict__ out, float* __restrict__ zero) {
     __shared__ double red[32][33];
+    if (zero && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) *zero = 0.f;
     int col = blockIdx.x * 32 + threadIdx.x;
     const bool is_max = col >= nsum;
     double s = 0.0;
@@ -81,9 +84,10 @@ __global__ void __launch_bounds__(1024) colsum_dd_kernel(const double* __restric
 // Stage 1: grid (ceil(C/32), S): block (x, y) reduces rows [y*rps, (y+1)*rps) of the conv partial rows
 // [nparts][4C] = (sum | sum of squares | min | max) into red[y][4C] (doubles; sums accumulated in double).
 __global__ void __launch_bounds__(1024) bn_stats_reduce_kernel(const float* __restrict__ part, int nparts, int rps, int C,
-                                                               double* __restrict__ red) {
+                                                               double* __restrict__ red, float* __restrict__ zero) {
     __shared__ double rs[32][33], rq[32][33];
     __shared__ float rn[32][33], rx[32][33];
+    if (zero && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) *zero = 0.f;   // see colsum_dd_kernel
     const int c = blockIdx.x * 32 + threadIdx.x;
     const int r0 = blockIdx.y * rps;
     const int r1 = min(r0 + rps, nparts);
@@ -616,7 +620,7 @@ extern "C" int fsdet_bn_finalize(const float* stat_partial, int nparts, double c
     } else {
         FSDET_CHECK_ARG(running_mean && running_var, "bn_finalize: eval needs running stats");
     }
-    if (amax_y) {
+    if (amax_y && !training) {       // (training: cleared by the stage-1 kernel)
         cudaError_t e = cudaMemsetAsync(amax_y, 0, sizeof(float), s);
         if (e != cudaSuccess) { set_error("bn_finalize: memset: %s", cudaGetErrorString(e)); return (int)e; }
     }
@@ -630,7 +634,7 @@ extern "C" int fsdet_bn_finalize(const float* stat_partial, int nparts, double c
         S = ceil_div(nparts, rps);
         double* scratch = reinterpret_cast<double*>(const_cast<float*>(stat_partial) + (size_t)nparts * 4 * C);
         dim3 block(32, 32), grid(ceil_div(C, 32), S);
-        bn_stats_reduce_kernel<<<grid, block, 0, s>>>(stat_partial, nparts, rps, C, scratch);
+        bn_stats_reduce_kernel<<<grid, block, 0, s>>>(stat_partial, nparts, rps, C, scratch, amax_y);
         int st = launch_status("bn_finalize/reduce");
         if (st) return st;
         red = scratch;
@@ -718,13 +722,9 @@ extern "C" int fsdet_bn_bwd_finalize(const double* partial, int nparts, double c
     cudaStream_t s = (cudaStream_t)stream;
     double* sums = const_cast<double*>(partial) + (size_t)nparts * 3 * C;  // the extra row
     dim3 block(32, 32), grid(ceil_div(3 * C, 32));
-    colsum_dd_kernel<<<grid, block, 0, s>>>(partial, nparts, 3 * C, 2 * C, sums);
+    colsum_dd_kernel<<<grid, block, 0, s>>>(partial, nparts, 3 * C, 2 * C, sums, amax_bound);
     int st = launch_status("bn_bwd_finalize/colsum");
     if (st) return st;
-    if (amax_bound) {
-        cudaError_t e = cudaMemsetAsync(amax_bound, 0, sizeof(float), s);
-        if (e != cudaSuccess) { set_error("bn_bwd_finalize: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    }
     bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, s>>>(sums, count, gamma, invstd, xhat_absmax, dgamma, dbeta, coef, amax_bound, C, has_bn);
     return launch_status("bn_bwd_finalize");
 }
