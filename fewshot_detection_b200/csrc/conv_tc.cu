@@ -486,7 +486,9 @@ static TcPlan tc_plan(long long M, int Cin, int Cout, int ksize, int mode, int B
         pl.grid = (int)(total < kNumSMs ? total : kNumSMs);
         return pl;
     }
-    const bool small_k = (Cin % 64 != 0) || (ksize * ksize * Cin <= 2304);
+    // layers up to this K run the short-K flavour (64-byte rows, two CTAs per SM).  FSDET_TC_SMALLK_MAX: developer knob for A/B runs
+    static const int small_k_max = [] { const char* e = getenv("FSDET_TC_SMALLK_MAX"); return e ? atoi(e) : 2304; }();
+    const bool small_k = (Cin % 64 != 0) || (ksize * ksize * Cin <= small_k_max);
     pl.bn = Cout >= 128 ? 128 : 64;
     pl.bk = small_k ? 32 : 64;
     pl.nh = (!small_k && pl.terms == 3) ? NHI : 1;

@@ -33,14 +33,17 @@ def main():
     pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
     peak_tf, peak_gb = pk.get('bf16_tflops_sustained', 1441.5), pk.get('hbm_gbs', 6577.7)
     seq = [(short(r['Kernel Name']), float(r['Metric Value']) / 1e3) for r in rows]
+    # the halo-tile flavour (conv_halo_kernel) is a conv_tc dispatch: same role in the sequence
+    seq = [('conv_tc_kernel' if n == 'conv_halo_kernel' else n, t) for n, t in seq]
     firsts = [i for i, (n, _) in enumerate(seq) if n == 'conv_first_fwd_kernel']
-    start = firsts[-1]                       # the detector's first layer of the last captured step (support runs before it)
+    # the detector's first layer of the last COMPLETELY captured step (the support net runs before it)
+    start = [f for f in firsts if sum(1 for n, _ in seq[f:] if n in ('conv_tc_kernel', 'wgrad_tc_kernel')) >= 66][-1]
     tc = [(i, n, t) for i, (n, t) in enumerate(seq) if i > start and n in ('conv_tc_kernel', 'wgrad_tc_kernel')]
     fwd = tc[:22]
     assert all(n == 'conv_tc_kernel' for _, n, _ in fwd)
     bwd = tc[22:22 + 44]
     assert [n for _, n, _ in bwd] == ['wgrad_tc_kernel', 'conv_tc_kernel'] * 22, 'unexpected backward launch order'
-    print('# Round 1 - the detector\'s tensor-core convolutions layer by layer (from profiles/launches_r01.csv)\n')
+    print('# The detector\'s tensor-core convolutions layer by layer (from %s)\n' % os.path.relpath(sys.argv[1], ROOT))
     print(__doc__.split('Usage')[0].strip() + '\n')
     print('Ceiling %.0f TFLOP/s (= %.1f / 3), HBM peak %.1f GB/s.\n' % (peak_tf / 3, peak_tf, peak_gb))
     print('| layer | Cin→Cout k @H | GFLOP | fwd us | TF/s | dgrad us | TF/s | wgrad us | TF/s | HBM floor us (fwd) | fwd bound |')
@@ -64,9 +67,8 @@ def main():
         tot[0], tot[1], tot[0] / (tot[1] * 1e-6) / 1e3, tot[2], tot[0] / (tot[2] * 1e-6) / 1e3, tot[3], tot[0] / (tot[3] * 1e-6) / 1e3))
     l2 = [fwd[0][2], bwd[43][2], bwd[42][2]]
     print('\nconv2 alone (32→64 channels at 208x208) takes %.2f ms of the step (forward %.0f + dgrad %.0f + wgrad %.0f us) for %.0f %% of '
-          'these FLOPs: it is HBM/launch bound (one 128-pixel tile per CTA, %d CTAs), the first candidate for a persistent tile loop.'
-          % (sum(l2) / 1e3, l2[0], l2[1], l2[2], 100 * 2.0 * B * 208 * 208 * 32 * 64 * 9 / 1e9 / tot[0], B * 208 * 208 // 128))
-
+          'these FLOPs (round 1: 2.77 ms; Cout = 64 means two ~100-clock MMAs per 96 clocks of tensor work, DESIGN.md section 3).'
+          % (sum(l2) / 1e3, l2[0], l2[1], l2[2], 100 * 2.0 * B * 208 * 208 * 32 * 64 * 9 / 1e9 / tot[0]))
 
 if __name__ == '__main__':
     main()

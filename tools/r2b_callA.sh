@@ -13,3 +13,8 @@ ls -la gpurun_out/bA_full*; rm -f gpurun_out/bA_full.ncu-rep
 FSDET_BENCH_NO_EXTRAS=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bA_bench.json 2> gpurun_out/bA_bench.err
 echo "bench rc=$?"; python -c "
 import json; d=json.loads(open('gpurun_out/bA_bench.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], {k: round(v['ms_per_step'],3) for k,v in d['roofline']['kernels'].items()}, d['gpu_launches'])"
+for cfg in "FSDET_TC_SMALLK_MAX=2303" "FSDET_TC_SMALLK_MAX=1151"; do
+  env $cfg FSDET_BENCH_NO_EXTRAS=1 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bA_bench2.json 2> gpurun_out/bA_bench2.err
+  echo "bench [$cfg] rc=$?"; python -c "
+import json; d=json.loads(open('gpurun_out/bA_bench2.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], {k: round(v['ms_per_step'],3) for k,v in d['roofline']['kernels'].items()})"
+done
