@@ -532,11 +532,20 @@ def main():
             rb = [tuple(t.to(dev) for t in b[:3]) + (b[3],) for b in hb]       # labels stay on the host (neg_filter)
             cfg.neg_ratio = neg
             fn = (lambda i: step(*rb[i % 2])) if graph else (lambda i: eager_step(*rb[i % 2]))
-            for i in range(3):
+            for i in range(4):      # first call of a new regime = graph capture; then three replays
                 fn(i)
-            m_ = timed(fn, nsteps)
+            # every step between its own pair of events as well: a one-off stall (allocator, first replay) shows as max >> min
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+
+            def fn_ev(i):
+                evs[i][0].record()
+                fn(i)
+                evs[i][1].record()
+            m_ = timed(fn_ev, nsteps)
+            per = [a.elapsed_time(b) for a, b in evs]
             v = Bq * world * nsteps / (m_ / 1e3)
             extras[tag] = {'value': v, 'unit': 'images/s', 'ms_per_step': m_ / nsteps, 'steps': nsteps,
+                           'ms_per_step_min_max': [min(per), max(per)],
                            'config': {'batch_per_gpu': Bq, 'n_cls': nc, 'side': sd, 'neg': str(neg),
                                       'launch': 'cuda-graph replay' if graph else 'eager'},
                            'roofline_whole_step': whole_step(Bq, nc, sd, m_ / nsteps)}
