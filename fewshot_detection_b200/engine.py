@@ -658,7 +658,7 @@ class NetRunner(object):
             assert cout_p == s.cout, 'BatchNorm conv with Cout % 4 != 0 is unsupported'
             z = Act.new(B, H, W, s.cout, dev)
             use_batch_stats = training or not bn.track_running_stats
-            rows_cap = max(_lib.lib.fsdet_conv_stat_rows(npix), _lib.lib.fsdet_colstats_rows(npix), (npix + 127) // 128 + 1, 2 * 148)
+            rows_cap = max(_lib.lib.fsdet_conv_stat_rows(npix), _lib.lib.fsdet_colstats_rows(npix), (npix + 127) // 128 + 1, 3 * 148)
             stat = _empty(rows_cap + _lib.lib.fsdet_bn_stat_scratch_rows(), 4 * s.cout, device=dev) if use_batch_stats else None
             wp = getattr(self, '_wp', {}).get(id(wuse))
             rows = self._conv('fwd', x, wuse, None, z, stat, cin_p, s.cout, s.k, 0, st, wplanes=wp['fwd'] if wp else None)
