@@ -9,8 +9,6 @@
 //
 // Tiles: 128 pixels x BN channels x 16 k, 256 threads, 8 x TN register tile,
 // double-buffered shared memory with register prefetch.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace fsdet {
@@ -491,8 +489,9 @@ template <bool PK> __device__ __forceinline__ Px4<PK> lds_px(const float4* p) {
 // STATS: the BatchNorm partial row of this CTA (sum | sum of squares | min | max per channel, the layout
 // fsdet_bn_finalize reads) is taken from the values while they are in registers - a thread owns ONE output channel, so
 // there is nothing to transpose - instead of a separate pass over the 1.4 GB tensor (fsdet_colstats).
-template <bool PK, bool STATS, int MINB>
-__global__ void __launch_bounds__(256, MINB) conv_first_fwd_kernel(const float* __restrict__ in0, int C0, const float* __restrict__ in1,
+// (two CTAs per SM at 122 registers; three at 80 registers measured slower: 1.12 vs 1.02 ms per step, tools/r2b_callE.sh)
+template <bool PK, bool STATS>
+__global__ void __launch_bounds__(256, 2) conv_first_fwd_kernel(const float* __restrict__ in0, int C0, const float* __restrict__ in1,
                                                                 int C1, const float* __restrict__ w /* [Cout][9][4] */,
                                                                 float* __restrict__ z, int ldz, int B, int H, int W, int Cout,
                                                                 float* __restrict__ stats) {
@@ -875,21 +874,13 @@ extern "C" int fsdet_conv_first_fwd(const float* in0, int C0, const float* in1, 
     FSDET_CHECK_ARG(tiles < (1ll << 31), "conv_first_fwd: too many tiles");
     const unsigned ctas = (unsigned)(tiles < 2LL * kNumSMs ? tiles : 2LL * kNumSMs);
     // packed FFMA2 flavour: fewer issue slots per pixel (measured 705 us vs 750 us at B=64, 416x416)
-    conv_first_fwd_kernel<true, false, 2><<<ctas, 256, 0, (cudaStream_t)stream>>>(in0, C0, in1, C1, w_pad4, z, ldz, B, H, W, Cout, nullptr);
+    conv_first_fwd_kernel<true, false><<<ctas, 256, 0, (cudaStream_t)stream>>>(in0, C0, in1, C1, w_pad4, z, ldz, B, H, W, Cout, nullptr);
     return launch_status("conv_first_fwd");
-}
-
-// resident CTAs per SM of the statistics flavour: 2 (122 registers) or 3 (80 registers, 24 warps per SM: the kernel is
-// latency-bound - ncu: issue slots 50 % busy at 16 warps per SM).  FSDET_FIRST_MINB: developer knob for A/B runs
-static int first_minb() {
-    static const int v = [] { const char* e = getenv("FSDET_FIRST_MINB"); return (e && atoi(e) == 3) ? 3 : 2; }();
-    return v;
 }
 
 extern "C" int fsdet_conv_first_stat_rows(int B, int H, int W) {
     long long tiles = (long long)B * ceil_div(H, FT_H) * ceil_div(W, FT_W);
-    const long long cap = (long long)first_minb() * kNumSMs;
-    return (int)(tiles < cap ? tiles : cap);
+    return (int)(tiles < 2LL * kNumSMs ? tiles : 2LL * kNumSMs);
 }
 
 extern "C" int fsdet_conv_first_fwd_stats(const float* in0, int C0, const float* in1, int C1, const float* w_pad4, float* z, int ldz,
@@ -902,12 +893,8 @@ extern "C" int fsdet_conv_first_fwd_stats(const float* in0, int C0, const float*
     if (tiles == 0) return 0;
     FSDET_CHECK_ARG(tiles < (1ll << 31), "conv_first_fwd_stats: too many tiles");
     const unsigned ctas = (unsigned)fsdet_conv_first_stat_rows(B, H, W);
-    if (first_minb() == 3)
-        conv_first_fwd_kernel<true, true, 3><<<ctas, 256, 0, (cudaStream_t)stream>>>(in0, C0, in1, C1, w_pad4, z, ldz, B, H, W, Cout,
-                                                                                     stat_partial);
-    else
-        conv_first_fwd_kernel<true, true, 2><<<ctas, 256, 0, (cudaStream_t)stream>>>(in0, C0, in1, C1, w_pad4, z, ldz, B, H, W, Cout,
-                                                                                     stat_partial);
+    conv_first_fwd_kernel<true, true><<<ctas, 256, 0, (cudaStream_t)stream>>>(in0, C0, in1, C1, w_pad4, z, ldz, B, H, W, Cout,
+                                                                              stat_partial);
     return launch_status("conv_first_fwd_stats");
 }
 
