@@ -910,11 +910,10 @@ extern "C" int fsdet_conv_first_wgrad(const float* in0, int C0, const float* in1
     const size_t smem = ((size_t)FW_SLOTS * (W + 2) * 4 + (size_t)2 * W * 32) * sizeof(float);
     FSDET_CHECK_ARG(smem <= 227 * 1024, "conv_first_wgrad: image width %d too large", W);
     cudaStream_t s = (cudaStream_t)stream;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_first_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {   // the opt-in ceiling (227 KB), per launch like every other kernel of the library: no cached state, and never lowered under
+        // a graph that was captured at a wider image
+        cudaError_t e = cudaFuncSetAttribute(conv_first_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("conv_first_wgrad: %s", cudaGetErrorString(e)); return (int)e; }
-        smem_set = smem;
     }
     // scalar FFMA flavour (the packed one is register-bandwidth bound here: 900 us vs 873 us)
     conv_first_wgrad_kernel<false><<<ctas, FW_THREADS, smem, s>>>(in0, C0, in1, C1, dz, lddz, workspace, B, H, W, Cout);
